@@ -1,0 +1,135 @@
+/*
+ * nam_b200.h -- C ABI of libnam_b200.so: NeuralAmpModelerCore's inference hot path on B200.
+ *
+ * The reference has no FFI of its own (it is a C++ static library); these entry points are what
+ * a binding of its public surface for this path needs, one for one:
+ *
+ *   nam_b200_create_from_file   <->  nam::get_dsp(std::filesystem::path, DspLoadOptions)   NAM/get_dsp.h:85-90
+ *   nam_b200_create_from_json   <->  nam::get_dsp(const nlohmann::json&, ...)              NAM/get_dsp.h:108-116
+ *   nam_b200_reset              <->  nam::DSP::Reset(sampleRate, maxBufferSize) + prewarm  NAM/dsp.h:165, NAM/dsp.cpp:67-101,130-140
+ *   nam_b200_process_f64_planar <->  nam::DSP::process(NAM_SAMPLE**, NAM_SAMPLE**, int)    NAM/dsp.h:97 (NAM_SAMPLE = double)
+ *   nam_b200_process_f32_planar <->  same with -DNAM_SAMPLE_FLOAT                          NAM/dsp.h:18-22
+ *   nam_b200_process_f32        <->  the batched reframing: `batch` independent streams per call
+ *                                    (each stream == one nam::DSP instance of the reference)
+ *   nam_b200_get_info           <->  NumInputChannels/NumOutputChannels/GetExpectedSampleRate/
+ *                                    GetPrewarmSamples/Has*,Get* level & loudness          NAM/dsp.h:100-231
+ *   nam_b200_set_fast_tanh      <->  nam::activations::Activation::enable/disable_fast_tanh NAM/activations.h:163-164
+ *   nam_b200_last_error         <->  the what() of the exception the reference would throw
+ *   nam_b200_destroy            <->  ~unique_ptr<nam::DSP>
+ *
+ * Conventions: every function returns 0 on success or a negative nam_b200_status; nothing
+ * throws across this boundary; pointers are plain host pointers unless the name says _device.
+ * A handle owns device weights, per-stream state and staging buffers; the caller owns audio
+ * buffers.  process_* calls on one handle are not re-entrant (same as nam::DSP::process).
+ * There is NO CPU fallback: if no CUDA device is usable, create fails with NAM_B200_ERR_CUDA.
+ */
+#ifndef NAM_B200_H
+#define NAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAM_B200_ABI_VERSION 1
+
+typedef struct nam_b200_model nam_b200_model;
+
+typedef enum nam_b200_status
+{
+  NAM_B200_OK = 0,
+  NAM_B200_ERR_INVALID_ARGUMENT = -1,
+  NAM_B200_ERR_FILE = -2, /* nam::NamFileValidationError */
+  NAM_B200_ERR_MODEL = -3, /* std::runtime_error / std::invalid_argument while parsing or building */
+  NAM_B200_ERR_UNSUPPORTED = -4, /* valid .nam, but an option the CUDA path does not implement yet */
+  NAM_B200_ERR_CUDA = -5, /* CUDA runtime failure (message carries cudaGetErrorString) */
+  NAM_B200_ERR_STATE = -6 /* call sequence error, e.g. process before reset */
+} nam_b200_status;
+
+typedef struct nam_b200_options
+{
+  int32_t struct_size; /* sizeof(nam_b200_options), for forward compatibility */
+  int32_t device; /* CUDA device ordinal, -1 = current device */
+  int32_t max_batch; /* number of independent streams this handle carries state for (>= 1) */
+  int32_t fast_tanh; /* 1 = Activation::enable_fast_tanh() was called before loading (benchmodel default) */
+  int32_t prewarm_on_reset; /* 1 (reference default) = reset() prewarms; 0 = SetPrewarmOnReset(false) */
+  int32_t ctas_per_sm; /* 0 = library default; tuning knob for the persistent WaveNet kernel */
+  int32_t reserved[8];
+} nam_b200_options;
+
+typedef struct nam_b200_info
+{
+  int32_t struct_size;
+  int32_t architecture; /* 1 WaveNet, 2 LSTM, 3 Linear */
+  int32_t in_channels, out_channels;
+  int32_t prewarm_samples; /* DSP::GetPrewarmSamples() */
+  int32_t max_batch, max_frames; /* max_frames = maxBufferSize of the last reset (0 before) */
+  int32_t has_loudness, has_input_level, has_output_level;
+  double expected_sample_rate; /* -1 when unknown */
+  double loudness, input_level_dbu, output_level_dbu;
+  int64_t n_weights;
+  int64_t state_bytes_per_stream; /* device bytes of per-stream history */
+  double flops_per_frame; /* algorithmic FLOPs (2 x MACs) per frame per stream */
+  int32_t kernel_variant; /* which CUDA specialisation serves this model (diagnostic) */
+  int32_t reserved[7];
+} nam_b200_info;
+
+/* Fill with defaults: device -1, max_batch 1, fast_tanh 0, prewarm_on_reset 1. */
+void nam_b200_default_options(nam_b200_options* opts);
+
+int nam_b200_abi_version(void);
+
+int nam_b200_create_from_file(const char* nam_path, const nam_b200_options* opts, nam_b200_model** out);
+int nam_b200_create_from_json(const char* nam_json_text, const nam_b200_options* opts, nam_b200_model** out);
+void nam_b200_destroy(nam_b200_model* m);
+
+int nam_b200_get_info(const nam_b200_model* m, nam_b200_info* info);
+
+/* DSP::Reset: (re)allocate for calls of up to max_frames frames, zero every stream's history, then
+ * (unless prewarm_on_reset == 0) prewarm exactly like DSP::prewarm(): zeros in max_frames-sized blocks
+ * until >= prewarm_samples were fed.  All max_batch streams end up in the identical prewarmed state. */
+int nam_b200_reset(nam_b200_model* m, double sample_rate, int max_frames);
+
+/* DSP::prewarm() on its own (after a reset with prewarm_on_reset == 0). */
+int nam_b200_prewarm(nam_b200_model* m);
+
+/* Batched throughput entry: `batch` (<= max_batch) mono streams, stream b reads
+ * in[b*in_stride .. +n_frames) and writes out[b*out_stride .. +n_frames); n_frames <= max_frames.
+ * Host pointers; copies ride the handle's stream; returns after the result is in `out`. */
+int nam_b200_process_f32(nam_b200_model* m, const float* in, float* out, int batch, int n_frames, int64_t in_stride,
+                         int64_t out_stride);
+
+/* Same, device pointers, asynchronous on `cuda_stream` (a cudaStream_t, may be NULL = handle's stream).
+ * No copies, no synchronisation. */
+int nam_b200_process_f32_device(nam_b200_model* m, const float* in_device, float* out_device, int batch, int n_frames,
+                                int64_t in_stride, int64_t out_stride, void* cuda_stream);
+
+/* nam::DSP::process for stream 0 of the handle: planar input[channel][frame]. */
+int nam_b200_process_f64_planar(nam_b200_model* m, const double* const* input, double* const* output, int n_frames);
+int nam_b200_process_f32_planar(nam_b200_model* m, const float* const* input, float* const* output, int n_frames);
+
+/* LSTM reads the fast-tanh switch at run time (NAM/lstm.cpp:48); WaveNet captured it at load. */
+int nam_b200_set_fast_tanh(nam_b200_model* m, int enabled);
+
+/* Block until all work queued on the handle's stream has finished. */
+int nam_b200_synchronize(nam_b200_model* m);
+
+/* Number of kernels this handle has launched since creation (diagnostic, used by bench.py). */
+int64_t nam_b200_launch_count(const nam_b200_model* m);
+
+/* Device time of the most recent process_* / reset call's kernels in milliseconds (CUDA events on the
+ * handle's stream); negative if unavailable. */
+double nam_b200_last_kernel_ms(nam_b200_model* m);
+
+/* Thread-local message of the last failing call on this thread. */
+const char* nam_b200_last_error(void);
+
+/* Measured FP32 FMA issue rate of the device (packed FFMA2 micro-benchmark), in TFLOP/s.  Used by
+ * bench.py as the compute roofline for the fused kernel. Returns < 0 on error. */
+double nam_b200_measure_fp32_tflops(int device, int use_ffma2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAM_B200_H */

@@ -1,0 +1,1083 @@
+// nam_b200.cu -- C ABI of libnam_b200.so (include/nam_b200.h): model handles, device state,
+// kernel launches.  Host code is C++; every hot-path operation is a hand-written sm_100a kernel
+// (wavenet_fused.cuh, and the LSTM / Linear kernels below).  There is deliberately no CPU
+// fallback anywhere in this file.
+#include "../../include/nam_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "nam_model_spec.h"
+#include "wavenet_fused.cuh"
+#include "wavenet_pack.h"
+
+using namespace namb200;
+
+// =================================================================================================
+// error plumbing
+// =================================================================================================
+namespace
+{
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg)
+{
+  g_last_error = msg;
+  return code;
+}
+
+struct CudaError : public std::runtime_error
+{
+  using std::runtime_error::runtime_error;
+};
+
+#define CUDA_CHECK(expr)                                                                                             \
+  do                                                                                                                 \
+  {                                                                                                                  \
+    cudaError_t _e = (expr);                                                                                         \
+    if (_e != cudaSuccess)                                                                                           \
+      throw CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e));                                    \
+  } while (0)
+
+// =================================================================================================
+// LSTM kernel  (NAM/lstm.cpp:31-68 cell, :103-168 process)
+//
+// One THREAD per stream (the recurrence forbids parallelism over time, batch is the only
+// parallel axis); the (W, b, head) parameters of all layers sit in shared memory and are read
+// with warp-uniform broadcasts; each thread's (h, c) state lives in shared memory in
+// [index][thread] order (conflict-free), is loaded from / stored to the per-stream state in
+// global memory at launch boundaries.  Input/output frames are staged through shared memory
+// in [32 streams x TC frames] tiles so global traffic is coalesced although each thread walks
+// its own stream.
+// =================================================================================================
+struct LstmKernelParams
+{
+  const float* __restrict__ weights; // per layer: W[4H][I+H] | b[4H] ; then head_w[H] | head_b
+  int n_weight_floats;
+  float* __restrict__ state; // [batch][state_stride]: per layer h[H] | c[H]
+  int state_stride;
+  const float* __restrict__ in;
+  float* __restrict__ out;
+  long in_stride, out_stride;
+  int batch, n_frames;
+  int num_layers, input_size, hidden;
+  int fast_tanh;
+};
+
+constexpr int kLstmThreads = 64; // streams per CTA
+constexpr int kLstmChunk = 32; // frames staged per tile
+
+__device__ __forceinline__ float lstm_sigmoid(float x, int fast)
+{
+  // fast regime: fast_sigmoid(x) = 0.5*(fast_tanh(x/2)+1)  (activations.h:100-103)
+  return fast ? 0.5f * (act_fast_tanh(x * 0.5f) + 1.0f) : act_sigmoid(x);
+}
+__device__ __forceinline__ float lstm_tanh(float x, int fast)
+{
+  return fast ? act_fast_tanh(x) : tanhf(x);
+}
+
+__global__ void __launch_bounds__(kLstmThreads) lstm_kernel(const LstmKernelParams p)
+{
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x;
+  const int H = p.hidden;
+  float* sw = smem; // weights
+  float* sstate = sw + ((p.n_weight_floats + 3) & ~3); // [num_layers*2*H][kLstmThreads]
+  float* sgate = sstate + p.num_layers * 2 * H * kLstmThreads; // [4H][kLstmThreads] scratch
+  float* sio = sgate + 4 * H * kLstmThreads; // [kLstmThreads][kLstmChunk+1] in, then same for out
+  float* sout = sio + kLstmThreads * (kLstmChunk + 1);
+
+  for (int i = tid; i < p.n_weight_floats; i += kLstmThreads)
+    sw[i] = __ldg(p.weights + i);
+  const int stream = blockIdx.x * kLstmThreads + tid;
+  const bool active = stream < p.batch;
+  const int n_state = p.num_layers * 2 * H;
+  if (active)
+    for (int i = 0; i < n_state; i++)
+      sstate[i * kLstmThreads + tid] = p.state[(size_t)stream * p.state_stride + i];
+  __syncthreads();
+
+  const int stream0 = blockIdx.x * kLstmThreads;
+  for (int t0 = 0; t0 < p.n_frames; t0 += kLstmChunk)
+  {
+    const int tc = min(kLstmChunk, p.n_frames - t0);
+    // coalesced load of the [streams x tc] input tile
+    for (int idx = tid; idx < kLstmThreads * kLstmChunk; idx += kLstmThreads)
+    {
+      const int s = idx / kLstmChunk, f = idx - s * kLstmChunk;
+      float v = 0.0f;
+      if (stream0 + s < p.batch && f < tc)
+        v = __ldg(p.in + (size_t)(stream0 + s) * p.in_stride + t0 + f);
+      sio[s * (kLstmChunk + 1) + f] = v;
+    }
+    __syncthreads();
+    if (active)
+    {
+      for (int f = 0; f < tc; f++)
+      {
+        float x_scalar = sio[tid * (kLstmChunk + 1) + f];
+        const float* w = sw;
+        for (int l = 0; l < p.num_layers; l++)
+        {
+          const int I = (l == 0) ? p.input_size : H;
+          const int W = I + H;
+          float* hs = sstate + (l * 2) * H * kLstmThreads;
+          float* cs = hs + H * kLstmThreads;
+          const float* xprev = (l == 0) ? nullptr : sstate + ((l - 1) * 2) * H * kLstmThreads;
+          const float* b = w + 4 * H * W;
+          // ifgo = W [x ; h] + b   (lstm.cpp:36-40); rows ordered i, f, g, o
+          for (int r = 0; r < 4 * H; r++)
+          {
+            const float* wr = w + r * W;
+            float acc = 0.0f;
+            if (l == 0)
+              acc = fmaf(wr[0], x_scalar, acc); // input_size == 1 on this path
+            else
+              for (int j = 0; j < I; j++)
+                acc = fmaf(wr[j], xprev[j * kLstmThreads + tid], acc);
+            for (int j = 0; j < H; j++)
+              acc = fmaf(wr[I + j], hs[j * kLstmThreads + tid], acc);
+            sgate[r * kLstmThreads + tid] = acc + b[r];
+          }
+          for (int i = 0; i < H; i++)
+          {
+            const float gi = sgate[(i)*kLstmThreads + tid];
+            const float gf = sgate[(H + i) * kLstmThreads + tid];
+            const float gg = sgate[(2 * H + i) * kLstmThreads + tid];
+            const float go = sgate[(3 * H + i) * kLstmThreads + tid];
+            const float c = lstm_sigmoid(gf, p.fast_tanh) * cs[i * kLstmThreads + tid]
+                            + lstm_sigmoid(gi, p.fast_tanh) * lstm_tanh(gg, p.fast_tanh); // lstm.cpp:50-53,61-63
+            cs[i * kLstmThreads + tid] = c;
+            hs[i * kLstmThreads + tid] = lstm_sigmoid(go, p.fast_tanh) * lstm_tanh(c, p.fast_tanh); // :55-57,65-66
+          }
+          w = b + 4 * H;
+        }
+        // head (lstm.cpp:164-167)
+        const float* hl = sstate + ((p.num_layers - 1) * 2) * H * kLstmThreads;
+        float y = 0.0f;
+        for (int j = 0; j < H; j++)
+          y = fmaf(w[j], hl[j * kLstmThreads + tid], y);
+        sout[tid * (kLstmChunk + 1) + f] = y + w[H];
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < kLstmThreads * kLstmChunk; idx += kLstmThreads)
+    {
+      const int s = idx / kLstmChunk, f = idx - s * kLstmChunk;
+      if (stream0 + s < p.batch && f < tc)
+        p.out[(size_t)(stream0 + s) * p.out_stride + t0 + f] = sout[s * (kLstmChunk + 1) + f];
+    }
+    __syncthreads();
+  }
+  if (active)
+    for (int i = 0; i < n_state; i++)
+      p.state[(size_t)stream * p.state_stride + i] = sstate[i * kLstmThreads + tid];
+}
+
+// =================================================================================================
+// Linear (FIR) kernel, direct form (NAM/linear.cpp:168-199): y[t] = bias + sum_j w[j] x[t-j]
+// One CTA per (stream, tile of frames); the tile plus RF-1 history samples are staged in shared
+// memory; the per-stream history (last RF-1 samples) persists in global state.
+// =================================================================================================
+struct LinearKernelParams
+{
+  const float* __restrict__ impulse; // impulse[j] multiplies x[t-j]
+  int rf;
+  float bias;
+  float* __restrict__ state; // [batch][state_stride]: last (rf-1) samples, oldest first
+  int state_stride;
+  const float* __restrict__ in;
+  float* __restrict__ out;
+  long in_stride, out_stride;
+  int batch, n_frames;
+};
+
+constexpr int kLinThreads = 256;
+
+__global__ void __launch_bounds__(kLinThreads) linear_kernel(const LinearKernelParams p)
+{
+  extern __shared__ float smem[];
+  const int hist = p.rf - 1;
+  float* sw = smem; // rf
+  float* sx = smem + ((p.rf + 3) & ~3); // hist + kLinThreads
+  const int stream = blockIdx.y;
+  const int t0 = blockIdx.x * kLinThreads;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < p.rf; i += kLinThreads)
+    sw[i] = __ldg(p.impulse + i);
+  const float* xin = p.in + (size_t)stream * p.in_stride;
+  const float* st = p.state + (size_t)stream * p.state_stride;
+  for (int i = tid; i < hist + kLinThreads; i += kLinThreads)
+  {
+    const int t = t0 - hist + i; // frame index relative to this call
+    float v = 0.0f;
+    if (t >= 0)
+      v = (t < p.n_frames) ? __ldg(xin + t) : 0.0f;
+    else
+      v = st[hist + t]; // t in [-hist, 0): state holds frames -hist..-1
+    sx[i] = v;
+  }
+  __syncthreads();
+  const int t = t0 + tid;
+  if (t < p.n_frames)
+  {
+    // oldest tap first, like the reference's dot over the reversed impulse (linear.cpp:71-74,184-186)
+    float acc = 0.0f;
+    for (int j = hist; j >= 0; j--)
+      acc = fmaf(sw[j], sx[hist + tid - j], acc);
+    p.out[(size_t)stream * p.out_stride + t] = p.bias + acc;
+  }
+}
+
+// new_state = last (rf-1) samples of [old_state | in[0:n)]
+__global__ void linear_update_state_kernel(const LinearKernelParams p, float* __restrict__ new_state)
+{
+  const int hist = p.rf - 1;
+  const int stream = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hist)
+    return;
+  const int t = p.n_frames - hist + i; // relative frame index of new history slot i
+  float v;
+  if (t >= 0)
+    v = p.in[(size_t)stream * p.in_stride + t];
+  else
+    v = p.state[(size_t)stream * p.state_stride + hist + t];
+  new_state[(size_t)stream * p.state_stride + i] = v;
+}
+
+// =================================================================================================
+// misc kernels
+// =================================================================================================
+// Copy stream 0's state to streams [1, batch) (all streams are identical after prewarm).
+__global__ void broadcast_state_kernel(float* __restrict__ state, long stride_floats, int batch)
+{
+  const long n4 = stride_floats / 4;
+  const float4* src = reinterpret_cast<const float4*>(state);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x)
+  {
+    const float4 v = src[i];
+    for (int b = 1 + blockIdx.y; b < batch; b += gridDim.y)
+      reinterpret_cast<float4*>(state + (size_t)b * stride_floats)[i] = v;
+  }
+}
+
+// FP32 FMA issue-rate micro-benchmark: 8 independent accumulator pairs per thread.
+template <bool PACKED>
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float seed)
+{
+  float2 a[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    a[i] = make_float2(seed + i, seed - i);
+  const float2 m = make_float2(1.0000001f, 0.9999999f);
+  const float2 c = make_float2(1e-7f, -1e-7f);
+  for (int it = 0; it < iters; it++)
+  {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+      if (PACKED)
+        a[i] = __ffma2_rn(a[i], m, c);
+      else
+      {
+        a[i].x = fmaf(a[i].x, m.x, c.x);
+        a[i].y = fmaf(a[i].y, m.y, c.y);
+      }
+    }
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    s += a[i].x + a[i].y;
+  if (s == 12345.678f)
+    out[0] = s;
+}
+
+} // namespace
+
+// =================================================================================================
+// the handle
+// =================================================================================================
+struct nam_b200_model
+{
+  ModelSpec spec;
+  nam_b200_options opts{};
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timing_valid = false;
+  int64_t launches = 0;
+  int max_frames = 0;
+  bool is_reset = false;
+  uint32_t t_base = 0;
+  int fast_tanh_runtime = 0;
+
+  // WaveNet
+  WaveNetPlan plan;
+  int variant = 0;
+  int wn_ctas_per_sm = 0; // resident CTAs per SM of the fused kernel (occupancy query, cached)
+  // LSTM / Linear packed weights
+  std::vector<float> host_weights;
+  float* d_weights = nullptr;
+  size_t n_weight_floats = 0;
+  // per-stream state
+  float* d_state = nullptr;
+  float* d_state_tmp = nullptr; // Linear double buffer
+  long state_stride = 0; // floats
+  // staging
+  float* d_in = nullptr;
+  float* d_out = nullptr;
+  size_t staging_floats = 0;
+  float* h_pin = nullptr; // pinned scratch for the planar (single stream) entry points
+  size_t h_pin_floats = 0;
+  double flops_per_frame = 0.0;
+
+  ~nam_b200_model()
+  {
+    cudaSetDevice(device);
+    if (d_weights)
+      cudaFree(d_weights);
+    if (d_state)
+      cudaFree(d_state);
+    if (d_state_tmp)
+      cudaFree(d_state_tmp);
+    if (d_in)
+      cudaFree(d_in);
+    if (d_out)
+      cudaFree(d_out);
+    if (h_pin)
+      cudaFreeHost(h_pin);
+    if (ev0)
+      cudaEventDestroy(ev0);
+    if (ev1)
+      cudaEventDestroy(ev1);
+    if (stream)
+      cudaStreamDestroy(stream);
+  }
+};
+
+namespace
+{
+
+// ---- WaveNet launch dispatch -----------------------------------------------------------------
+constexpr int kWnS = 2; // time steps per thread
+constexpr int kWnNT = 128; // threads per CTA
+
+template <int C0, int C1>
+void launch_wavenet_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem, cudaStream_t st)
+{
+  auto kern = wavenet_fused_kernel<C0, C1, kWnS, kWnNT>;
+  static bool configured[64] = {false};
+  if (!configured[m->device & 63])
+  {
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[m->device & 63] = true;
+  }
+  kern<<<grid, kWnNT, smem, st>>>(kp);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+template <int C0, int C1>
+int occupancy_wavenet_variant(size_t smem)
+{
+  auto kern = wavenet_fused_kernel<C0, C1, kWnS, kWnNT>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kWnNT, smem) != cudaSuccess)
+    return 1;
+  return n > 0 ? n : 1;
+}
+
+#define WN_DISPATCH(FN, ...)                                                                                         \
+  switch (c0 * 100 + c1)                                                                                             \
+  {                                                                                                                  \
+    case 400: return FN<4, 0>(__VA_ARGS__);                                                                          \
+    case 800: return FN<8, 0>(__VA_ARGS__);                                                                          \
+    case 1600: return FN<16, 0>(__VA_ARGS__);                                                                        \
+    case 404: return FN<4, 4>(__VA_ARGS__);                                                                          \
+    case 408: return FN<4, 8>(__VA_ARGS__);                                                                          \
+    case 804: return FN<8, 4>(__VA_ARGS__);                                                                          \
+    case 808: return FN<8, 8>(__VA_ARGS__);                                                                          \
+    case 1604: return FN<16, 4>(__VA_ARGS__);                                                                        \
+    case 1608: return FN<16, 8>(__VA_ARGS__);                                                                        \
+    case 1616: return FN<16, 16>(__VA_ARGS__);                                                                       \
+    default: throw std::runtime_error("no fused WaveNet kernel for channel pair " + std::to_string(c0) + "/"         \
+                                      + std::to_string(c1));                                                         \
+  }
+
+void launch_wavenet_dispatch(int c0, int c1, nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem,
+                             cudaStream_t st)
+{
+  WN_DISPATCH(launch_wavenet_variant, m, kp, grid, smem, st)
+}
+int occupancy_wavenet_dispatch(int c0, int c1, size_t smem)
+{
+  WN_DISPATCH(occupancy_wavenet_variant, smem)
+}
+
+size_t wavenet_smem_bytes(const WaveNetPlan& plan)
+{
+  const int cmax = std::max(plan.cp[0], plan.cp[1]);
+  const size_t tile4 = (size_t)(cmax / 4) * (kHalo + kWnS * kWnNT);
+  return (plan.blob.size() + 3) / 4 * 16 + tile4 * 16;
+}
+
+void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batch, int n_frames, long in_stride,
+                    long out_stride, cudaStream_t st)
+{
+  const WaveNetPlan& plan = m->plan;
+  WaveNetKernelParams kp{};
+  kp.weights = m->d_weights;
+  kp.n_weight_floats = (int)plan.blob.size();
+  kp.state = m->d_state;
+  kp.state_stride = m->state_stride;
+  kp.in = d_in;
+  kp.out = d_out;
+  kp.in_stride = in_stride;
+  kp.out_stride = out_stride;
+  kp.batch = batch;
+  kp.n_frames = n_frames;
+  kp.t_base = m->t_base;
+  kp.head_scale = plan.head_scale;
+  kp.n_arrays = plan.n_arrays;
+  for (size_t i = 0; i < plan.arrays.size(); i++)
+    kp.arrays[i] = plan.arrays[i];
+  for (size_t i = 0; i < plan.layers.size(); i++)
+    kp.layers[i] = plan.layers[i];
+  const size_t smem = wavenet_smem_bytes(plan);
+  const int c0 = plan.cp[0], c1 = plan.n_arrays > 1 ? plan.cp[1] : 0;
+  if (m->wn_ctas_per_sm <= 0)
+    m->wn_ctas_per_sm = m->opts.ctas_per_sm > 0 ? m->opts.ctas_per_sm : occupancy_wavenet_dispatch(c0, c1, smem);
+  const int per_sm = m->wn_ctas_per_sm;
+  int grid = std::min(batch, per_sm * m->sm_count);
+  if (grid < 1)
+    grid = 1;
+  launch_wavenet_dispatch(c0, c1, m, kp, grid, smem, st);
+  m->launches++;
+}
+
+void launch_lstm(nam_b200_model* m, const float* d_in, float* d_out, int batch, int n_frames, long in_stride,
+                 long out_stride, cudaStream_t st)
+{
+  const LstmSpec& ls = m->spec.lstm;
+  LstmKernelParams kp{};
+  kp.weights = m->d_weights;
+  kp.n_weight_floats = (int)m->n_weight_floats;
+  kp.state = m->d_state;
+  kp.state_stride = (int)m->state_stride;
+  kp.in = d_in;
+  kp.out = d_out;
+  kp.in_stride = in_stride;
+  kp.out_stride = out_stride;
+  kp.batch = batch;
+  kp.n_frames = n_frames;
+  kp.num_layers = ls.num_layers;
+  kp.input_size = ls.input_size;
+  kp.hidden = ls.hidden;
+  kp.fast_tanh = m->fast_tanh_runtime;
+  const int H = ls.hidden;
+  const size_t smem = (((m->n_weight_floats + 3) & ~(size_t)3) + (size_t)ls.num_layers * 2 * H * kLstmThreads
+                       + (size_t)4 * H * kLstmThreads + (size_t)2 * kLstmThreads * (kLstmChunk + 1))
+                      * sizeof(float);
+  static bool configured[64] = {false};
+  if (!configured[m->device & 63])
+  {
+    CUDA_CHECK(cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[m->device & 63] = true;
+  }
+  if (smem > 227 * 1024)
+    throw std::runtime_error("LSTM too large for the shared-memory resident kernel");
+  const int grid = (batch + kLstmThreads - 1) / kLstmThreads;
+  lstm_kernel<<<grid, kLstmThreads, smem, st>>>(kp);
+  CUDA_CHECK(cudaGetLastError());
+  m->launches++;
+}
+
+void launch_linear(nam_b200_model* m, const float* d_in, float* d_out, int batch, int n_frames, long in_stride,
+                   long out_stride, cudaStream_t st)
+{
+  const LinearSpec& li = m->spec.linear;
+  LinearKernelParams kp{};
+  kp.impulse = m->d_weights;
+  kp.rf = li.receptive_field;
+  kp.bias = li.bias_value;
+  kp.state = m->d_state;
+  kp.state_stride = (int)m->state_stride;
+  kp.in = d_in;
+  kp.out = d_out;
+  kp.in_stride = in_stride;
+  kp.out_stride = out_stride;
+  kp.batch = batch;
+  kp.n_frames = n_frames;
+  const size_t smem = (((size_t)li.receptive_field + 3) & ~(size_t)3) * 4 + ((size_t)li.receptive_field - 1 + kLinThreads) * 4;
+  static bool configured[64] = {false};
+  if (!configured[m->device & 63])
+  {
+    CUDA_CHECK(cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[m->device & 63] = true;
+  }
+  if (smem > 227 * 1024)
+    throw std::runtime_error("Linear receptive field too long for the direct-form kernel");
+  dim3 grid((n_frames + kLinThreads - 1) / kLinThreads, batch);
+  linear_kernel<<<grid, kLinThreads, smem, st>>>(kp);
+  CUDA_CHECK(cudaGetLastError());
+  m->launches++;
+  const int hist = li.receptive_field - 1;
+  if (hist > 0)
+  {
+    dim3 g2((hist + 255) / 256, batch);
+    linear_update_state_kernel<<<g2, 256, 0, st>>>(kp, m->d_state_tmp);
+    CUDA_CHECK(cudaGetLastError());
+    m->launches++;
+    std::swap(m->d_state, m->d_state_tmp);
+  }
+}
+
+// Run the hot path on device buffers and advance the stream clock.
+void run_device(nam_b200_model* m, const float* d_in, float* d_out, int batch, int n_frames, long in_stride,
+                long out_stride, cudaStream_t st)
+{
+  switch (m->spec.arch)
+  {
+    case Arch::WaveNet: launch_wavenet(m, d_in, d_out, batch, n_frames, in_stride, out_stride, st); break;
+    case Arch::LSTM: launch_lstm(m, d_in, d_out, batch, n_frames, in_stride, out_stride, st); break;
+    case Arch::Linear: launch_linear(m, d_in, d_out, batch, n_frames, in_stride, out_stride, st); break;
+  }
+  m->t_base += (uint32_t)n_frames;
+}
+
+void ensure_staging(nam_b200_model* m, size_t floats)
+{
+  if (floats <= m->staging_floats)
+    return;
+  if (m->d_in)
+    cudaFree(m->d_in);
+  if (m->d_out)
+    cudaFree(m->d_out);
+  m->d_in = m->d_out = nullptr;
+  m->staging_floats = 0;
+  CUDA_CHECK(cudaMalloc(&m->d_in, floats * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&m->d_out, floats * sizeof(float)));
+  m->staging_floats = floats;
+}
+
+void ensure_pinned(nam_b200_model* m, size_t floats)
+{
+  if (floats <= m->h_pin_floats)
+    return;
+  if (m->h_pin)
+    cudaFreeHost(m->h_pin);
+  m->h_pin = nullptr;
+  m->h_pin_floats = 0;
+  CUDA_CHECK(cudaMallocHost(&m->h_pin, floats * sizeof(float)));
+  m->h_pin_floats = floats;
+}
+
+// Zero the state, set the trained initial state where the architecture has one.
+void init_state(nam_b200_model* m)
+{
+  const size_t total = (size_t)m->state_stride * m->opts.max_batch;
+  CUDA_CHECK(cudaMemsetAsync(m->d_state, 0, total * sizeof(float), m->stream));
+  if (m->spec.arch == Arch::LSTM)
+  {
+    // h0 / c0 are trained parameters (lstm.cpp:24-28): stream 0 gets them, then broadcast
+    std::vector<float> st((size_t)m->state_stride, 0.0f);
+    const int H = m->spec.lstm.hidden;
+    for (int l = 0; l < m->spec.lstm.num_layers; l++)
+    {
+      std::copy(m->spec.lstm.cells[l].h0.begin(), m->spec.lstm.cells[l].h0.end(), st.begin() + (size_t)l * 2 * H);
+      std::copy(m->spec.lstm.cells[l].c0.begin(), m->spec.lstm.cells[l].c0.end(), st.begin() + (size_t)l * 2 * H + H);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(m->d_state, st.data(), st.size() * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    CUDA_CHECK(cudaStreamSynchronize(m->stream));
+  }
+  if (m->spec.arch == Arch::Linear && m->d_state_tmp)
+    CUDA_CHECK(cudaMemsetAsync(m->d_state_tmp, 0, total * sizeof(float), m->stream));
+  m->t_base = 0;
+}
+
+void broadcast_state(nam_b200_model* m)
+{
+  const int batch = m->opts.max_batch;
+  if (batch <= 1 || m->state_stride == 0)
+    return;
+  dim3 grid((unsigned)std::min<long>((m->state_stride / 4 + 255) / 256, 1024), (unsigned)std::min(batch - 1, 64));
+  if (grid.x < 1)
+    grid.x = 1;
+  broadcast_state_kernel<<<grid, 256, 0, m->stream>>>(m->d_state, m->state_stride, batch);
+  CUDA_CHECK(cudaGetLastError());
+  m->launches++;
+}
+
+// DSP::prewarm (dsp.cpp:67-101): zeros in max_frames blocks until >= prewarm_samples; done once on
+// stream 0 (every stream would compute the identical state) and broadcast.
+void prewarm(nam_b200_model* m)
+{
+  const int ps = m->spec.prewarm_samples;
+  if (ps <= 0)
+    return;
+  const int bs = std::max(m->max_frames, 1);
+  ensure_staging(m, (size_t)std::max<size_t>((size_t)bs, (size_t)m->opts.max_batch * bs));
+  CUDA_CHECK(cudaMemsetAsync(m->d_in, 0, (size_t)bs * sizeof(float), m->stream));
+  int done = 0;
+  while (done < ps)
+  {
+    run_device(m, m->d_in, m->d_out, 1, bs, bs, bs, m->stream);
+    done += bs;
+  }
+  broadcast_state(m);
+  if (m->spec.arch == Arch::Linear && m->d_state_tmp)
+    CUDA_CHECK(cudaMemcpyAsync(m->d_state_tmp, m->d_state, (size_t)m->state_stride * m->opts.max_batch * sizeof(float),
+                               cudaMemcpyDeviceToDevice, m->stream));
+  CUDA_CHECK(cudaStreamSynchronize(m->stream));
+}
+
+int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_model** out)
+{
+  std::unique_ptr<nam_b200_model> m(new nam_b200_model());
+  nam_b200_default_options(&m->opts);
+  if (user_opts)
+  {
+    const size_t n = std::min<size_t>(sizeof(nam_b200_options), (size_t)std::max(user_opts->struct_size, 0));
+    std::memcpy(&m->opts, user_opts, n);
+    m->opts.struct_size = sizeof(nam_b200_options);
+  }
+  if (m->opts.max_batch < 1)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "max_batch must be >= 1");
+  m->spec = std::move(spec);
+  m->fast_tanh_runtime = m->opts.fast_tanh;
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(NAM_B200_ERR_CUDA, std::string("no usable CUDA device (libnam_b200 has no CPU path): ")
+                                     + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  try
+  {
+    if (m->opts.device >= 0)
+      CUDA_CHECK(cudaSetDevice(m->opts.device));
+    CUDA_CHECK(cudaGetDevice(&m->device));
+    cudaDeviceProp prop{};
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, m->device));
+    m->sm_count = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreate(&m->ev0));
+    CUDA_CHECK(cudaEventCreate(&m->ev1));
+
+    if (m->spec.in_channels != 1 || m->spec.out_channels != 1)
+      return fail(NAM_B200_ERR_UNSUPPORTED, "CUDA path is mono in / mono out (model has "
+                                              + std::to_string(m->spec.in_channels) + " in, "
+                                              + std::to_string(m->spec.out_channels) + " out channels)");
+    std::vector<float> blob;
+    switch (m->spec.arch)
+    {
+      case Arch::WaveNet:
+      {
+        m->plan = plan_wavenet(m->spec);
+        if (!m->plan.eligible)
+          return fail(NAM_B200_ERR_UNSUPPORTED, "WaveNet option not implemented on the CUDA path yet: " + m->plan.why_not);
+        blob = m->plan.blob;
+        m->state_stride = m->plan.state_floats;
+        m->flops_per_frame = 2.0 * m->plan.macs_per_frame;
+        m->variant = m->plan.cp[0] * 100 + (m->plan.n_arrays > 1 ? m->plan.cp[1] : 0);
+        if (wavenet_smem_bytes(m->plan) > 227 * 1024)
+          return fail(NAM_B200_ERR_UNSUPPORTED, "WaveNet weights do not fit in shared memory");
+        break;
+      }
+      case Arch::LSTM:
+      {
+        const LstmSpec& ls = m->spec.lstm;
+        if (ls.input_size != 1)
+          return fail(NAM_B200_ERR_UNSUPPORTED, "LSTM input_size != 1");
+        if (ls.num_layers < 1)
+          return fail(NAM_B200_ERR_UNSUPPORTED, "LSTM with zero layers");
+        double macs = 0.0;
+        for (const auto& c : ls.cells)
+        {
+          blob.insert(blob.end(), c.w.begin(), c.w.end());
+          blob.insert(blob.end(), c.b.begin(), c.b.end());
+          macs += 4.0 * c.hidden * (c.input_size + c.hidden);
+        }
+        blob.insert(blob.end(), ls.head_w.begin(), ls.head_w.end());
+        blob.insert(blob.end(), ls.head_b.begin(), ls.head_b.end());
+        macs += ls.hidden;
+        m->state_stride = ((long)ls.num_layers * 2 * ls.hidden + 3) & ~3L;
+        m->flops_per_frame = 2.0 * macs;
+        m->variant = 2000 + ls.hidden;
+        break;
+      }
+      case Arch::Linear:
+      {
+        blob = m->spec.linear.impulse;
+        m->state_stride = ((long)std::max(m->spec.linear.receptive_field - 1, 1) + 3) & ~3L;
+        m->flops_per_frame = 2.0 * m->spec.linear.receptive_field;
+        m->variant = 3000;
+        break;
+      }
+    }
+    m->n_weight_floats = blob.size();
+    const size_t alloc_floats = (blob.size() + 3) & ~(size_t)3;
+    blob.resize(alloc_floats, 0.0f);
+    CUDA_CHECK(cudaMalloc(&m->d_weights, alloc_floats * sizeof(float)));
+    CUDA_CHECK(cudaMemcpy(m->d_weights, blob.data(), alloc_floats * sizeof(float), cudaMemcpyHostToDevice));
+    const size_t state_total = (size_t)m->state_stride * m->opts.max_batch;
+    CUDA_CHECK(cudaMalloc(&m->d_state, std::max<size_t>(state_total, 4) * sizeof(float)));
+    if (m->spec.arch == Arch::Linear)
+      CUDA_CHECK(cudaMalloc(&m->d_state_tmp, std::max<size_t>(state_total, 4) * sizeof(float)));
+    init_state(m.get());
+    CUDA_CHECK(cudaStreamSynchronize(m->stream));
+  }
+  catch (const CudaError& ex)
+  {
+    return fail(NAM_B200_ERR_CUDA, ex.what());
+  }
+  catch (const std::exception& ex)
+  {
+    return fail(NAM_B200_ERR_MODEL, ex.what());
+  }
+  *out = m.release();
+  return NAM_B200_OK;
+}
+
+template <typename F>
+int guarded(nam_b200_model* m, F&& body)
+{
+  if (!m)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null model handle");
+  try
+  {
+    CUDA_CHECK(cudaSetDevice(m->device));
+    return body();
+  }
+  catch (const CudaError& ex)
+  {
+    return fail(NAM_B200_ERR_CUDA, ex.what());
+  }
+  catch (const std::exception& ex)
+  {
+    return fail(NAM_B200_ERR_MODEL, ex.what());
+  }
+}
+
+int check_process_args(nam_b200_model* m, const void* in, const void* out, int batch, int n_frames)
+{
+  if (!in || !out)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null audio buffer");
+  if (!m->is_reset)
+    return fail(NAM_B200_ERR_STATE, "process called before reset");
+  if (batch < 1 || batch > m->opts.max_batch)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT,
+                "batch " + std::to_string(batch) + " outside [1, max_batch=" + std::to_string(m->opts.max_batch) + "]");
+  if (n_frames < 0 || n_frames > m->max_frames)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "n_frames " + std::to_string(n_frames) + " exceeds max_frames "
+                                                 + std::to_string(m->max_frames) + " of the last reset");
+  return NAM_B200_OK;
+}
+
+} // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+void nam_b200_default_options(nam_b200_options* opts)
+{
+  if (!opts)
+    return;
+  std::memset(opts, 0, sizeof(*opts));
+  opts->struct_size = sizeof(nam_b200_options);
+  opts->device = -1;
+  opts->max_batch = 1;
+  opts->fast_tanh = 0;
+  opts->prewarm_on_reset = 1;
+  opts->ctas_per_sm = 0;
+}
+
+int nam_b200_abi_version(void)
+{
+  return NAM_B200_ABI_VERSION;
+}
+
+const char* nam_b200_last_error(void)
+{
+  return g_last_error.c_str();
+}
+
+int nam_b200_create_from_file(const char* nam_path, const nam_b200_options* opts, nam_b200_model** out)
+{
+  if (!nam_path || !out)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  LoadOptions lo;
+  lo.fast_tanh = opts ? (opts->fast_tanh != 0) : false;
+  try
+  {
+    ModelSpec spec = model_spec_from_file(nam_path, lo);
+    return create_common(std::move(spec), opts, out);
+  }
+  catch (const NamFileValidationError& ex)
+  {
+    return fail(NAM_B200_ERR_FILE, ex.what());
+  }
+  catch (const std::exception& ex)
+  {
+    return fail(NAM_B200_ERR_MODEL, ex.what());
+  }
+}
+
+int nam_b200_create_from_json(const char* nam_json_text, const nam_b200_options* opts, nam_b200_model** out)
+{
+  if (!nam_json_text || !out)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  LoadOptions lo;
+  lo.fast_tanh = opts ? (opts->fast_tanh != 0) : false;
+  try
+  {
+    ModelSpec spec = model_spec_from_text(nam_json_text, lo);
+    return create_common(std::move(spec), opts, out);
+  }
+  catch (const json::ParseError& ex)
+  {
+    return fail(NAM_B200_ERR_FILE, ex.what());
+  }
+  catch (const std::exception& ex)
+  {
+    return fail(NAM_B200_ERR_MODEL, ex.what());
+  }
+}
+
+void nam_b200_destroy(nam_b200_model* m)
+{
+  delete m;
+}
+
+int nam_b200_get_info(const nam_b200_model* m, nam_b200_info* info)
+{
+  if (!m || !info)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null argument");
+  nam_b200_info r;
+  std::memset(&r, 0, sizeof(r));
+  r.struct_size = sizeof(nam_b200_info);
+  r.architecture = (int)m->spec.arch;
+  r.in_channels = m->spec.in_channels;
+  r.out_channels = m->spec.out_channels;
+  r.prewarm_samples = m->spec.prewarm_samples;
+  r.max_batch = m->opts.max_batch;
+  r.max_frames = m->max_frames;
+  r.has_loudness = m->spec.loudness.has_value();
+  r.has_input_level = m->spec.input_level.has_value();
+  r.has_output_level = m->spec.output_level.has_value();
+  r.expected_sample_rate = m->spec.sample_rate;
+  r.loudness = m->spec.loudness.value_or(0.0);
+  r.input_level_dbu = m->spec.input_level.value_or(0.0);
+  r.output_level_dbu = m->spec.output_level.value_or(0.0);
+  r.n_weights = (int64_t)m->spec.n_weights;
+  r.state_bytes_per_stream = (int64_t)m->state_stride * 4;
+  r.flops_per_frame = m->flops_per_frame;
+  r.kernel_variant = m->variant;
+  const size_t n = std::min<size_t>(sizeof(r), (size_t)std::max(info->struct_size, 0));
+  const int32_t user_size = info->struct_size;
+  std::memcpy(info, &r, n);
+  info->struct_size = user_size;
+  return NAM_B200_OK;
+}
+
+int nam_b200_reset(nam_b200_model* m, double sample_rate, int max_frames)
+{
+  (void)sample_rate; // like the reference, the external rate is recorded but does not change the arithmetic
+  return guarded(m, [&]() -> int {
+    if (max_frames < 1)
+      return fail(NAM_B200_ERR_INVALID_ARGUMENT, "max_frames must be >= 1");
+    m->max_frames = max_frames;
+    ensure_staging(m, (size_t)m->opts.max_batch * max_frames);
+    ensure_pinned(m, (size_t)2 * max_frames);
+    init_state(m);
+    m->is_reset = true;
+    CUDA_CHECK(cudaEventRecord(m->ev0, m->stream));
+    if (m->opts.prewarm_on_reset)
+      prewarm(m);
+    CUDA_CHECK(cudaEventRecord(m->ev1, m->stream));
+    CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    m->timing_valid = true;
+    return NAM_B200_OK;
+  });
+}
+
+int nam_b200_prewarm(nam_b200_model* m)
+{
+  return guarded(m, [&]() -> int {
+    if (!m->is_reset)
+      return fail(NAM_B200_ERR_STATE, "prewarm called before reset");
+    prewarm(m);
+    return NAM_B200_OK;
+  });
+}
+
+int nam_b200_process_f32_device(nam_b200_model* m, const float* in_device, float* out_device, int batch, int n_frames,
+                                int64_t in_stride, int64_t out_stride, void* cuda_stream)
+{
+  return guarded(m, [&]() -> int {
+    const int rc = check_process_args(m, in_device, out_device, batch, n_frames);
+    if (rc != NAM_B200_OK)
+      return rc;
+    if (n_frames == 0)
+      return NAM_B200_OK;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : m->stream;
+    CUDA_CHECK(cudaEventRecord(m->ev0, st));
+    run_device(m, in_device, out_device, batch, n_frames, (long)in_stride, (long)out_stride, st);
+    CUDA_CHECK(cudaEventRecord(m->ev1, st));
+    m->timing_valid = true;
+    return NAM_B200_OK;
+  });
+}
+
+int nam_b200_process_f32(nam_b200_model* m, const float* in, float* out, int batch, int n_frames, int64_t in_stride,
+                         int64_t out_stride)
+{
+  return guarded(m, [&]() -> int {
+    const int rc = check_process_args(m, in, out, batch, n_frames);
+    if (rc != NAM_B200_OK)
+      return rc;
+    if (n_frames == 0)
+      return NAM_B200_OK;
+    if (in_stride < n_frames || out_stride < n_frames)
+      return fail(NAM_B200_ERR_INVALID_ARGUMENT, "stride smaller than n_frames");
+    const size_t row = (size_t)n_frames * sizeof(float);
+    CUDA_CHECK(cudaMemcpy2DAsync(m->d_in, row, in, (size_t)in_stride * sizeof(float), row, (size_t)batch,
+                                 cudaMemcpyHostToDevice, m->stream));
+    CUDA_CHECK(cudaEventRecord(m->ev0, m->stream));
+    run_device(m, m->d_in, m->d_out, batch, n_frames, n_frames, n_frames, m->stream);
+    CUDA_CHECK(cudaEventRecord(m->ev1, m->stream));
+    CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)out_stride * sizeof(float), m->d_out, row, row, (size_t)batch,
+                                 cudaMemcpyDeviceToHost, m->stream));
+    CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    m->timing_valid = true;
+    return NAM_B200_OK;
+  });
+}
+
+int nam_b200_process_f32_planar(nam_b200_model* m, const float* const* input, float* const* output, int n_frames)
+{
+  if (!input || !output)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null channel array");
+  return nam_b200_process_f32(m, input[0], output[0], 1, n_frames, n_frames, n_frames);
+}
+
+int nam_b200_process_f64_planar(nam_b200_model* m, const double* const* input, double* const* output, int n_frames)
+{
+  return guarded(m, [&]() -> int {
+    if (!input || !output)
+      return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null channel array");
+    const int rc = check_process_args(m, input[0], output[0], 1, n_frames);
+    if (rc != NAM_B200_OK)
+      return rc;
+    if (n_frames == 0)
+      return NAM_B200_OK;
+    float* hin = m->h_pin;
+    float* hout = m->h_pin + m->max_frames;
+    for (int i = 0; i < n_frames; i++)
+      hin[i] = (float)input[0][i]; // the double -> float cast of model.cpp:817 / lstm.cpp:111
+    CUDA_CHECK(cudaMemcpyAsync(m->d_in, hin, (size_t)n_frames * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    CUDA_CHECK(cudaEventRecord(m->ev0, m->stream));
+    run_device(m, m->d_in, m->d_out, 1, n_frames, n_frames, n_frames, m->stream);
+    CUDA_CHECK(cudaEventRecord(m->ev1, m->stream));
+    CUDA_CHECK(cudaMemcpyAsync(hout, m->d_out, (size_t)n_frames * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    m->timing_valid = true;
+    for (int i = 0; i < n_frames; i++)
+      output[0][i] = (double)hout[i];
+    return NAM_B200_OK;
+  });
+}
+
+int nam_b200_set_fast_tanh(nam_b200_model* m, int enabled)
+{
+  if (!m)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null model handle");
+  m->fast_tanh_runtime = enabled ? 1 : 0; // only the LSTM kernel reads it (lstm.cpp:48)
+  return NAM_B200_OK;
+}
+
+int nam_b200_synchronize(nam_b200_model* m)
+{
+  return guarded(m, [&]() -> int {
+    CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    return NAM_B200_OK;
+  });
+}
+
+int64_t nam_b200_launch_count(const nam_b200_model* m)
+{
+  return m ? m->launches : -1;
+}
+
+double nam_b200_last_kernel_ms(nam_b200_model* m)
+{
+  if (!m || !m->timing_valid)
+    return -1.0;
+  cudaSetDevice(m->device);
+  if (cudaEventSynchronize(m->ev1) != cudaSuccess)
+    return -1.0;
+  float ms = 0.0f;
+  if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) != cudaSuccess)
+    return -1.0;
+  return (double)ms;
+}
+
+double nam_b200_measure_fp32_tflops(int device, int use_ffma2)
+{
+  try
+  {
+    if (device >= 0)
+      CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    float* d = nullptr;
+    CUDA_CHECK(cudaMalloc(&d, 4));
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = prop.multiProcessorCount * 8, threads = 256;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++)
+    {
+      CUDA_CHECK(cudaEventRecord(e0));
+      if (use_ffma2)
+        fma_peak_kernel<true><<<blocks, threads>>>(d, iters, 1.0f);
+      else
+        fma_peak_kernel<false><<<blocks, threads>>>(d, iters, 1.0f);
+      CUDA_CHECK(cudaEventRecord(e1));
+      CUDA_CHECK(cudaEventSynchronize(e1));
+      float ms = 0.0f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+      const double flops = 2.0 * 16.0 * (double)iters * blocks * threads;
+      best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return best;
+  }
+  catch (const std::exception& ex)
+  {
+    fail(NAM_B200_ERR_CUDA, ex.what());
+    return -1.0;
+  }
+}
+
+} // extern "C"

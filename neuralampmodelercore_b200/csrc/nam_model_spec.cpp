@@ -1,0 +1,735 @@
+#include "nam_model_spec.h"
+
+#include <array>
+#include <cctype>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+namespace namb200
+{
+
+namespace
+{
+
+// ---- weight stream ---------------------------------------------------------------------------
+class WeightStream
+{
+public:
+  explicit WeightStream(const std::vector<float>& w)
+  : _w(w)
+  {
+  }
+  float next()
+  {
+    if (_pos >= _w.size())
+    {
+      // NAM/wavenet/model.cpp:681
+      throw std::runtime_error("Weight mismatch: provided " + std::to_string(_w.size())
+                               + " weights, but the model expects more.");
+    }
+    return _w[_pos++];
+  }
+  size_t position() const { return _pos; }
+  size_t size() const { return _w.size(); }
+
+private:
+  const std::vector<float>& _w;
+  size_t _pos = 0;
+};
+
+void check_groups(const char* what, int in, int out, int groups)
+{
+  if (groups <= 0 || in % groups != 0)
+    throw std::runtime_error(std::string(what) + ": in_channels (" + std::to_string(in)
+                             + ") must be divisible by numGroups (" + std::to_string(groups) + ")");
+  if (out % groups != 0)
+    throw std::runtime_error(std::string(what) + ": out_channels (" + std::to_string(out)
+                             + ") must be divisible by numGroups (" + std::to_string(groups) + ")");
+}
+
+// NAM/dsp.cpp:363-398
+void read_conv1x1(Conv1x1W& m, int in, int out, bool bias, int groups, WeightStream* ws)
+{
+  check_groups("Conv1x1", in, out, groups);
+  m.in = in;
+  m.out = out;
+  m.groups = groups;
+  m.bias = bias;
+  m.w.assign((size_t)in * out, 0.0f);
+  m.b.assign((size_t)out, 0.0f);
+  if (!ws)
+    return;
+  const int opg = out / groups, ipg = in / groups;
+  for (int g = 0; g < groups; g++)
+    for (int i = 0; i < opg; i++)
+      for (int j = 0; j < ipg; j++)
+        m.w[(size_t)(g * opg + i) * in + (g * ipg + j)] = ws->next();
+  if (bias)
+    for (int i = 0; i < out; i++)
+      m.b[i] = ws->next();
+}
+
+// NAM/conv1d.cpp:11-56 : (group, out, in, tap) with the tap index innermost
+void read_conv1d(Conv1DW& m, int in, int out, int kernel, bool bias, int dilation, int groups, WeightStream* ws)
+{
+  check_groups("Conv1D", in, out, groups);
+  if (kernel < 1 || dilation < 1)
+    throw std::runtime_error("Conv1D: kernel_size and dilation must be >= 1");
+  m.in = in;
+  m.out = out;
+  m.kernel = kernel;
+  m.dilation = dilation;
+  m.groups = groups;
+  m.bias = bias;
+  m.w.assign((size_t)kernel * in * out, 0.0f);
+  m.b.assign((size_t)out, 0.0f);
+  if (!ws)
+    return;
+  const int opg = out / groups, ipg = in / groups;
+  for (int g = 0; g < groups; g++)
+    for (int i = 0; i < opg; i++)
+      for (int j = 0; j < ipg; j++)
+        for (int k = 0; k < kernel; k++)
+          m.w[((size_t)k * out + (g * opg + i)) * in + (g * ipg + j)] = ws->next();
+  if (bias)
+    for (int i = 0; i < out; i++)
+      m.b[i] = ws->next();
+}
+
+// ---- activations (NAM/activations.cpp:55-130) -----------------------------------------------
+ActType act_type_from_name(const std::string& name)
+{
+  static const std::pair<const char*, ActType> table[] = {
+    {"Tanh", ActType::Tanh},
+    {"Hardtanh", ActType::Hardtanh},
+    {"Fasttanh", ActType::Fasttanh},
+    {"ReLU", ActType::ReLU},
+    {"LeakyReLU", ActType::LeakyReLU},
+    {"PReLU", ActType::PReLU},
+    {"Sigmoid", ActType::Sigmoid},
+    {"SiLU", ActType::SiLU},
+    {"Hardswish", ActType::Hardswish},
+    {"LeakyHardtanh", ActType::LeakyHardtanh},
+    {"LeakyHardTanh", ActType::LeakyHardtanh},
+    {"Softsign", ActType::Softsign},
+  };
+  for (const auto& e : table)
+    if (name == e.first)
+      return e.second;
+  throw std::runtime_error("Unknown activation type: " + name);
+}
+
+ActSpec parse_activation(const json::Value& j, const LoadOptions& opts)
+{
+  ActSpec a;
+  if (j.is_null())
+  {
+    a.type = ActType::Identity;
+    return a;
+  }
+  if (j.is_string())
+  {
+    a.type = act_type_from_name(j.as_string());
+  }
+  else if (j.is_object())
+  {
+    a.type = act_type_from_name(j.at("type").as_string("activation.type"));
+    if (a.type == ActType::PReLU)
+    {
+      if (j.contains("negative_slope"))
+        a.slopes = {(float)j.at("negative_slope").as_double()};
+      else if (j.contains("negative_slopes"))
+        for (const auto& v : j.at("negative_slopes").items("negative_slopes"))
+          a.slopes.push_back((float)v.as_double());
+    }
+    else if (a.type == ActType::LeakyReLU)
+      a.slope = (float)j.value_double("negative_slope", 0.01);
+    else if (a.type == ActType::LeakyHardtanh)
+    {
+      a.min_val = (float)j.value_double("min_val", -1.0);
+      a.max_val = (float)j.value_double("max_val", 1.0);
+      a.min_slope = (float)j.value_double("min_slope", 0.01);
+      a.max_slope = (float)j.value_double("max_slope", 0.01);
+    }
+  }
+  else
+    throw std::runtime_error("Invalid activation config: expected string or object");
+  if (a.type == ActType::PReLU && a.slopes.empty())
+    a.slopes = {0.01f};
+  // enable_fast_tanh() swaps the "Tanh" entry of the name map (activations.cpp:168-177)
+  if (opts.fast_tanh && a.type == ActType::Tanh)
+    a.type = ActType::Fasttanh;
+  return a;
+}
+
+Gating parse_gating(const std::string& s)
+{
+  if (s == "gated")
+    return Gating::Gated;
+  if (s == "blended")
+    return Gating::Blended;
+  if (s == "none")
+    return Gating::None;
+  throw std::runtime_error("Invalid gating_mode: " + s);
+}
+
+struct FilmParams
+{
+  bool active = false, shift = false;
+  int groups = 1;
+};
+
+// parse_film_params, model.cpp:1190-1201
+FilmParams parse_film(const json::Value& lc, const char* key)
+{
+  FilmParams f;
+  if (!lc.contains(key))
+    return f;
+  const json::Value& v = lc.at(key);
+  if (v.is_bool() && !v.as_bool())
+    return f;
+  f.active = v.value_bool("active", true);
+  f.shift = v.value_bool("shift", true);
+  f.groups = v.value_int("groups", 1);
+  return f;
+}
+
+const char* kFilmKeys[F_COUNT] = {"conv_pre_film",       "conv_post_film",       "input_mixin_pre_film",
+                                  "input_mixin_post_film", "activation_pre_film", "activation_post_film",
+                                  "layer1x1_post_film",  "head1x1_post_film"};
+
+ModelSpec build_spec(const json::Value& root, const LoadOptions& opts);
+
+// ---- WaveNet (model.cpp:913-1276 config, :591-683 construction + weights) --------------------
+void build_wavenet(ModelSpec& ms, const json::Value& config, const std::vector<float>& weights,
+                   const LoadOptions& opts)
+{
+  WaveNetSpec& wn = ms.wavenet;
+  if (config.contains("condition_dsp") && !config.at("condition_dsp").is_null())
+  {
+    wn.condition_dsp = std::make_shared<ModelSpec>(build_spec(config.at("condition_dsp"), opts));
+    if (wn.condition_dsp->sample_rate != ms.sample_rate)
+    {
+      std::stringstream ss;
+      ss << "Condition DSP expected sample rate (" << wn.condition_dsp->sample_rate
+         << ") doesn't match WaveNet expected sample rate (" << ms.sample_rate << "!\n";
+      throw std::runtime_error(ss.str());
+    }
+  }
+  const auto& layers_json = config.at("layers").items("layers");
+  if (layers_json.empty())
+    throw std::runtime_error("WaveNet config requires at least one layer array");
+  wn.in_channels = config.value_int("in_channels", 1);
+  wn.with_head = config.contains("head") && !config.at("head").is_null();
+
+  struct PerLayer
+  {
+    int kernel, dilation;
+    Gating gating;
+    ActSpec act, sec;
+  };
+  std::vector<std::vector<PerLayer>> per_layer(layers_json.size());
+  std::vector<std::array<FilmParams, F_COUNT>> films(layers_json.size());
+
+  for (size_t i = 0; i < layers_json.size(); i++)
+  {
+    const json::Value& lc = layers_json[i];
+    const std::string where = "Layer array " + std::to_string(i);
+    ArraySpec A;
+    A.groups_input = lc.value_int("groups_input", 1);
+    A.groups_input_mixin = lc.value_int("groups_input_mixin", 1);
+    A.channels = lc.at("channels").as_int("channels");
+    A.bottleneck = lc.value_int("bottleneck", A.channels);
+    if (lc.contains("layer1x1"))
+    {
+      A.l1x1_active = lc.at("layer1x1").at("active").as_bool("layer1x1.active");
+      A.l1x1_groups = lc.at("layer1x1").at("groups").as_int("layer1x1.groups");
+    }
+    A.input_size = lc.at("input_size").as_int("input_size");
+    A.condition_size = lc.at("condition_size").as_int("condition_size");
+    if (lc.contains("head") && !lc.at("head").is_null())
+    {
+      const json::Value& hj = lc.at("head");
+      if (!hj.is_object())
+        throw std::runtime_error(where + ": 'head' must be a JSON object");
+      A.head_size = hj.at("out_channels").as_int("head.out_channels");
+      if (hj.contains("head_dilation"))
+        A.head_dilation = hj.at("head_dilation").as_int("head.head_dilation");
+      A.head_kernel = hj.at("kernel_size").as_int("head.kernel_size");
+      A.head_bias = hj.at("bias").as_bool("head.bias");
+    }
+    else if (lc.contains("head_size"))
+    {
+      A.head_size = lc.at("head_size").as_int("head_size");
+      A.head_kernel = 1;
+      A.head_bias = lc.at("head_bias").as_bool("head_bias");
+    }
+    else
+      throw std::runtime_error(where
+                               + ": expected 'head' object with out_channels, kernel_size, and bias, "
+                                 "or legacy 'head_size' and 'head_bias'");
+    if (A.head_kernel < 1)
+      throw std::runtime_error(where + ": head.kernel_size must be >= 1");
+
+    const auto& dil_json = lc.at("dilations").items("dilations");
+    const size_t n_layers = dil_json.size();
+    const bool has_k = lc.contains("kernel_size"), has_ks = lc.contains("kernel_sizes");
+    std::vector<int> kernel_sizes;
+    if (has_k && has_ks)
+      throw std::runtime_error(where + ": only one of kernel_size (int) or kernel_sizes (array) may be provided");
+    else if (has_ks)
+    {
+      if (!lc.at("kernel_sizes").is_array())
+        throw std::runtime_error(where + ": kernel_sizes must be an array");
+      for (const auto& k : lc.at("kernel_sizes").items())
+        kernel_sizes.push_back(k.as_int("kernel_sizes[]"));
+      if (kernel_sizes.size() != n_layers)
+        throw std::runtime_error(where + ": kernel_sizes array size (" + std::to_string(kernel_sizes.size())
+                                 + ") must match dilations size (" + std::to_string(n_layers) + ")");
+    }
+    else if (has_k)
+      kernel_sizes.assign(n_layers, lc.at("kernel_size").as_int("kernel_size"));
+    else
+      throw std::runtime_error(where + ": either kernel_size (int) or kernel_sizes (array) must be provided");
+
+    std::vector<ActSpec> acts;
+    const json::Value& act_json = lc.at("activation");
+    if (act_json.is_array())
+    {
+      for (const auto& a : act_json.items())
+        acts.push_back(parse_activation(a, opts));
+      if (acts.size() != n_layers)
+        throw std::runtime_error(where + ": activation array size (" + std::to_string(acts.size())
+                                 + ") must match dilations size (" + std::to_string(n_layers) + ")");
+    }
+    else
+      acts.assign(n_layers, parse_activation(act_json, opts));
+
+    std::vector<Gating> modes;
+    std::vector<ActSpec> secs;
+    const json::Value sigmoid_json = json::Value::parse("\"Sigmoid\"");
+    if (lc.contains("gating_mode"))
+    {
+      const json::Value& gm = lc.at("gating_mode");
+      const bool has_sec = lc.contains("secondary_activation");
+      const json::Value& sj = lc.get("secondary_activation");
+      if (gm.is_array())
+      {
+        for (const auto& g : gm.items())
+        {
+          const Gating mode = parse_gating(g.as_string("gating_mode[]"));
+          modes.push_back(mode);
+          if (mode != Gating::None)
+          {
+            if (has_sec)
+            {
+              if (sj.is_array())
+              {
+                if (modes.size() > sj.size())
+                  throw std::runtime_error(where + ": secondary_activation array size must be at least "
+                                           + std::to_string(modes.size()));
+                secs.push_back(parse_activation(sj[modes.size() - 1], opts));
+              }
+              else
+                secs.push_back(parse_activation(sj, opts));
+            }
+            else
+              secs.push_back(parse_activation(sigmoid_json, opts));
+          }
+          else
+            secs.push_back(ActSpec{});
+        }
+        if (modes.size() != n_layers)
+          throw std::runtime_error(where + ": gating_mode array size (" + std::to_string(modes.size())
+                                   + ") must match dilations size (" + std::to_string(n_layers) + ")");
+        if (has_sec && sj.is_array() && sj.size() != n_layers)
+          throw std::runtime_error(where + ": secondary_activation array size (" + std::to_string(sj.size())
+                                   + ") must match dilations size (" + std::to_string(n_layers) + ")");
+      }
+      else
+      {
+        const Gating mode = parse_gating(gm.as_string("gating_mode"));
+        modes.assign(n_layers, mode);
+        ActSpec sec;
+        if (mode != Gating::None)
+          sec = has_sec ? parse_activation(sj, opts) : parse_activation(sigmoid_json, opts);
+        secs.assign(n_layers, sec);
+      }
+    }
+    else if (lc.contains("gated"))
+    {
+      const bool gated = lc.at("gated").as_bool("gated");
+      modes.assign(n_layers, gated ? Gating::Gated : Gating::None);
+      secs.assign(n_layers, gated ? parse_activation(sigmoid_json, opts) : ActSpec{});
+    }
+    else
+    {
+      modes.assign(n_layers, Gating::None);
+      secs.assign(n_layers, ActSpec{});
+    }
+
+    A.h1x1_out = A.channels;
+    if (lc.contains("head1x1"))
+    {
+      const json::Value& h = lc.at("head1x1");
+      A.h1x1_active = h.at("active").as_bool("head1x1.active");
+      A.h1x1_out = h.at("out_channels").as_int("head1x1.out_channels");
+      A.h1x1_groups = h.at("groups").as_int("head1x1.groups");
+    }
+    for (int f = 0; f < F_COUNT; f++)
+      films[i][f] = parse_film(lc, kFilmKeys[f]);
+    if (films[i][F_L1X1_POST].active && !A.l1x1_active)
+      throw std::runtime_error(where + ": layer1x1_post_film cannot be active when layer1x1.active is false");
+
+    for (size_t l = 0; l < n_layers; l++)
+      per_layer[i].push_back(PerLayer{kernel_sizes[l], dil_json[l].as_int("dilations[]"), modes[l], acts[l], secs[l]});
+    wn.arrays.push_back(std::move(A));
+  }
+
+  // Constructor-time validation (model.cpp:596-651, detail.h:56-90)
+  if (wn.condition_dsp)
+  {
+    if (wn.in_channels != wn.condition_dsp->in_channels)
+      throw std::runtime_error("input channels of WaveNet (" + std::to_string(wn.in_channels)
+                               + ") don't match input channels of condition DSP ("
+                               + std::to_string(wn.condition_dsp->in_channels) + "!\n");
+    for (size_t i = 0; i < wn.arrays.size(); i++)
+      if (wn.arrays[i].condition_size != wn.condition_dsp->out_channels)
+        throw std::runtime_error("condition_size of layer " + std::to_string(i) + " ("
+                                 + std::to_string(wn.arrays[i].condition_size)
+                                 + ") doesn't match output channels of condition DSP ("
+                                 + std::to_string(wn.condition_dsp->out_channels) + "!\n");
+  }
+  for (size_t i = 1; i < wn.arrays.size(); i++)
+  {
+    if (wn.arrays[i].channels != wn.arrays[i - 1].head_size)
+      throw std::runtime_error("channels of layer " + std::to_string(i) + " (" + std::to_string(wn.arrays[i].channels)
+                               + ") doesn't match head_size of preceding layer ("
+                               + std::to_string(wn.arrays[i - 1].head_size) + "!\n");
+    // The head accumulator of array i is initialised by a straight copy of array i-1's head
+    // output (model.cpp:473-486), so the row counts must agree.
+    if (wn.arrays[i].head_out_size() != wn.arrays[i - 1].head_size)
+      throw std::runtime_error("layer array " + std::to_string(i) + ": head accumulator rows ("
+                               + std::to_string(wn.arrays[i].head_out_size()) + ") != previous head_size ("
+                               + std::to_string(wn.arrays[i - 1].head_size) + ")");
+  }
+
+  PostHeadSpec& ph = wn.post_head;
+  std::vector<int> ph_kernels;
+  if (wn.with_head)
+  {
+    const json::Value& hj = config.at("head");
+    const int implied_in = wn.arrays.back().head_size;
+    if (hj.contains("in_channels") && !hj.at("in_channels").is_null()
+        && hj.at("in_channels").as_int("head.in_channels") != implied_in)
+      throw std::runtime_error("WaveNet config: head.in_channels (" + std::to_string(hj.at("in_channels").as_int())
+                               + ") must equal last layer's head_size (" + std::to_string(implied_in) + ")");
+    ph.in_channels = implied_in;
+    ph.channels = hj.at("channels").as_int("head.channels");
+    ph.out_channels = hj.at("out_channels").as_int("head.out_channels");
+    for (const auto& k : hj.at("kernel_sizes").items("head.kernel_sizes"))
+      ph_kernels.push_back(k.as_int());
+    ph.act = parse_activation(hj.at("activation"), opts);
+    if (ph_kernels.empty())
+      throw std::runtime_error("WaveNet config: head.kernel_sizes must be non-empty");
+    for (int k : ph_kernels)
+      if (k < 1)
+        throw std::runtime_error("WaveNet Head: kernel_sizes entries must be >= 1");
+  }
+
+  // ---- weights, in stream order (model.cpp:661-670, :563-569, :152-181) ----
+  WeightStream ws(weights);
+  for (size_t i = 0; i < wn.arrays.size(); i++)
+  {
+    ArraySpec& A = wn.arrays[i];
+    read_conv1x1(A.rechannel, A.input_size, A.channels, false, 1, &ws);
+    for (const PerLayer& pl : per_layer[i])
+    {
+      LayerSpec L;
+      L.gating = pl.gating;
+      L.act = pl.act;
+      L.sec_act = pl.sec;
+      const int zrows = (pl.gating != Gating::None) ? 2 * A.bottleneck : A.bottleneck;
+      L.has_l1x1 = A.l1x1_active;
+      L.has_h1x1 = A.h1x1_active;
+      if (!A.l1x1_active && A.bottleneck != A.channels)
+        throw std::invalid_argument("When layer1x1.active is false, bottleneck (" + std::to_string(A.bottleneck)
+                                    + ") must equal channels (" + std::to_string(A.channels) + ")");
+      if (!A.h1x1_active && films[i][F_H1X1_POST].active)
+        throw std::invalid_argument("Do not use post-head 1x1 FiLM if there is no head 1x1");
+      read_conv1d(L.conv, A.channels, zrows, pl.kernel, true, pl.dilation, A.groups_input, &ws);
+      read_conv1x1(L.mixin, A.condition_size, zrows, false, A.groups_input_mixin, &ws);
+      if (L.has_l1x1)
+        read_conv1x1(L.l1x1, A.bottleneck, A.channels, true, A.l1x1_groups, &ws);
+      if (L.has_h1x1)
+        read_conv1x1(L.h1x1, A.bottleneck, A.h1x1_out, true, A.h1x1_groups, &ws);
+      const int dims[F_COUNT] = {A.channels, zrows, A.condition_size, zrows, zrows, A.bottleneck, A.channels,
+                                 A.h1x1_out};
+      for (int f = 0; f < F_COUNT; f++)
+      {
+        FilmSpec& fs = L.film[f];
+        fs.active = films[i][f].active;
+        if (f == F_L1X1_POST && !A.l1x1_active)
+          fs.active = false;
+        if (f == F_H1X1_POST && !A.h1x1_active)
+          fs.active = false;
+        if (!fs.active)
+          continue;
+        fs.shift = films[i][f].shift;
+        fs.groups = films[i][f].groups;
+        fs.dim = dims[f];
+        read_conv1x1(fs.css, A.condition_size, (fs.shift ? 2 : 1) * fs.dim, true, fs.groups, &ws);
+      }
+      A.layers.push_back(std::move(L));
+    }
+    // LayerArray ctor (model.cpp:397-400): Conv1D(head_out_size -> head_size, head_kernel, head_bias, head_dilation)
+    read_conv1d(A.head_rechannel, A.head_out_size(), A.head_size, A.head_kernel, A.head_bias, A.head_dilation, 1, &ws);
+  }
+  if (wn.with_head)
+  {
+    int cin = ph.in_channels;
+    for (size_t i = 0; i < ph_kernels.size(); i++)
+    {
+      const int cout = (i + 1 == ph_kernels.size()) ? ph.out_channels : ph.channels;
+      Conv1DW c;
+      read_conv1d(c, cin, cout, ph_kernels[i], true, 1, 1, &ws);
+      ph.convs.push_back(std::move(c));
+      cin = cout;
+    }
+  }
+  wn.head_scale = ws.next();
+  if (ws.position() != ws.size())
+    throw std::runtime_error("Weight mismatch: assigned " + std::to_string(ws.position()) + " weights, but "
+                             + std::to_string(ws.size()) + " were provided.");
+
+  ms.in_channels = wn.in_channels;
+  ms.out_channels = wn.with_head ? ph.out_channels : wn.arrays.back().head_size;
+  // model.cpp:653-658
+  long pw = wn.condition_dsp ? wn.condition_dsp->prewarm_samples : 1;
+  for (const auto& A : wn.arrays)
+    pw += A.receptive_field();
+  if (wn.with_head)
+  {
+    long rf = 1;
+    for (const auto& c : ph.convs)
+      rf += c.kernel - 1;
+    pw += rf - 1;
+  }
+  ms.prewarm_samples = (int)pw;
+}
+
+void build_lstm(ModelSpec& ms, const json::Value& config, const std::vector<float>& weights)
+{
+  LstmSpec& ls = ms.lstm;
+  ls.num_layers = config.at("num_layers").as_int("num_layers");
+  ls.input_size = config.at("input_size").as_int("input_size");
+  ls.hidden = config.at("hidden_size").as_int("hidden_size");
+  ms.in_channels = config.value_int("in_channels", 1);
+  ms.out_channels = config.value_int("out_channels", 1);
+  if (ls.num_layers < 0 || ls.hidden <= 0 || ls.input_size <= 0)
+    throw std::runtime_error("LSTM: bad configuration");
+  WeightStream ws(weights);
+  const int H = ls.hidden;
+  for (int l = 0; l < ls.num_layers; l++)
+  {
+    LstmCellW c;
+    c.input_size = (l == 0) ? ls.input_size : H;
+    c.hidden = H;
+    const int W = c.input_size + H;
+    c.w.resize((size_t)4 * H * W);
+    for (auto& v : c.w)
+      v = ws.next();
+    c.b.resize((size_t)4 * H);
+    for (auto& v : c.b)
+      v = ws.next();
+    c.h0.resize(H);
+    for (auto& v : c.h0)
+      v = ws.next();
+    c.c0.resize(H);
+    for (auto& v : c.c0)
+      v = ws.next();
+    ls.cells.push_back(std::move(c));
+  }
+  ls.head_w.resize((size_t)ms.out_channels * H);
+  for (auto& v : ls.head_w)
+    v = ws.next();
+  ls.head_b.resize((size_t)ms.out_channels);
+  for (auto& v : ls.head_b)
+    v = ws.next();
+  if (ws.position() != ws.size())
+    throw std::runtime_error("LSTM weight mismatch: assigned " + std::to_string(ws.position()) + " weights, but "
+                             + std::to_string(ws.size()) + " were provided.");
+  // lstm.cpp:127-134
+  const int pw = (int)(0.5 * ms.sample_rate);
+  ms.prewarm_samples = pw <= 0 ? 1 : pw;
+}
+
+void build_linear(ModelSpec& ms, const json::Value& config, const std::vector<float>& weights)
+{
+  LinearSpec& li = ms.linear;
+  li.receptive_field = config.at("receptive_field").as_int("receptive_field");
+  li.bias = config.at("bias").as_bool("bias");
+  ms.in_channels = config.value_int("in_channels", 1);
+  ms.out_channels = config.value_int("out_channels", 1);
+  if (li.receptive_field <= 0)
+    throw std::runtime_error("Linear: receptive_field must be positive");
+  if ((int)weights.size() != li.receptive_field + (li.bias ? 1 : 0))
+    throw std::runtime_error("Params vector does not match expected size based on architecture parameters");
+  li.impulse.assign(weights.begin(), weights.begin() + li.receptive_field);
+  li.bias_value = li.bias ? weights[li.receptive_field] : 0.0f;
+  ms.prewarm_samples = 0;
+}
+
+ModelSpec build_spec(const json::Value& root, const LoadOptions& opts)
+{
+  if (!root.is_object())
+    throw std::runtime_error("Invalid .nam: root JSON value must be an object.");
+  static const char* required[] = {"version", "architecture", "config", "weights"};
+  for (const char* key : required)
+    if (!root.contains(key))
+      throw std::runtime_error(std::string("Invalid .nam: missing required key \"") + key + "\".");
+  ModelSpec ms;
+  ms.version = root.at("version").as_string("version");
+  const VersionSupport sup = version_support(ms.version);
+  if (sup == VersionSupport::No)
+    throw std::runtime_error("Model config is an unsupported version " + ms.version + ".");
+  if (sup == VersionSupport::Partial)
+    std::cerr << "Model config is a partially-supported version " << ms.version << ". Continuing with partial support."
+              << std::endl;
+  ms.architecture = root.at("architecture").as_string("architecture");
+  ms.sample_rate = root.contains("sample_rate") ? root.at("sample_rate").as_double("sample_rate") : -1.0;
+  std::vector<float> weights;
+  {
+    const auto& wj = root.at("weights").items("weights");
+    weights.reserve(wj.size());
+    for (const auto& v : wj)
+      weights.push_back((float)v.as_double("weights[]"));
+  }
+  ms.n_weights = weights.size();
+  const json::Value& md = root.get("metadata");
+  if (md.is_object())
+  {
+    auto extract = [&md](const char* key) -> std::optional<double> {
+      if (md.contains(key) && !md.at(key).is_null())
+        return md.at(key).as_double(key);
+      return std::nullopt;
+    };
+    ms.loudness = extract("loudness");
+    ms.input_level = extract("input_level_dbu");
+    ms.output_level = extract("output_level_dbu");
+  }
+  const json::Value& config = root.at("config");
+  if (ms.architecture == "WaveNet")
+  {
+    ms.arch = Arch::WaveNet;
+    build_wavenet(ms, config, weights, opts);
+  }
+  else if (ms.architecture == "LSTM")
+  {
+    ms.arch = Arch::LSTM;
+    build_lstm(ms, config, weights);
+  }
+  else if (ms.architecture == "Linear")
+  {
+    ms.arch = Arch::Linear;
+    build_linear(ms, config, weights);
+  }
+  else
+    throw std::runtime_error("No config parser registered for architecture: " + ms.architecture);
+  if (ms.in_channels <= 0 || ms.out_channels <= 0)
+    throw std::runtime_error("Channel counts must be positive");
+  return ms;
+}
+
+} // namespace
+
+long ArraySpec::receptive_field() const
+{
+  long r = 0;
+  for (const auto& L : layers)
+    r += L.conv.lookback();
+  r += head_rechannel.lookback();
+  return r;
+}
+
+// NAM/get_dsp.cpp:18-39; versions: 0.5.0 <= v, same major/minor <= 0.7, later patch = partial
+VersionSupport version_support(const std::string& version)
+{
+  int parts[3] = {0, 0, 0};
+  size_t pos = 0;
+  for (int p = 0; p < 3; p++)
+  {
+    if (pos >= version.size() || !std::isdigit((unsigned char)version[pos]))
+      return VersionSupport::No;
+    long v = 0;
+    while (pos < version.size() && std::isdigit((unsigned char)version[pos]))
+    {
+      v = v * 10 + (version[pos] - '0');
+      if (v > 1000000)
+        return VersionSupport::No;
+      pos++;
+    }
+    parts[p] = (int)v;
+    if (p < 2)
+    {
+      if (pos >= version.size() || version[pos] != '.')
+        return VersionSupport::No;
+      pos++;
+    }
+  }
+  if (pos != version.size())
+    return VersionSupport::No;
+  const int latest[3] = {0, 7, 0}, earliest[3] = {0, 5, 0};
+  auto less = [](const int* a, const int* b) {
+    return a[0] < b[0] || (a[0] == b[0] && (a[1] < b[1] || (a[1] == b[1] && a[2] < b[2])));
+  };
+  if (less(parts, earliest))
+    return VersionSupport::No;
+  if (parts[0] > latest[0] || parts[1] > latest[1])
+    return VersionSupport::No;
+  if (less(latest, parts))
+    return VersionSupport::Partial;
+  return VersionSupport::Yes;
+}
+
+ModelSpec model_spec_from_json(const json::Value& root, const LoadOptions& opts)
+{
+  return build_spec(root, opts);
+}
+
+ModelSpec model_spec_from_text(const std::string& text, const LoadOptions& opts)
+{
+  return build_spec(json::Value::parse(text), opts);
+}
+
+ModelSpec model_spec_from_file(const std::string& path, const LoadOptions& opts)
+{
+  std::ifstream in(path, std::ios::binary);
+  if (!in.is_open())
+  {
+    std::ifstream probe(path);
+    throw NamFileValidationError("Could not validate .nam file [" + path + "]: "
+                                 + (probe.good() ? "file could not be read." : "file does not exist."));
+  }
+  std::stringstream ss;
+  ss << in.rdbuf();
+  json::Value root;
+  try
+  {
+    root = json::Value::parse(ss.str());
+  }
+  catch (const json::ParseError& e)
+  {
+    throw NamFileValidationError("Could not parse .nam file [" + path + "]: " + e.what());
+  }
+  if (!root.is_object())
+    throw NamFileValidationError("Invalid .nam file [" + path + "]: root JSON value must be an object.");
+  static const char* required[] = {"version", "architecture", "config", "weights"};
+  for (const char* key : required)
+    if (!root.contains(key))
+      throw NamFileValidationError("Invalid .nam file [" + path + "]: missing required key \"" + key + "\".");
+  return build_spec(root, opts);
+}
+
+} // namespace namb200

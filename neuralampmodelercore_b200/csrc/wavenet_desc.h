@@ -1,0 +1,66 @@
+// wavenet_desc.h -- plain-data descriptors shared by the host packer (wavenet_pack.cpp, compiled
+// by the host compiler) and the fused kernel (wavenet_fused.cuh, compiled by nvcc).
+#pragma once
+
+#include <stdint.h>
+
+namespace namb200
+{
+
+constexpr int kMaxLayers = 64;
+constexpr int kMaxArrays = 4;
+constexpr int kHalo = 64; // columns of left halo kept in the shared tile
+
+// Activation codes follow ActType (nam_model_spec.h)
+enum : int
+{
+  KACT_TANH = 0,
+  KACT_HARDTANH = 1,
+  KACT_FASTTANH = 2,
+  KACT_RELU = 3,
+  KACT_LEAKYRELU = 4,
+  KACT_PRELU = 5,
+  KACT_SIGMOID = 6,
+  KACT_SILU = 7,
+  KACT_HARDSWISH = 8,
+  KACT_LEAKYHARDTANH = 9,
+  KACT_SOFTSIGN = 10,
+  KACT_IDENTITY = 100
+};
+
+struct LayerDesc
+{
+  int w_off; // float offset in the weight blob: conv[K][C][C] | b[C] | M[C] | P[C][C] | p[C] | slopes[C]
+  int kernel, dilation;
+  int lookback; // (K-1)*dilation
+  int ring_off; // float offset of this layer's ring inside one stream's state: [C/4][R][4]
+  int ring_mask; // R-1, R = power of two >= lookback
+  int act;
+  float ap0, ap1, ap2, ap3;
+};
+
+struct ArrayDesc
+{
+  int layer0, n_layers;
+  int rech_off; // [CIN][C]
+  int head_off; // [C][HOUT] | bias[HOUT]
+};
+
+struct WaveNetKernelParams
+{
+  const float* weights; // packed blob
+  int n_weight_floats;
+  float* state; // [batch][state_stride]
+  long state_stride; // floats
+  const float* in; // [batch][in_stride]
+  float* out;
+  long in_stride, out_stride;
+  int batch, n_frames;
+  uint32_t t_base; // absolute frame index of in[:,0] (mod 2^32)
+  float head_scale;
+  int n_arrays;
+  ArrayDesc arrays[kMaxArrays];
+  LayerDesc layers[kMaxLayers];
+};
+
+} // namespace namb200

@@ -1,0 +1,449 @@
+// wavenet_fused.cuh -- the fused WaveNet layer-array kernel for sm_100a.
+//
+// What it replaces (reference file:line, all under NAM/):
+//   wavenet/model.cpp:822-910   WaveNet::process            (whole kernel)
+//   wavenet/model.cpp:463-549   LayerArray::Process{,Inner} (array_forward)
+//   wavenet/model.cpp:183-393   Layer::Process, non-gated / no-FiLM / no-head1x1 path
+//   conv1d.cpp:163-183,666-683,769-774  Conv1D::Process     (tap loop, history)
+//   ring_buffer.cpp:7-109       RingBuffer                  (per-stream device rings)
+//   dsp.cpp:436-836             Conv1x1::process_           (rechannel / mixin / layer1x1 / head)
+//   activations.h:59-133        scalar activations
+//
+// Reframing (not a port): the reference walks ONE stream, layer by layer, over a 64-frame
+// block with ~65 small GEMM calls.  Here one CTA owns one stream at a time and a tile of
+// T = S*NT consecutive frames; THREAD t owns time steps {t, t+NT, ...} for the whole depth of
+// the network.  With that mapping everything in a layer except the dilated taps is
+// thread-local -- conv accumulate, +mixin, activation, head accumulate, 1x1, residual -- so
+// activations never leave registers, and the only cross-thread traffic is "my column of the
+// layer input" -> shared memory -> "columns t-d, t-2d of other threads".  Taps that reach
+// behind the tile come from the stream's history rings in global memory; a persistent CTA
+// keeps one stream's rings (196 KB for the standard model) L2-resident while it works
+// through that stream's frames.
+//
+// Data layout: activations everywhere are "planes of 4 channels": [C/4][time][4 floats], so a
+// thread's 16-byte vector load of (time, 4 channels) is contiguous across the warp's 32
+// consecutive time steps (conflict-free LDS.128 / fully coalesced LDG.128), at ANY tap
+// offset.  Weights live in shared memory as [in][out] rows so one warp-uniform LDS.128 yields 4
+// output-channel weights, consumed by packed FFMA2 (fma.rn.f32x2: two output channels per
+// instruction, input sample broadcast).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "wavenet_desc.h"
+
+namespace namb200
+{
+
+// ---- activations ---------------------------------------------------------------------------
+// fast_tanh: the reference's rational approximation (activations.h:91-98).  The quotient uses
+// MUFU.RCP (__fdividef, <= 2 ulp) instead of an IEEE division; measured against the oracle in
+// tests/test_parity_gpu.py.
+__device__ __forceinline__ float act_fast_tanh(float x)
+{
+  const float ax = fabsf(x);
+  const float x2 = x * x;
+  const float num = x * (2.45550750702956f + 2.45550750702956f * ax + (0.893229853513558f + 0.821226666969744f * ax) * x2);
+  const float den = 2.44506634652299f + (2.44506634652299f + x2) * fabsf(x + 0.814642734961073f * x * ax);
+  return __fdividef(num, den);
+}
+
+// sigmoid(x) = 1/(1+expf(-x)) (activations.h:64-67); the quotient via MUFU.RCP (<= 2 ulp) so the
+// kernel stays free of division slow-path subroutine calls.
+__device__ __forceinline__ float act_sigmoid(float x)
+{
+  return __fdividef(1.0f, 1.0f + expf(-x));
+}
+
+template <int N>
+__device__ __forceinline__ void apply_activation(float (&v)[N], const LayerDesc& L, const float* __restrict__ slopes)
+{
+  switch (L.act)
+  {
+    case KACT_TANH:
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        v[i] = tanhf(v[i]);
+      break;
+    case KACT_FASTTANH:
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        v[i] = act_fast_tanh(v[i]);
+      break;
+    case KACT_HARDTANH:
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        v[i] = fminf(fmaxf(v[i], -1.0f), 1.0f);
+      break;
+    case KACT_RELU:
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        v[i] = v[i] > 0.0f ? v[i] : 0.0f;
+      break;
+    case KACT_LEAKYRELU:
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        v[i] = v[i] > 0.0f ? v[i] : L.ap0 * v[i];
+      break;
+    case KACT_PRELU:
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        v[i] = v[i] > 0.0f ? v[i] : slopes[i] * v[i];
+      break;
+    case KACT_SIGMOID:
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        v[i] = act_sigmoid(v[i]);
+      break;
+    case KACT_SILU:
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        v[i] = v[i] * act_sigmoid(v[i]);
+      break;
+    case KACT_HARDSWISH:
+#pragma unroll
+      for (int i = 0; i < N; i++)
+      {
+        const float t = v[i] + 3.0f;
+        const float cl = t < 0.0f ? 0.0f : (t > 6.0f ? 6.0f : t);
+        v[i] = v[i] * cl * (1.0f / 6.0f);
+      }
+      break;
+    case KACT_LEAKYHARDTANH:
+#pragma unroll
+      for (int i = 0; i < N; i++)
+      {
+        const float x = v[i];
+        v[i] = x < L.ap0 ? (x - L.ap0) * L.ap2 + L.ap0 : (x > L.ap1 ? (x - L.ap1) * L.ap3 + L.ap1 : x);
+      }
+      break;
+    case KACT_SOFTSIGN:
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        v[i] = __fdividef(v[i], 1.0f + fabsf(v[i]));
+      break;
+    default: break;
+  }
+}
+
+// ---- small helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_ring(const float4* p)
+{
+  return __ldcg(p); // L2 only: ring lines are written by this CTA and re-read tiles later
+}
+__device__ __forceinline__ void st_ring(float4* p, const float4& v)
+{
+  __stcg(p, v);
+}
+
+// acc[o] += w_row[o] * x for C outputs, two per FFMA2.
+template <int C>
+__device__ __forceinline__ void axpy_row(float2 (&acc)[C / 2], const float* __restrict__ w_row, const float x)
+{
+  const float2 xx = make_float2(x, x);
+#pragma unroll
+  for (int q = 0; q < C / 4; q++)
+  {
+    const float4 w = *reinterpret_cast<const float4*>(w_row + 4 * q);
+    acc[2 * q] = __ffma2_rn(make_float2(w.x, w.y), xx, acc[2 * q]);
+    acc[2 * q + 1] = __ffma2_rn(make_float2(w.z, w.w), xx, acc[2 * q + 1]);
+  }
+}
+
+// One layer array for the S time steps a thread owns.
+//   CIN  : channels of the array input (1 for the first array: the raw sample)
+//   C    : channels == bottleneck (padded to a multiple of 4)
+//   HOUT : rows of the head output (next array's C, or 1 for the last array)
+template <int CIN, int C, int HOUT, int S, int NT>
+__device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, const ArrayDesc& A,
+                                              const float* __restrict__ sw, float4* __restrict__ tile,
+                                              float* __restrict__ state, const uint32_t tabs0, const int Tv,
+                                              const float (&hin)[S][CIN], const float (&cond)[S],
+                                              float2 (&head)[S][C / 2], float (&hout)[S][C],
+                                              float (&headout)[S][HOUT])
+{
+  constexpr int T = S * NT;
+  constexpr int TW = kHalo + T; // columns per plane in the shared tile
+  constexpr int P = C / 4; // planes
+  const int tid = threadIdx.x;
+
+  // ---- rechannel (Conv1x1, no bias; model.cpp:492) -> this thread's columns of the tile
+#pragma unroll
+  for (int j = 0; j < S; j++)
+  {
+    float2 h[C / 2];
+#pragma unroll
+    for (int q = 0; q < C / 2; q++)
+      h[q] = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int i = 0; i < CIN; i++)
+      axpy_row<C>(h, sw + A.rech_off + i * C, hin[j][i]);
+#pragma unroll
+    for (int pl = 0; pl < P; pl++)
+      tile[pl * TW + kHalo + j * NT + tid] = make_float4(h[2 * pl].x, h[2 * pl].y, h[2 * pl + 1].x, h[2 * pl + 1].y);
+  }
+
+#pragma unroll 1
+  for (int li = 0; li < A.n_layers; li++)
+  {
+    const LayerDesc& L = p.layers[A.layer0 + li];
+    const float* __restrict__ w = sw + L.w_off;
+    const float* __restrict__ w_bias = w + L.kernel * C * C;
+    const float* __restrict__ w_mix = w_bias + C;
+    const float* __restrict__ w_p = w_mix + C;
+    const float* __restrict__ w_pb = w_p + C * C;
+    const float* __restrict__ w_slopes = w_pb + C;
+    float4* __restrict__ ring = reinterpret_cast<float4*>(state + L.ring_off);
+    const int R = L.ring_mask + 1;
+    const int halo = (L.lookback <= kHalo) ? L.lookback : 0;
+
+    // ---- phase 0: small-dilation layers pull their history [t0-L, t0) into the halo
+    for (int idx = tid; idx < halo * P; idx += NT)
+    {
+      const int pl = idx / halo, col = idx - pl * halo;
+      tile[pl * TW + kHalo - halo + col] = ld_ring(ring + pl * R + ((tabs0 - (uint32_t)halo + (uint32_t)col) & L.ring_mask));
+    }
+    __syncthreads(); // B0: tile columns (previous layer's phase 2) + halo are visible
+
+    // ---- phase 1: z = b + M c + sum_k W_k h[t-(K-1-k)d] ; a = act(z) ; head += a
+    float2 acc[S][C / 2];
+#pragma unroll
+    for (int j = 0; j < S; j++)
+    {
+#pragma unroll
+      for (int q = 0; q < C / 2; q++)
+        acc[j][q] = *reinterpret_cast<const float2*>(w_bias + 2 * q);
+      axpy_row<C>(acc[j], w_mix, cond[j]);
+    }
+#pragma unroll 1
+    for (int k = 0; k < L.kernel; k++)
+    {
+      const int off = (L.kernel - 1 - k) * L.dilation;
+      const float* __restrict__ wk = w + k * C * C;
+#pragma unroll 1
+      for (int pl = 0; pl < P; pl++)
+      {
+        float4 xq[S];
+#pragma unroll
+        for (int j = 0; j < S; j++)
+        {
+          const int rel = j * NT + tid - off;
+          if (rel >= -halo)
+            xq[j] = tile[pl * TW + kHalo + rel];
+          else
+            xq[j] = ld_ring(ring + pl * R + ((tabs0 + (uint32_t)rel) & L.ring_mask));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+          const float* __restrict__ w_row = wk + (pl * 4 + i) * C;
+#pragma unroll
+          for (int j = 0; j < S; j++)
+          {
+            const float xs = (i == 0) ? xq[j].x : (i == 1) ? xq[j].y : (i == 2) ? xq[j].z : xq[j].w;
+            axpy_row<C>(acc[j], w_row, xs);
+          }
+        }
+      }
+    }
+    float a[S][C];
+#pragma unroll
+    for (int j = 0; j < S; j++)
+    {
+#pragma unroll
+      for (int q = 0; q < C / 2; q++)
+      {
+        a[j][2 * q] = acc[j][q].x;
+        a[j][2 * q + 1] = acc[j][q].y;
+      }
+      apply_activation<C>(a[j], L, w_slopes);
+#pragma unroll
+      for (int q = 0; q < C / 2; q++)
+        head[j][q] = __fadd2_rn(head[j][q], make_float2(a[j][2 * q], a[j][2 * q + 1])); // model.cpp:530
+    }
+    __syncthreads(); // B1: every tap read of this layer's input is done
+
+    // ---- phase 2: persist the tail of h_l, then h_{l+1} = h_l + p + P a  (model.cpp:243,376)
+    const bool last = (li + 1 == A.n_layers);
+    float2 hn[S][C / 2];
+#pragma unroll
+    for (int j = 0; j < S; j++)
+    {
+      const int trel = j * NT + tid;
+      const bool keep = (trel < Tv) && (trel >= Tv - L.lookback);
+#pragma unroll
+      for (int pl = 0; pl < P; pl++)
+      {
+        const float4 own = tile[pl * TW + kHalo + trel];
+        if (keep)
+          st_ring(ring + pl * R + ((tabs0 + (uint32_t)trel) & L.ring_mask), own);
+        const float4 pb = *reinterpret_cast<const float4*>(w_pb + 4 * pl);
+        hn[j][2 * pl] = make_float2(own.x + pb.x, own.y + pb.y);
+        hn[j][2 * pl + 1] = make_float2(own.z + pb.z, own.w + pb.w);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < C; i++)
+    {
+      const float* __restrict__ w_row = w_p + i * C;
+#pragma unroll
+      for (int j = 0; j < S; j++)
+        axpy_row<C>(hn[j], w_row, a[j][i]);
+    }
+#pragma unroll
+    for (int j = 0; j < S; j++)
+    {
+      const int trel = j * NT + tid;
+      if (!last)
+      {
+#pragma unroll
+        for (int pl = 0; pl < P; pl++)
+          tile[pl * TW + kHalo + trel] =
+            make_float4(hn[j][2 * pl].x, hn[j][2 * pl].y, hn[j][2 * pl + 1].x, hn[j][2 * pl + 1].y);
+      }
+      else
+      {
+#pragma unroll
+        for (int q = 0; q < C / 2; q++)
+        {
+          hout[j][2 * q] = hn[j][q].x;
+          hout[j][2 * q + 1] = hn[j][q].y;
+        }
+      }
+    }
+  }
+
+  // ---- head rechannel (kernel size 1; model.cpp:548): headout = H head (+ g)
+  const float* __restrict__ wh = sw + A.head_off;
+#pragma unroll
+  for (int j = 0; j < S; j++)
+  {
+    if constexpr (HOUT == 1)
+    {
+      float s = 0.0f;
+#pragma unroll
+      for (int q = 0; q < C / 2; q++)
+      {
+        s = fmaf(wh[2 * q], head[j][q].x, s);
+        s = fmaf(wh[2 * q + 1], head[j][q].y, s);
+      }
+      headout[j][0] = s + wh[C];
+    }
+    else
+    {
+      float2 ho[HOUT / 2];
+#pragma unroll
+      for (int q = 0; q < HOUT / 2; q++)
+        ho[q] = make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int q = 0; q < C / 2; q++)
+      {
+        axpy_row<HOUT>(ho, wh + (2 * q) * HOUT, head[j][q].x);
+        axpy_row<HOUT>(ho, wh + (2 * q + 1) * HOUT, head[j][q].y);
+      }
+#pragma unroll
+      for (int q = 0; q < HOUT / 2; q++)
+      {
+        const float2 g = *reinterpret_cast<const float2*>(wh + C * HOUT + 2 * q);
+        headout[j][2 * q] = ho[q].x + g.x;
+        headout[j][2 * q + 1] = ho[q].y + g.y;
+      }
+    }
+  }
+}
+
+// One persistent CTA per stream-slot.  C1 == 0: single layer array.
+template <int C0, int C1, int S, int NT>
+__global__ void __launch_bounds__(NT) wavenet_fused_kernel(const __grid_constant__ WaveNetKernelParams p)
+{
+  constexpr int T = S * NT;
+  constexpr int CMAX = (C0 > C1) ? C0 : C1;
+  constexpr int TW = kHalo + T;
+  extern __shared__ float4 smem4[];
+  float* sw = reinterpret_cast<float*>(smem4);
+  float4* tile = smem4 + (p.n_weight_floats + 3) / 4;
+  (void)CMAX;
+  (void)TW;
+
+  const int tid = threadIdx.x;
+  // weights -> shared memory, once per CTA
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.weights);
+    for (int i = tid; i < (p.n_weight_floats + 3) / 4; i += NT)
+      smem4[i] = __ldg(src + i);
+  }
+  __syncthreads();
+
+  for (int stream = blockIdx.x; stream < p.batch; stream += gridDim.x)
+  {
+    float* __restrict__ state = p.state + (size_t)stream * p.state_stride;
+    const float* __restrict__ xin = p.in + (size_t)stream * p.in_stride;
+    float* __restrict__ yout = p.out + (size_t)stream * p.out_stride;
+
+    for (int t0 = 0; t0 < p.n_frames; t0 += T)
+    {
+      const int Tv = min(T, p.n_frames - t0);
+      const uint32_t tabs0 = p.t_base + (uint32_t)t0;
+      float x[S][1], cond[S];
+#pragma unroll
+      for (int j = 0; j < S; j++)
+      {
+        const int trel = j * NT + tid;
+        x[j][0] = (trel < Tv) ? __ldg(xin + t0 + trel) : 0.0f;
+        cond[j] = x[j][0]; // no condition_dsp: condition == input (model.cpp:781)
+      }
+      float y[S];
+      if constexpr (C1 == 0)
+      {
+        float2 head0[S][C0 / 2];
+#pragma unroll
+        for (int j = 0; j < S; j++)
+#pragma unroll
+          for (int q = 0; q < C0 / 2; q++)
+            head0[j][q] = make_float2(0.0f, 0.0f); // model.cpp:469
+        float hout0[S][C0], ho0[S][1];
+        array_forward<1, C0, 1, S, NT>(p, p.arrays[0], sw, tile, state, tabs0, Tv, x, cond, head0, hout0, ho0);
+#pragma unroll
+        for (int j = 0; j < S; j++)
+          y[j] = ho0[j][0];
+      }
+      else
+      {
+        float hout0[S][C0], ho0[S][C1];
+        {
+          float2 head0[S][C0 / 2];
+#pragma unroll
+          for (int j = 0; j < S; j++)
+#pragma unroll
+            for (int q = 0; q < C0 / 2; q++)
+              head0[j][q] = make_float2(0.0f, 0.0f);
+          array_forward<1, C0, C1, S, NT>(p, p.arrays[0], sw, tile, state, tabs0, Tv, x, cond, head0, hout0, ho0);
+        }
+        // second array: layer input = previous array's layer output, head accumulator starts from
+        // the previous array's head output (model.cpp:846-848, :473-486)
+        float2 head1[S][C1 / 2];
+#pragma unroll
+        for (int j = 0; j < S; j++)
+#pragma unroll
+          for (int q = 0; q < C1 / 2; q++)
+            head1[j][q] = make_float2(ho0[j][2 * q], ho0[j][2 * q + 1]);
+        float hout1[S][C1], ho1[S][1];
+        array_forward<C0, C1, 1, S, NT>(p, p.arrays[1], sw, tile, state, tabs0, Tv, hout0, cond, head1, hout1, ho1);
+#pragma unroll
+        for (int j = 0; j < S; j++)
+          y[j] = ho1[j][0];
+      }
+#pragma unroll
+      for (int j = 0; j < S; j++)
+      {
+        const int trel = j * NT + tid;
+        if (trel < Tv)
+          yout[t0 + trel] = p.head_scale * y[j]; // model.cpp:888-897
+      }
+    }
+    __syncthreads(); // the next stream reuses the tile
+  }
+}
+
+} // namespace namb200

@@ -1980,3 +1980,49 @@ int nam_oracle_gating(int mode, int act_type, const float* act_params, int n_act
   act_free(&s);
   return 0;
 }
+
+/* One WaveNet Layer in isolation (model.cpp:183-393), for the reference's layer-level pins
+ * (tools/test/test_wavenet/test_layer.cpp).  cfg = array params (as in the model cfg: 15 ints +
+ * 8 x 3 FiLM ints), then kernel, dilation, gating_mode, ACT, SECONDARY_ACT.  Zero history. */
+int nam_oracle_layer(const int32_t* cfg, int n_cfg, const float* fparams, int n_fparams, const float* weights,
+                     int n_weights, const float* in, const float* cond, float* out_next, float* out_head, int n,
+                     int fast_tanh)
+{
+  cursor_t c;
+  memset(&c, 0, sizeof(c));
+  c.cfg = cfg;
+  c.n_cfg = n_cfg;
+  c.fp = fparams;
+  c.n_fp = n_fparams;
+  c.w = weights;
+  c.n_w = n_weights;
+  array_params_t p;
+  if (parse_array_params(&p, &c))
+    return -1;
+  const int kernel = take_i(&c), dilation = take_i(&c), gating = take_i(&c);
+  layer_t L;
+  if (layer_init(&L, &p, kernel, dilation, gating, &c))
+  {
+    layer_free(&L);
+    return -1;
+  }
+  if (c.failed)
+  {
+    set_err("layer config stream truncated");
+    layer_free(&L);
+    return -1;
+  }
+  layer_set_weights(&L, &c);
+  if (c.failed || c.i_w != n_weights)
+  {
+    set_err("Layer weight count mismatch: consumed %d of %d", c.i_w, n_weights);
+    layer_free(&L);
+    return -1;
+  }
+  layer_set_max_buffer(&L, n);
+  layer_process(&L, in, cond, n, fast_tanh);
+  memcpy(out_next, L.out_next, sizeof(float) * (size_t)L.channels * n);
+  memcpy(out_head, L.out_head, sizeof(float) * (size_t)L.head_rows * n);
+  layer_free(&L);
+  return 0;
+}

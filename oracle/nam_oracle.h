@@ -91,6 +91,13 @@ int nam_oracle_activation(int type, const float* params, int n_params, int fast_
 int nam_oracle_gating(int mode, int act_type, const float* act_params, int n_act_params, int sec_type,
                       const float* sec_params, int n_sec_params, int channels, const float* in, float* out, int n);
 
+/* One WaveNet Layer (NAM/wavenet/model.cpp:183-393) from a zero history.  cfg = the per-array ints of
+ * the model cfg (15 + 8x3), then kernel, dilation, gating_mode, ACT, SECONDARY_ACT.
+ * out_next is (channels x n), out_head is (bottleneck or head1x1.out_channels x n). */
+int nam_oracle_layer(const int32_t* cfg, int n_cfg, const float* fparams, int n_fparams, const float* weights,
+                     int n_weights, const float* in, const float* cond, float* out_next, float* out_head, int n,
+                     int fast_tanh);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,8 @@ def _declare(lib: C.CDLL) -> C.CDLL:
     lib.nam_oracle_activation.argtypes = [C.c_int, f32p, C.c_int, C.c_int, f32p, C.c_int, C.c_int]
     lib.nam_oracle_gating.restype = C.c_int
     lib.nam_oracle_gating.argtypes = [C.c_int, C.c_int, f32p, C.c_int, C.c_int, f32p, C.c_int, C.c_int, f32p, f32p, C.c_int]
+    lib.nam_oracle_layer.restype = C.c_int
+    lib.nam_oracle_layer.argtypes = [i32p, C.c_int, f32p, C.c_int, f32p, C.c_int, f32p, f32p, f32p, f32p, C.c_int, C.c_int]
     return lib
 
 
@@ -205,7 +207,7 @@ class OracleModel:
 # ---- module-level helpers (column-major (channels x frames) numpy arrays in "F" order) --------------------------
 def _cm(a: np.ndarray) -> np.ndarray:
     """(channels, frames) array -> flat column-major float32 buffer."""
-    return np.ascontiguousarray(np.asarray(a, dtype=np.float32).T).ravel()
+    return np.array(np.asarray(a, dtype=np.float32).T, dtype=np.float32, order="C", copy=True).ravel()
 
 
 def _from_cm(buf: np.ndarray, channels: int, frames: int) -> np.ndarray:
@@ -283,3 +285,37 @@ def gating(x, mode: str, act, sec_act, channels: int, lib=None) -> np.ndarray:
     _check(lib.nam_oracle_gating({"gated": 1, "blended": 2}[mode], c1, _fp(p1), len(p1), c2, _fp(p2), len(p2), channels,
                                  _fp(xin), _fp(out), n), lib)
     return _from_cm(out, channels, n)
+
+
+def layer(x, cond, weights, *, condition_size=1, channels=1, bottleneck=None, kernel_size=1, dilation=1,
+          activation="ReLU", gating_mode="none", secondary_activation=None, groups_input=1, groups_input_mixin=1,
+          layer1x1=(True, 1), head1x1=(False, None, 1), films=None, fast_tanh=False, lib=None):
+    """One Layer (reference make_layer() in tools/test/test_wavenet/test_layer.cpp) from zero history.
+    Returns (output_next_layer [channels, n], output_head [rows, n])."""
+    lib = lib or load_lib()
+    bottleneck = channels if bottleneck is None else bottleneck
+    h1_active, h1_out, h1_groups = head1x1
+    h1_out = channels if h1_out is None else h1_out
+    films = films or {}
+    cfg: list = [1, condition_size, channels, bottleneck, 1, 1, 1, 0, groups_input, groups_input_mixin,
+                 int(layer1x1[0]), layer1x1[1], int(h1_active), h1_out, h1_groups]
+    for key in nam_config.FILM_KEYS:
+        a, s, g = films.get(key, (0, 0, 1))
+        cfg += [int(a), int(s), int(g)]
+    cfg += [kernel_size, dilation, nam_config.GATING[gating_mode]]
+    fp: list = []
+    nam_config._act(activation, cfg, fp)
+    nam_config._act(secondary_activation, cfg, fp)
+    x = np.asarray(x, dtype=np.float32).reshape(channels, -1)
+    n = x.shape[1]
+    cond = np.asarray(cond, dtype=np.float32).reshape(condition_size, -1)
+    cfg_a = np.asarray(cfg, dtype=np.int32)
+    fp_a = np.asarray(fp, dtype=np.float32)
+    w = np.ascontiguousarray(weights, dtype=np.float32)
+    head_rows = h1_out if h1_active else bottleneck
+    xin, cin = _cm(x), _cm(cond)
+    o_next = np.zeros(channels * n, dtype=np.float32)
+    o_head = np.zeros(head_rows * n, dtype=np.float32)
+    _check(lib.nam_oracle_layer(cfg_a.ctypes.data_as(i32p), len(cfg_a), _fp(fp_a), len(fp_a), _fp(w), len(w), _fp(xin),
+                                _fp(cin), _fp(o_next), _fp(o_head), n, int(fast_tanh)), lib)
+    return _from_cm(o_next, channels, n), _from_cm(o_head, head_rows, n)
