@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the NAM inference hot path on B200 (one JSON line, driver contract).
+
+Workload (BASELINE.json metric): wavenet_a1_standard.nam, batch 4096 independent 48 kHz streams per GPU,
+float32.  A "step" is ONE pass of the hot path over one batch of synthetic input: 4096 streams x
+`--frames` frames (default 4096), state carried across steps in HBM exactly like successive
+DSP::process() calls.  Weak scaling: every GPU runs its own 4096 streams (no data-path collective; the
+streams are independent).
+
+  value      Msamples/s, whole job, inputs/outputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the public host API (nam_b200_process_f32 with pinned host buffers:
+             H2D + kernel + D2H inside the timed region)
+  roofline   the fused kernel against the FP32 FMA pipe (self-measured FFMA2 peak) -- the binding roof
+             for this path (DESIGN.md "Roofline") -- plus HBM / tensor fractions for context
+  cpu_baseline  the CPU restatement (oracle/, "port") on all host cores, bounded sample
+  --impl reference   times that CPU port as the reference arm (the reference itself cannot be built
+             here: Eigen is an un-vendored submodule)
+
+Nothing here reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "Msamples/sec (48kHz RTF) wavenet_a1_standard.nam, batch 4096, 1/2/4/8 GPU vs Eigen CPU"
+MODEL = "wavenet_a1_standard"
+CPU_BLOCK = 64  # AUDIO_BUFFER_SIZE of tools/benchmodel.cpp:18
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="streams per GPU")
+    ap.add_argument("--frames", type=int, default=4096, help="frames per stream per step")
+    ap.add_argument("--model", default=MODEL)
+    ap.add_argument("--tanh", default="fast", choices=["fast", "exact"],
+                    help="fast = tools/benchmodel.cpp default (enable_fast_tanh); exact = library default")
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", action="store_true", help="also time an NCCL all_gather of one step's outputs")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+def load_peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            d["_source"] = "measured"
+            return d
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows: list[list[str]] = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(names, r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def fixtures():
+    from tests import nam_fixtures as fx
+
+    return fx
+
+
+def cpu_port_lib():
+    """The CPU restatement built -march=native on THIS box (falls back to the in-tree x86-64-v3 build)."""
+    from oracle import oracle
+
+    oracle.build()
+    native = oracle.build_native_fast(tempfile.mkdtemp(prefix="nam_oracle_"))
+    if native is not None:
+        try:
+            return oracle.load_lib(path=native), "-O3 -march=native -ffast-math"
+        except OSError:
+            pass
+    return oracle.load_lib("fast"), "-O3 -march=x86-64-v3 -ffast-math"
+
+
+def time_cpu_port(nam: dict, fast_tanh: bool, frames: int, streams: int, threads: int, reps: int = 1) -> tuple[float, float]:
+    """Returns (Msamples/s, seconds per rep) of the CPU port on `threads` host threads."""
+    from oracle import oracle
+
+    lib, _ = cpu_port_lib()
+    fx = fixtures()
+    proto = oracle.OracleModel.from_dict(nam, fast_tanh=fast_tanh, lib=lib)
+    proto.reset(48000.0, CPU_BLOCK)  # the reference tools' protocol: Reset(sr, 64), 64-frame process() calls
+    pool = oracle.OracleBatch(proto, streams)  # one DSP instance per stream, created outside the timed region
+    x = fx.synthetic_batch(streams, frames, seed=99)
+    y = np.empty_like(x)
+    pool.process(np.ascontiguousarray(x[:, :CPU_BLOCK * 4]), None, CPU_BLOCK, threads)  # warm-up
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        pool.process(x, y, CPU_BLOCK, threads)
+        best = min(best, time.perf_counter() - t0)
+    pool.close()
+    return streams * frames / best / 1e6, best
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_reference(args) -> None:
+    """--impl reference: the reference's CPU algorithm for the path (oracle port; the reference's own
+    sources need Eigen, absent here) on all host threads, same config/metric/unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fx = fixtures()
+    nam = fx.load_model(args.model)
+    cores = os.cpu_count() or 1
+    streams = 2 * cores  # bounded sample of the 4096-stream batch
+    from oracle import oracle
+
+    lib, flags = cpu_port_lib()
+    proto = oracle.OracleModel.from_dict(nam, fast_tanh=(args.tanh == "fast"), lib=lib)
+    proto.reset(48000.0, CPU_BLOCK)
+    pool = oracle.OracleBatch(proto, streams)
+    x = fx.synthetic_batch(streams, args.frames, seed=99)
+    y = np.empty_like(x)
+    for _ in range(max(args.warmup, 1)):
+        pool.process(x, y, CPU_BLOCK, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pool.process(x, y, CPU_BLOCK, cores)
+    dt = time.perf_counter() - t0
+    value = streams * args.frames * args.steps / dt / 1e6
+    sample = (f"{streams} of {args.batch} streams x {args.frames} frames per step in {CPU_BLOCK}-frame process() calls "
+              f"(tools/benchmodel.cpp protocol), one instance per stream, {cores} threads, gcc {flags}")
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": "Msamples/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args),
+        "rtf_48k_aggregate": value * 1e6 / 48000.0,
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the reference algorithm (oracle/nam_oracle.c); the reference's own sources "
+                "need the Eigen submodule, which is not vendored and not in this image",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args) -> dict:
+    return {
+        "workload": f"{args.model}.nam, {args.batch} independent 48 kHz streams per GPU x {args.frames} frames per step, "
+                    f"float32, {args.tanh}-tanh regime, stateful (history carried across steps in HBM)",
+        "streams_per_gpu": args.batch,
+        "frames_per_step": args.frames,
+        "tanh": args.tanh,
+        "l2_policy": "working set per step (in+out+touched state) exceeds L2; no flush needed",
+    }
+
+
+def run_b200(args) -> None:
+    import torch
+
+    import neuralampmodelercore_b200 as nb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    fx = fixtures()
+    nam = fx.load_model(args.model)
+    B, n = args.batch, args.frames
+    fast = args.tanh == "fast"
+
+    model = nb.get_dsp(nam, batch=B, device=local_rank, fast_tanh=fast, ctas_per_sm=args.ctas_per_sm)
+    model.Reset(48000.0, n)
+    flops_per_frame = model.flops_per_frame
+    state_bytes = model.state_bytes_per_stream
+
+    x_host = torch.from_numpy(fx.synthetic_batch(B, n, seed=1234 + rank)).pin_memory()
+    y_host = torch.empty_like(x_host).pin_memory()
+    x_dev = x_host.cuda(non_blocking=True)
+    y_dev = torch.empty_like(x_dev)
+    # a non-default stream: its handle is passed to the C ABI so kernels and the timing events share a stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+
+    def step_device():
+        model.process_batch_device(x_dev.data_ptr(), y_dev.data_ptr(), B, n, n, n, stream.cuda_stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (value) ----
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = model.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local_rank) as clocks:
+        ev[0].record(stream)
+        for i in range(args.steps):
+            step_device()
+            ev[i + 1].record(stream)
+        barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    launches = model.launch_count() - launches0
+    t = torch.tensor([total_ms], device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * B * n * args.steps / (total_ms_max * 1e-3) / 1e6
+
+    # ---- end to end through the host API ----
+    e2e = None
+    if not args.no_e2e:
+        xh, yh = x_host.numpy(), y_host.numpy()
+        for _ in range(max(1, min(args.warmup, 3))):
+            model.process_batch(xh, yh)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            model.process_batch(xh, yh)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        loss = float(np.abs(yh[0, :8]).sum())  # touch the result on the host
+        e2e = {"value": world * B * n * args.steps / float(t.item()) / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(y_host.numel() * 4),
+               "ms_per_step": float(t.item()) / args.steps * 1e3, "checksum": loss}
+
+    gather = None
+    if args.gather and dist is not None:
+        outs = [torch.empty_like(y_dev) for _ in range(world)]
+        dist.all_gather(outs, y_dev)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            dist.all_gather(outs, y_dev)
+        g1.record()
+        torch.cuda.synchronize()
+        gms = g0.elapsed_time(g1) / 5
+        gather = {"ms_per_step": gms, "bytes_per_rank": int(y_dev.numel() * 4),
+                  "busbw_GBs": y_dev.numel() * 4 * (world - 1) / (gms * 1e-3) / 1e9}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the fused kernel (one launch per step) ----
+    peaks = load_peaks()
+    kernel_ms = statistics.mean(step_ms)  # one kernel per step on this stream: event-to-event == launch duration
+    fp32_peak = nb.measure_fp32_tflops(local_rank, packed=True)
+    fp32_scalar = nb.measure_fp32_tflops(local_rank, packed=False)
+    flops_per_launch = flops_per_frame * B * n
+    achieved_tf = flops_per_launch / (kernel_ms * 1e-3) / 1e12
+    alg_bytes = B * n * 8.0 + 2.0 * state_bytes * B  # in + out + history read & written once per launch
+    roofline = {
+        "bound": "fp32_fma",
+        "achieved": achieved_tf,
+        "peak": fp32_peak,
+        "unit": "TFLOP/s",
+        "frac": achieved_tf / fp32_peak if fp32_peak > 0 else None,
+        "peak_source": "self-measured FFMA2 issue rate on this GPU (nam_b200_measure_fp32_tflops); "
+                       f"scalar FFMA measures {fp32_scalar:.1f} TFLOP/s",
+        "flops_per_launch": flops_per_launch,
+        "kernel_ms": kernel_ms,
+        "traffic": None,
+        "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_GBs": alg_bytes / (kernel_ms * 1e-3) / 1e9,
+                "peak_GBs": peaks["hbm_gbs"], "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "of": peaks["_source"]},
+        "tensor": {"frac_of_bf16_peak": achieved_tf / peaks["bf16_tflops"], "of": peaks["_source"],
+                   "note": "kernel uses the FP32 FMA pipe, not tensor cores (1e-5 parity forbids TF32/BF16 operands)"},
+    }
+    prof = ROOT / "profiles" / "r01_traffic.json"
+    if prof.exists():
+        try:
+            roofline["traffic"] = json.loads(prof.read_text()).get("dram_bytes_per_launch_at_bench_shape")
+        except Exception:
+            pass
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        streams, cframes = 4 * cores, 24000
+        v, secs = time_cpu_port(nam, fast, cframes, streams, cores)
+        _, flags = cpu_port_lib()
+        cpu = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port",
+               "sample": f"{streams} streams x {cframes} frames ({secs:.1f} s wall on {cores} threads), "
+                         f"oracle/nam_oracle.c gcc {flags}, same tanh regime"}
+
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": "Msamples/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": total_ms_max / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args),
+        "rtf_48k_aggregate": value * 1e6 / 48000.0,
+        "rtf_48k_per_stream": value * 1e6 / 48000.0 / (world * B),
+        "clocks": clocks.summary(),
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    if gather is not None:
+        line["nccl_gather"] = gather
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -122,6 +122,14 @@ int64_t nam_b200_launch_count(const nam_b200_model* m);
  * handle's stream); negative if unavailable. */
 double nam_b200_last_kernel_ms(nam_b200_model* m);
 
+/* Host-only: parse + validate a .nam document and describe what the library would do with it, as a
+ * small JSON object written to `out` (NUL-terminated, truncated to `capacity`): architecture, channels,
+ * prewarm_samples, n_weights, expected_sample_rate, flops_per_frame, state_bytes_per_stream,
+ * kernel ("fused" | "lstm" | "linear" | "unsupported"), reason.  Never touches CUDA, so it is usable on a
+ * machine without a GPU (host-logic tests).  Returns 0, or the same error codes as create. */
+int nam_b200_inspect_json(const char* nam_json_text, int fast_tanh, char* out, int64_t capacity);
+int nam_b200_inspect_file(const char* nam_path, int fast_tanh, char* out, int64_t capacity);
+
 /* Thread-local message of the last failing call on this thread. */
 const char* nam_b200_last_error(void);
 

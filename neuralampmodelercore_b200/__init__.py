@@ -13,6 +13,7 @@ from .dsp import (  # noqa: F401
     disable_fast_tanh,
     enable_fast_tanh,
     get_dsp,
+    inspect,
     measure_fp32_tflops,
     using_fast_tanh,
 )
@@ -22,6 +23,7 @@ __all__ = [
     "LIB_PATH",
     "DSP",
     "get_dsp",
+    "inspect",
     "enable_fast_tanh",
     "disable_fast_tanh",
     "using_fast_tanh",

@@ -68,6 +68,8 @@ EXPORTED_SYMBOLS = [
     "nam_b200_last_kernel_ms",
     "nam_b200_last_error",
     "nam_b200_measure_fp32_tflops",
+    "nam_b200_inspect_json",
+    "nam_b200_inspect_file",
 ]
 
 
@@ -112,6 +114,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.nam_b200_last_kernel_ms.argtypes = [vp]
     lib.nam_b200_last_kernel_ms.restype = C.c_double
     lib.nam_b200_last_error.restype = C.c_char_p
+    lib.nam_b200_inspect_json.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int64]
+    lib.nam_b200_inspect_json.restype = C.c_int
+    lib.nam_b200_inspect_file.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int64]
+    lib.nam_b200_inspect_file.restype = C.c_int
     lib.nam_b200_measure_fp32_tflops.argtypes = [C.c_int, C.c_int]
     lib.nam_b200_measure_fp32_tflops.restype = C.c_double
     for name in (

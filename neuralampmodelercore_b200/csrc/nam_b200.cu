@@ -864,6 +864,107 @@ void nam_b200_destroy(nam_b200_model* m)
   delete m;
 }
 
+static int inspect_spec(const ModelSpec& spec, char* out, int64_t capacity)
+{
+  if (!out || capacity <= 0)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null output buffer");
+  std::string kernel = "unsupported", reason;
+  double flops = 0.0;
+  long state_floats = 0;
+  int variant = 0;
+  if (spec.in_channels != 1 || spec.out_channels != 1)
+    reason = "CUDA path is mono in / mono out";
+  else if (spec.arch == Arch::WaveNet)
+  {
+    const WaveNetPlan plan = plan_wavenet(spec);
+    if (plan.eligible)
+    {
+      kernel = "fused";
+      flops = 2.0 * plan.macs_per_frame;
+      state_floats = plan.state_floats;
+      variant = plan.cp[0] * 100 + (plan.n_arrays > 1 ? plan.cp[1] : 0);
+    }
+    else
+      reason = plan.why_not;
+  }
+  else if (spec.arch == Arch::LSTM)
+  {
+    if (spec.lstm.input_size != 1 || spec.lstm.num_layers < 1)
+      reason = "LSTM input_size != 1 or no layers";
+    else
+    {
+      kernel = "lstm";
+      double macs = spec.lstm.hidden;
+      for (const auto& c : spec.lstm.cells)
+        macs += 4.0 * c.hidden * (c.input_size + c.hidden);
+      flops = 2.0 * macs;
+      state_floats = (long)spec.lstm.num_layers * 2 * spec.lstm.hidden;
+      variant = 2000 + spec.lstm.hidden;
+    }
+  }
+  else
+  {
+    kernel = "linear";
+    flops = 2.0 * spec.linear.receptive_field;
+    state_floats = std::max(spec.linear.receptive_field - 1, 0);
+    variant = 3000;
+  }
+  for (auto& ch : reason)
+    if (ch == '"' || ch == '\\' || ch == '\n')
+      ch = ' ';
+  char buf[1024];
+  std::snprintf(buf, sizeof(buf),
+                "{\"architecture\": \"%s\", \"in_channels\": %d, \"out_channels\": %d, \"prewarm_samples\": %d, "
+                "\"n_weights\": %zu, \"expected_sample_rate\": %.17g, \"flops_per_frame\": %.17g, "
+                "\"state_bytes_per_stream\": %ld, \"kernel\": \"%s\", \"kernel_variant\": %d, \"has_loudness\": %s, "
+                "\"loudness\": %.17g, \"reason\": \"%s\"}",
+                spec.architecture.c_str(), spec.in_channels, spec.out_channels, spec.prewarm_samples, spec.n_weights,
+                spec.sample_rate, flops, state_floats * 4, kernel.c_str(), variant, spec.loudness ? "true" : "false",
+                spec.loudness.value_or(0.0), reason.c_str());
+  std::snprintf(out, (size_t)capacity, "%s", buf);
+  return NAM_B200_OK;
+}
+
+int nam_b200_inspect_json(const char* nam_json_text, int fast_tanh, char* out, int64_t capacity)
+{
+  if (!nam_json_text)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null argument");
+  LoadOptions lo;
+  lo.fast_tanh = fast_tanh != 0;
+  try
+  {
+    return inspect_spec(model_spec_from_text(nam_json_text, lo), out, capacity);
+  }
+  catch (const json::ParseError& ex)
+  {
+    return fail(NAM_B200_ERR_FILE, ex.what());
+  }
+  catch (const std::exception& ex)
+  {
+    return fail(NAM_B200_ERR_MODEL, ex.what());
+  }
+}
+
+int nam_b200_inspect_file(const char* nam_path, int fast_tanh, char* out, int64_t capacity)
+{
+  if (!nam_path)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null argument");
+  LoadOptions lo;
+  lo.fast_tanh = fast_tanh != 0;
+  try
+  {
+    return inspect_spec(model_spec_from_file(nam_path, lo), out, capacity);
+  }
+  catch (const NamFileValidationError& ex)
+  {
+    return fail(NAM_B200_ERR_FILE, ex.what());
+  }
+  catch (const std::exception& ex)
+  {
+    return fail(NAM_B200_ERR_MODEL, ex.what());
+  }
+}
+
 int nam_b200_get_info(const nam_b200_model* m, nam_b200_info* info)
 {
   if (!m || !info)

@@ -220,9 +220,10 @@ class DSP:
         b, n = x.shape
         if out is None:
             out = np.empty_like(x)
-        rc = self._lib.nam_b200_process_f32(
-            self._h, x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), b, n, x.strides[0] // 4, out.strides[0] // 4
-        )
+        # numpy may report an arbitrary stride for a length-1 axis
+        xs = x.strides[0] // 4 if b > 1 else n
+        os_ = out.strides[0] // 4 if b > 1 else n
+        rc = self._lib.nam_b200_process_f32(self._h, x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), b, n, xs, os_)
         if rc != 0:
             _raise(rc, self._lib)
         return out
@@ -271,6 +272,24 @@ def get_dsp(config, batch: int = 1, device: int = -1, prewarm: Optional[bool] = 
     if rc != 0:
         _raise(rc, lib)
     return DSP(h.value, lib, int(batch))
+
+
+def inspect(config, fast_tanh: Optional[bool] = None) -> dict:
+    """Host-only: parse/validate a .nam (path, dict or JSON text) with the product's C++ loader and report
+    what the CUDA path would do with it.  Needs no GPU."""
+    import json
+
+    lib = _capi.load()
+    buf = C.create_string_buffer(2048)
+    ft = int(_using_fast_tanh if fast_tanh is None else bool(fast_tanh))
+    if isinstance(config, (str, os.PathLike)) and not (isinstance(config, str) and config.lstrip().startswith("{")):
+        rc = lib.nam_b200_inspect_file(str(Path(config)).encode(), ft, buf, len(buf))
+    else:
+        text = config if isinstance(config, str) else json.dumps(config)
+        rc = lib.nam_b200_inspect_json(text.encode(), ft, buf, len(buf))
+    if rc != 0:
+        _raise(rc, lib)
+    return json.loads(buf.value.decode())
 
 
 def measure_fp32_tflops(device: int = -1, packed: bool = True) -> float:

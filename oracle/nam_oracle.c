@@ -1864,6 +1864,87 @@ int nam_oracle_run_batch_mono_f32(const nam_oracle* proto, const float* in, floa
   return 0;
 }
 
+/* ---- persistent batch: `batch` independent DSP instances that keep their state across calls ---- */
+struct nam_oracle_batch
+{
+  int batch;
+  nam_oracle** models;
+};
+
+typedef struct
+{
+  struct nam_oracle_batch* B;
+  const float* in;
+  float* out;
+  long n_total, in_stride, out_stride;
+  int block;
+  int* next;
+} pbatch_job_t;
+
+static void* pbatch_worker(void* arg)
+{
+  pbatch_job_t* j = (pbatch_job_t*)arg;
+  for (;;)
+  {
+    const int b = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED);
+    if (b >= j->B->batch)
+      break;
+    nam_oracle_run_mono_f32(j->B->models[b], j->in + (size_t)b * j->in_stride, j->out + (size_t)b * j->out_stride,
+                            j->n_total, j->block);
+  }
+  return NULL;
+}
+
+struct nam_oracle_batch* nam_oracle_batch_create(const nam_oracle* proto, int batch)
+{
+  if (proto->in_ch != 1 || proto->out_ch != 1 || batch < 1)
+  {
+    set_err("batch_create: model must be mono and batch >= 1");
+    return NULL;
+  }
+  struct nam_oracle_batch* B = (struct nam_oracle_batch*)xcalloc(1, sizeof(*B));
+  B->batch = batch;
+  B->models = (nam_oracle**)xcalloc((size_t)batch, sizeof(nam_oracle*));
+  for (int b = 0; b < batch; b++)
+    B->models[b] = clone_model(proto);
+  return B;
+}
+
+int nam_oracle_batch_process(struct nam_oracle_batch* B, const float* in, float* out, long n_total, long in_stride,
+                             long out_stride, int block, int threads)
+{
+  if (block > B->models[0]->max_buf)
+  {
+    set_err("batch_process: block (%d) exceeds max_buffer_size (%d)", block, B->models[0]->max_buf);
+    return -1;
+  }
+  if (threads < 1)
+    threads = 1;
+  if (threads > 256)
+    threads = 256;
+  int next = 0;
+  pbatch_job_t job = {B, in, out, n_total, in_stride, out_stride, block, &next};
+  pthread_t tid[256];
+  int started = 0;
+  for (int t = 1; t < threads; t++)
+    if (pthread_create(&tid[started], NULL, pbatch_worker, &job) == 0)
+      started++;
+  pbatch_worker(&job);
+  for (int t = 0; t < started; t++)
+    pthread_join(tid[t], NULL);
+  return 0;
+}
+
+void nam_oracle_batch_destroy(struct nam_oracle_batch* B)
+{
+  if (!B)
+    return;
+  for (int b = 0; b < B->batch; b++)
+    nam_oracle_destroy(B->models[b]);
+  free(B->models);
+  free(B);
+}
+
 /* ------------------------------------------------------------------------------------------
  * Module-level entry points
  * ---------------------------------------------------------------------------------------- */

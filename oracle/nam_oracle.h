@@ -69,6 +69,16 @@ void nam_oracle_run_mono_f32(nam_oracle* o, const float* in, float* out, long n_
 int nam_oracle_run_batch_mono_f32(const nam_oracle* proto, const float* in, float* out, int batch, long n_total,
                                   int block, int threads);
 
+/* Persistent batch for CPU-baseline timing: `batch` independent instances (clones of `proto`, state
+ * included) that keep their own state across calls -- the reference's "one nam::DSP object per stream".
+ * process(): stream b reads in[b*in_stride ..+n_total) in `block`-frame process() calls, on `threads`
+ * pthreads (streams are distributed dynamically). */
+typedef struct nam_oracle_batch nam_oracle_batch;
+nam_oracle_batch* nam_oracle_batch_create(const nam_oracle* proto, int batch);
+int nam_oracle_batch_process(nam_oracle_batch* b, const float* in, float* out, long n_total, long in_stride,
+                             long out_stride, int block, int threads);
+void nam_oracle_batch_destroy(nam_oracle_batch* b);
+
 /* ---- module-level entry points (used to pin the restatement against the reference's own
  * known-answer unit tests) ---- */
 

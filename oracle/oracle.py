@@ -74,6 +74,11 @@ def _declare(lib: C.CDLL) -> C.CDLL:
     lib.nam_oracle_activation.argtypes = [C.c_int, f32p, C.c_int, C.c_int, f32p, C.c_int, C.c_int]
     lib.nam_oracle_gating.restype = C.c_int
     lib.nam_oracle_gating.argtypes = [C.c_int, C.c_int, f32p, C.c_int, C.c_int, f32p, C.c_int, C.c_int, f32p, f32p, C.c_int]
+    lib.nam_oracle_batch_create.restype = C.c_void_p
+    lib.nam_oracle_batch_create.argtypes = [C.c_void_p, C.c_int]
+    lib.nam_oracle_batch_process.restype = C.c_int
+    lib.nam_oracle_batch_process.argtypes = [C.c_void_p, f32p, f32p, C.c_long, C.c_long, C.c_long, C.c_int, C.c_int]
+    lib.nam_oracle_batch_destroy.argtypes = [C.c_void_p]
     lib.nam_oracle_layer.restype = C.c_int
     lib.nam_oracle_layer.argtypes = [i32p, C.c_int, f32p, C.c_int, f32p, C.c_int, f32p, f32p, f32p, f32p, C.c_int, C.c_int]
     return lib
@@ -202,6 +207,40 @@ class OracleModel:
         if rc != 0:
             raise OracleError(self.lib.nam_oracle_last_error().decode())
         return out
+
+
+class OracleBatch:
+    """`batch` independent instances (clones of a prepared OracleModel, state included) that keep their state
+    across process() calls -- one nam::DSP per stream, spread over host threads.  CPU-baseline timing."""
+
+    def __init__(self, proto: OracleModel, batch: int):
+        self.lib = proto.lib
+        self.batch = int(batch)
+        self.max_buffer_size = proto.max_buffer_size
+        self._h = self.lib.nam_oracle_batch_create(proto._h, self.batch)
+        if not self._h:
+            raise OracleError(self.lib.nam_oracle_last_error().decode())
+
+    def process(self, x: np.ndarray, out: np.ndarray | None = None, block: int = 64, threads: int | None = None) -> np.ndarray:
+        assert x.dtype == np.float32 and x.ndim == 2 and x.shape[0] == self.batch and x.flags["C_CONTIGUOUS"]
+        if out is None:
+            out = np.empty_like(x)
+        threads = threads or os.cpu_count() or 1
+        rc = self.lib.nam_oracle_batch_process(self._h, _fp(x), _fp(out), x.shape[1], x.shape[1], out.shape[1], int(block), threads)
+        if rc != 0:
+            raise OracleError(self.lib.nam_oracle_last_error().decode())
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.nam_oracle_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---- module-level helpers (column-major (channels x frames) numpy arrays in "F" order) --------------------------

@@ -1,0 +1,141 @@
+"""CPU-only tests of the product's host side: the C-ABI library loads and exports every symbol
+include/nam_b200.h declares, and its own C++ .nam loader / packer agrees with the (independent) Python
+restatement used by the oracle.  No compute calls: those need a GPU (tests/test_parity_gpu.py)."""
+import ctypes
+import json
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import neuralampmodelercore_b200 as nb
+from neuralampmodelercore_b200 import _capi
+from oracle import nam_config, oracle
+from tests import nam_fixtures as fx
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "nam_b200.h").read_text()
+    declared = sorted(set(re.findall(r"\b(nam_b200_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(str(nb.build()))
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/nam_b200.h but not exported"
+    assert sorted(_capi.EXPORTED_SYMBOLS) == declared
+    assert _capi.load().nam_b200_abi_version() == 1
+
+
+def test_options_struct_defaults_and_sizes():
+    lib = _capi.load()
+    o = _capi.Options()
+    lib.nam_b200_default_options(ctypes.byref(o))
+    assert o.struct_size == ctypes.sizeof(_capi.Options) == 56
+    assert (o.device, o.max_batch, o.fast_tanh, o.prewarm_on_reset) == (-1, 1, 0, 1)
+    assert ctypes.sizeof(_capi.Info) == 128
+
+
+@pytest.mark.parametrize("name", ["wavenet", "wavenet_a1_standard", "lstm", "a2_lite", "a2_full", "wavenet_a2_max",
+                                  "wavenet_condition_dsp"])
+def test_cxx_loader_agrees_with_python_restatement(name):
+    nam = fx.load_model(name)
+    info = nb.inspect(nam)
+    m = oracle.OracleModel.from_dict(nam)
+    assert info["n_weights"] == len(nam["weights"]) == m.weights_consumed
+    assert info["prewarm_samples"] == m.prewarm_samples
+    assert info["in_channels"] == m.in_channels and info["out_channels"] == m.out_channels
+    assert info["expected_sample_rate"] == nam_config.flatten(nam).sample_rate
+
+
+def test_kernel_selection_and_algorithmic_work():
+    a1 = nb.inspect(fx.load_model("wavenet_a1_standard"))
+    # 13,320 MACs = 26,640 FLOP per frame; 196,416 B of history per stream (+ alignment)
+    assert a1["kernel"] == "fused" and a1["kernel_variant"] == 1608
+    assert a1["flops_per_frame"] == 26640
+    assert 196416 <= a1["state_bytes_per_stream"] <= 196416 + 128
+    w = nb.inspect(fx.load_model("wavenet"))
+    assert w["kernel"] == "fused" and w["flops_per_frame"] == 226 and w["kernel_variant"] == 404
+    assert nb.inspect(fx.load_model("lstm"))["kernel"] == "lstm"
+    assert nb.inspect(fx.load_model("lstm"))["flops_per_frame"] == 102
+    for name, why in (("wavenet_a2_max", "condition_dsp"), ("a2_full", "head kernel size")):
+        info = nb.inspect(fx.load_model(name))
+        assert info["kernel"] == "unsupported" and why in info["reason"]
+
+
+def test_loader_errors_match_reference_behaviour():
+    good = fx.load_model("wavenet")
+    # NAM/nam_file.cpp:31-37 required keys
+    for key in ("version", "architecture", "config", "weights"):
+        bad = {k: v for k, v in good.items() if k != key}
+        with pytest.raises(RuntimeError, match="missing required key"):
+            nb.inspect(bad)
+    # NAM/get_dsp.cpp:113-121 unsupported version
+    with pytest.raises(RuntimeError, match="unsupported version"):
+        nb.inspect({**good, "version": "0.4.0"})
+    with pytest.raises(RuntimeError, match="unsupported version"):
+        nb.inspect({**good, "version": "0.8.0"})
+    nb.inspect({**good, "version": "0.7.9"})  # partial support: loads with a warning
+    # NAM/model_config.h:81-88 unknown architecture
+    with pytest.raises(RuntimeError, match="No config parser registered"):
+        nb.inspect({**good, "architecture": "Transformer"})
+    # NAM/wavenet/model.cpp:671-682 weight count
+    with pytest.raises(RuntimeError, match="Weight mismatch"):
+        nb.inspect({**good, "weights": good["weights"] + [0.0]})
+    with pytest.raises(RuntimeError, match="expects more"):
+        nb.inspect({**good, "weights": good["weights"][:-2]})
+    # activations.cpp:83-87
+    bad = json.loads(json.dumps(good))
+    bad["config"]["layers"][0]["activation"] = "Gelu"
+    with pytest.raises(RuntimeError, match="Unknown activation type"):
+        nb.inspect(bad)
+    with pytest.raises(nb.NamFileValidationError, match="does not exist"):
+        nb.inspect("/nonexistent/dir/model.nam")
+    with pytest.raises(nb.NamFileValidationError):
+        nb.inspect("{ this is not json")
+
+
+def test_inspect_file_roundtrip(tmp_path):
+    nam = fx.load_model("wavenet")
+    p = tmp_path / "m.nam"
+    p.write_text(json.dumps(nam))
+    assert nb.inspect(p) == nb.inspect(nam)
+    (tmp_path / "bad.nam").write_text("[1, 2, 3]")
+    with pytest.raises(nb.NamFileValidationError, match="root JSON value must be an object"):
+        nb.inspect(tmp_path / "bad.nam")
+
+
+def test_json_parser_edge_cases():
+    # numbers in exponent form, escapes, nested arrays, unicode -- the .nam writer is Python's json module
+    nam = fx.load_model("wavenet")
+    text = json.dumps(nam).replace("0.02", "2e-2", 1)
+    text = text.replace('"version"', '"note": "caf\\u00e9 \\"quoted\\" \\n", "version"', 1)
+    assert nb.inspect(text)["n_weights"] == 131
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a machine without CUDA the product must fail loudly, not compute on the host."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present: exercised by the gpu tests")
+    with pytest.raises(nb.CudaUnavailableError, match="no CPU path"):
+        nb.get_dsp(fx.load_model("wavenet"))
+
+
+def test_product_does_not_import_the_oracle():
+    """oracle/ is test infrastructure: nothing in the product package may reference it."""
+    pkg = ROOT / "neuralampmodelercore_b200"
+    for f in list(pkg.rglob("*.py")) + list((pkg / "csrc").glob("*")):
+        if f.is_file() and f.suffix in (".py", ".cu", ".cuh", ".cpp", ".h"):
+            text = f.read_text()
+            assert "nam_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_synthetic_signal_definition():
+    # deterministic, distinct per stream, bounded
+    a = fx.synthetic_batch(4, 256)
+    b = fx.synthetic_batch(4, 256)
+    assert np.array_equal(a, b) and a.dtype == np.float32
+    assert not np.array_equal(a[0], a[1]) and np.abs(a).max() < 0.5
