@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--tanh", default="fast", choices=["fast", "exact"],
                     help="fast = tools/benchmodel.cpp default (enable_fast_tanh); exact = library default")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--geometry", type=int, default=0, help="0 default, 1 = 128-thread CTAs, 2 = 256-thread CTAs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--gather", action="store_true", help="also time an NCCL all_gather of one step's outputs")
@@ -249,7 +250,8 @@ def run_b200(args) -> None:
     B, n = args.batch, args.frames
     fast = args.tanh == "fast"
 
-    model = nb.get_dsp(nam, batch=B, device=local_rank, fast_tanh=fast, ctas_per_sm=args.ctas_per_sm)
+    model = nb.get_dsp(nam, batch=B, device=local_rank, fast_tanh=fast, ctas_per_sm=args.ctas_per_sm,
+                       kernel_geometry=args.geometry)
     model.Reset(48000.0, n)
     flops_per_frame = model.flops_per_frame
     state_bytes = model.state_bytes_per_stream

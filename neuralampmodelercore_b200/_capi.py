@@ -20,7 +20,8 @@ class Options(C.Structure):
         ("fast_tanh", C.c_int32),
         ("prewarm_on_reset", C.c_int32),
         ("ctas_per_sm", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("kernel_geometry", C.c_int32),
+        ("reserved", C.c_int32 * 7),
     ]
 
 

@@ -327,6 +327,7 @@ struct nam_b200_model
   WaveNetPlan plan;
   int variant = 0;
   int wn_ctas_per_sm = 0; // resident CTAs per SM of the fused kernel (occupancy query, cached)
+  int wn_geometry = 1; // index into kWnGeom
   // LSTM / Linear packed weights
   std::vector<float> host_weights;
   float* d_weights = nullptr;
@@ -371,65 +372,80 @@ namespace
 {
 
 // ---- WaveNet launch dispatch -----------------------------------------------------------------
+// Two CTA geometries of the same kernel (S = 2 time steps per thread):
+//   geometry 0: 128 threads, tile 256 frames, >= 3 CTAs/SM (<= 168 registers)
+//   geometry 1: 256 threads, tile 512 frames, >= 2 CTAs/SM (<= 128 registers) -- 16 warps/SM, the
+//               weights (one copy per CTA) cost half the shared memory per warp
 constexpr int kWnS = 2; // time steps per thread
-constexpr int kWnNT = 128; // threads per CTA
 
-template <int C0, int C1>
+struct WnGeometry
+{
+  int nt, min_ctas;
+};
+constexpr WnGeometry kWnGeom[2] = {{128, 3}, {256, 2}};
+
+template <int C0, int C1, int NT, int MINB>
 void launch_wavenet_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem, cudaStream_t st)
 {
-  auto kern = wavenet_fused_kernel<C0, C1, kWnS, kWnNT>;
+  auto kern = wavenet_fused_kernel<C0, C1, kWnS, NT, MINB>;
   static bool configured[64] = {false};
   if (!configured[m->device & 63])
   {
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured[m->device & 63] = true;
   }
-  kern<<<grid, kWnNT, smem, st>>>(kp);
+  kern<<<grid, NT, smem, st>>>(kp);
   CUDA_CHECK(cudaGetLastError());
 }
 
-template <int C0, int C1>
+template <int C0, int C1, int NT, int MINB>
 int occupancy_wavenet_variant(size_t smem)
 {
-  auto kern = wavenet_fused_kernel<C0, C1, kWnS, kWnNT>;
+  auto kern = wavenet_fused_kernel<C0, C1, kWnS, NT, MINB>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kWnNT, smem) != cudaSuccess)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, NT, smem) != cudaSuccess)
     return 1;
   return n > 0 ? n : 1;
 }
 
+#define WN_CASE(C0, C1, FN, ...)                                                                                     \
+  case (C0) * 100 + (C1):                                                                                            \
+    return geom == 0 ? FN<C0, C1, 128, 3>(__VA_ARGS__) : FN<C0, C1, 256, 2>(__VA_ARGS__);
+
 #define WN_DISPATCH(FN, ...)                                                                                         \
   switch (c0 * 100 + c1)                                                                                             \
   {                                                                                                                  \
-    case 400: return FN<4, 0>(__VA_ARGS__);                                                                          \
-    case 800: return FN<8, 0>(__VA_ARGS__);                                                                          \
-    case 1600: return FN<16, 0>(__VA_ARGS__);                                                                        \
-    case 404: return FN<4, 4>(__VA_ARGS__);                                                                          \
-    case 408: return FN<4, 8>(__VA_ARGS__);                                                                          \
-    case 804: return FN<8, 4>(__VA_ARGS__);                                                                          \
-    case 808: return FN<8, 8>(__VA_ARGS__);                                                                          \
-    case 1604: return FN<16, 4>(__VA_ARGS__);                                                                        \
-    case 1608: return FN<16, 8>(__VA_ARGS__);                                                                        \
-    case 1616: return FN<16, 16>(__VA_ARGS__);                                                                       \
+    WN_CASE(4, 0, FN, __VA_ARGS__)                                                                                   \
+    WN_CASE(8, 0, FN, __VA_ARGS__)                                                                                   \
+    WN_CASE(16, 0, FN, __VA_ARGS__)                                                                                  \
+    WN_CASE(4, 4, FN, __VA_ARGS__)                                                                                   \
+    WN_CASE(4, 8, FN, __VA_ARGS__)                                                                                   \
+    WN_CASE(4, 16, FN, __VA_ARGS__)                                                                                  \
+    WN_CASE(8, 4, FN, __VA_ARGS__)                                                                                   \
+    WN_CASE(8, 8, FN, __VA_ARGS__)                                                                                   \
+    WN_CASE(8, 16, FN, __VA_ARGS__)                                                                                  \
+    WN_CASE(16, 4, FN, __VA_ARGS__)                                                                                  \
+    WN_CASE(16, 8, FN, __VA_ARGS__)                                                                                  \
+    WN_CASE(16, 16, FN, __VA_ARGS__)                                                                                 \
     default: throw std::runtime_error("no fused WaveNet kernel for channel pair " + std::to_string(c0) + "/"         \
                                       + std::to_string(c1));                                                         \
   }
 
-void launch_wavenet_dispatch(int c0, int c1, nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem,
-                             cudaStream_t st)
+void launch_wavenet_dispatch(int c0, int c1, int geom, nam_b200_model* m, const WaveNetKernelParams& kp, int grid,
+                             size_t smem, cudaStream_t st)
 {
   WN_DISPATCH(launch_wavenet_variant, m, kp, grid, smem, st)
 }
-int occupancy_wavenet_dispatch(int c0, int c1, size_t smem)
+int occupancy_wavenet_dispatch(int c0, int c1, int geom, size_t smem)
 {
   WN_DISPATCH(occupancy_wavenet_variant, smem)
 }
 
-size_t wavenet_smem_bytes(const WaveNetPlan& plan)
+size_t wavenet_smem_bytes(const WaveNetPlan& plan, int geom)
 {
   const int cmax = std::max(plan.cp[0], plan.cp[1]);
-  const size_t tile4 = (size_t)(cmax / 4) * (kHalo + kWnS * kWnNT);
+  const size_t tile4 = (size_t)(cmax / 4) * (kHalo + kWnS * kWnGeom[geom].nt);
   return (plan.blob.size() + 3) / 4 * 16 + tile4 * 16;
 }
 
@@ -455,15 +471,16 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
     kp.arrays[i] = plan.arrays[i];
   for (size_t i = 0; i < plan.layers.size(); i++)
     kp.layers[i] = plan.layers[i];
-  const size_t smem = wavenet_smem_bytes(plan);
+  const int geom = m->wn_geometry;
+  const size_t smem = wavenet_smem_bytes(plan, geom);
   const int c0 = plan.cp[0], c1 = plan.n_arrays > 1 ? plan.cp[1] : 0;
   if (m->wn_ctas_per_sm <= 0)
-    m->wn_ctas_per_sm = m->opts.ctas_per_sm > 0 ? m->opts.ctas_per_sm : occupancy_wavenet_dispatch(c0, c1, smem);
+    m->wn_ctas_per_sm = m->opts.ctas_per_sm > 0 ? m->opts.ctas_per_sm : occupancy_wavenet_dispatch(c0, c1, geom, smem);
   const int per_sm = m->wn_ctas_per_sm;
   int grid = std::min(batch, per_sm * m->sm_count);
   if (grid < 1)
     grid = 1;
-  launch_wavenet_dispatch(c0, c1, m, kp, grid, smem, st);
+  launch_wavenet_dispatch(c0, c1, geom, m, kp, grid, smem, st);
   m->launches++;
 }
 
@@ -691,7 +708,8 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
         m->state_stride = m->plan.state_floats;
         m->flops_per_frame = 2.0 * m->plan.macs_per_frame;
         m->variant = m->plan.cp[0] * 100 + (m->plan.n_arrays > 1 ? m->plan.cp[1] : 0);
-        if (wavenet_smem_bytes(m->plan) > 227 * 1024)
+        m->wn_geometry = (m->opts.kernel_geometry == 1) ? 0 : 1; // option: 0 default, 1 = 128-thread, 2 = 256-thread
+        if (wavenet_smem_bytes(m->plan, m->wn_geometry) > 227 * 1024)
           return fail(NAM_B200_ERR_UNSUPPORTED, "WaveNet weights do not fit in shared memory");
         break;
       }

@@ -33,8 +33,15 @@
 
 #include "wavenet_desc.h"
 
+// unroll factor of the per-tap plane loop (4 input channels per plane): full unroll removes the
+// loop-carried accumulator copies ptxas otherwise inserts at the back-edge
+#ifndef NAMB200_PL_UNROLL
+#define NAMB200_PL_UNROLL 4
+#endif
+
 namespace namb200
 {
+constexpr int kPlUnroll = NAMB200_PL_UNROLL;
 
 // ---- activations ---------------------------------------------------------------------------
 // fast_tanh: the reference's rational approximation (activations.h:91-98).  The quotient uses
@@ -137,17 +144,43 @@ __device__ __forceinline__ void st_ring(float4* p, const float4& v)
   __stcg(p, v);
 }
 
-// acc[o] += w_row[o] * x for C outputs, two per FFMA2.
-template <int C>
-__device__ __forceinline__ void axpy_row(float2 (&acc)[C / 2], const float* __restrict__ w_row, const float x)
+// ---- packed fp32 pairs ------------------------------------------------------------------------
+// Accumulators are kept as 64-bit register pairs and updated IN PLACE with fma.rn.f32x2 (SASS
+// FFMA2) through inline PTX: the "+l" constraint pins destination == addend, which stops ptxas
+// from rotating the accumulators through fresh registers (and paying one MOV per accumulator per
+// loop trip, 15% of all issued instructions in the first version of this kernel; profiles/).
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pack2(const float lo, const float hi)
 {
-  const float2 xx = make_float2(x, x);
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(const u64 v, float& lo, float& hi)
+{
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void fma2_acc(u64& acc, const u64 w, const u64 xx)
+{
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(w), "l"(xx));
+}
+__device__ __forceinline__ void add2_acc(u64& acc, const u64 v)
+{
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(v));
+}
+
+// acc[o] += w_row[o] * x for C outputs, two per FFMA2 (x broadcast to both halves).
+template <int C>
+__device__ __forceinline__ void axpy_row(u64 (&acc)[C / 2], const float* __restrict__ w_row, const float x)
+{
+  const u64 xx = pack2(x, x);
 #pragma unroll
   for (int q = 0; q < C / 4; q++)
   {
     const float4 w = *reinterpret_cast<const float4*>(w_row + 4 * q);
-    acc[2 * q] = __ffma2_rn(make_float2(w.x, w.y), xx, acc[2 * q]);
-    acc[2 * q + 1] = __ffma2_rn(make_float2(w.z, w.w), xx, acc[2 * q + 1]);
+    fma2_acc(acc[2 * q], pack2(w.x, w.y), xx);
+    fma2_acc(acc[2 * q + 1], pack2(w.z, w.w), xx);
   }
 }
 
@@ -160,8 +193,7 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
                                               const float* __restrict__ sw, float4* __restrict__ tile,
                                               float* __restrict__ state, const uint32_t tabs0, const int Tv,
                                               const float (&hin)[S][CIN], const float (&cond)[S],
-                                              float2 (&head)[S][C / 2], float (&hout)[S][C],
-                                              float (&headout)[S][HOUT])
+                                              u64 (&head)[S][C / 2], float (&hout)[S][C], float (&headout)[S][HOUT])
 {
   constexpr int T = S * NT;
   constexpr int TW = kHalo + T; // columns per plane in the shared tile
@@ -172,78 +204,103 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
 #pragma unroll
   for (int j = 0; j < S; j++)
   {
-    float2 h[C / 2];
+    u64 h[C / 2];
 #pragma unroll
     for (int q = 0; q < C / 2; q++)
-      h[q] = make_float2(0.0f, 0.0f);
+      h[q] = 0ull;
 #pragma unroll
     for (int i = 0; i < CIN; i++)
       axpy_row<C>(h, sw + A.rech_off + i * C, hin[j][i]);
 #pragma unroll
     for (int pl = 0; pl < P; pl++)
-      tile[pl * TW + kHalo + j * NT + tid] = make_float4(h[2 * pl].x, h[2 * pl].y, h[2 * pl + 1].x, h[2 * pl + 1].y);
+    {
+      float4 v;
+      unpack2(h[2 * pl], v.x, v.y);
+      unpack2(h[2 * pl + 1], v.z, v.w);
+      tile[pl * TW + kHalo + j * NT + tid] = v;
+    }
   }
 
 #pragma unroll 1
   for (int li = 0; li < A.n_layers; li++)
   {
-    const LayerDesc& L = p.layers[A.layer0 + li];
-    const float* __restrict__ w = sw + L.w_off;
-    const float* __restrict__ w_bias = w + L.kernel * C * C;
+    // descriptor fields -> registers once per layer (they live in the kernel-parameter constant bank)
+    const LayerDesc& Ld = p.layers[A.layer0 + li];
+    const int K = Ld.kernel, dil = Ld.dilation, lookback = Ld.lookback;
+    const uint32_t ring_mask = (uint32_t)Ld.ring_mask;
+    const int R = Ld.ring_mask + 1;
+    const float* __restrict__ w = sw + Ld.w_off;
+    const float* __restrict__ w_bias = w + K * C * C;
     const float* __restrict__ w_mix = w_bias + C;
     const float* __restrict__ w_p = w_mix + C;
     const float* __restrict__ w_pb = w_p + C * C;
     const float* __restrict__ w_slopes = w_pb + C;
-    float4* __restrict__ ring = reinterpret_cast<float4*>(state + L.ring_off);
-    const int R = L.ring_mask + 1;
-    const int halo = (L.lookback <= kHalo) ? L.lookback : 0;
+    float4* __restrict__ ring = reinterpret_cast<float4*>(state + Ld.ring_off);
+    const int halo = (lookback <= kHalo) ? lookback : 0;
 
     // ---- phase 0: small-dilation layers pull their history [t0-L, t0) into the halo
     for (int idx = tid; idx < halo * P; idx += NT)
     {
       const int pl = idx / halo, col = idx - pl * halo;
-      tile[pl * TW + kHalo - halo + col] = ld_ring(ring + pl * R + ((tabs0 - (uint32_t)halo + (uint32_t)col) & L.ring_mask));
+      tile[pl * TW + kHalo - halo + col] = ld_ring(ring + pl * R + ((tabs0 - (uint32_t)halo + (uint32_t)col) & ring_mask));
     }
     __syncthreads(); // B0: tile columns (previous layer's phase 2) + halo are visible
 
     // ---- phase 1: z = b + M c + sum_k W_k h[t-(K-1-k)d] ; a = act(z) ; head += a
-    float2 acc[S][C / 2];
+    u64 acc[S][C / 2];
 #pragma unroll
     for (int j = 0; j < S; j++)
     {
 #pragma unroll
-      for (int q = 0; q < C / 2; q++)
-        acc[j][q] = *reinterpret_cast<const float2*>(w_bias + 2 * q);
+      for (int q = 0; q < C / 4; q++)
+      {
+        const float4 b4 = *reinterpret_cast<const float4*>(w_bias + 4 * q);
+        acc[j][2 * q] = pack2(b4.x, b4.y);
+        acc[j][2 * q + 1] = pack2(b4.z, b4.w);
+      }
       axpy_row<C>(acc[j], w_mix, cond[j]);
     }
+    const float* __restrict__ w_row = w; // walks [k][in][out] linearly
 #pragma unroll 1
-    for (int k = 0; k < L.kernel; k++)
+    for (int k = 0; k < K; k++)
     {
-      const int off = (L.kernel - 1 - k) * L.dilation;
-      const float* __restrict__ wk = w + k * C * C;
-#pragma unroll 1
+      const int off = (K - 1 - k) * dil;
+      // tap source per owned time step, resolved once per tap: the shared tile (incl. halo) or the ring
+      const float4* sp[S];
+      uint32_t gi[S];
+      bool glob[S];
+#pragma unroll
+      for (int j = 0; j < S; j++)
+      {
+        const int rel = j * NT + tid - off;
+        glob[j] = rel < -halo;
+        sp[j] = tile + kHalo + rel;
+        gi[j] = (tabs0 + (uint32_t)rel) & ring_mask;
+      }
+#pragma unroll kPlUnroll
       for (int pl = 0; pl < P; pl++)
       {
         float4 xq[S];
 #pragma unroll
         for (int j = 0; j < S; j++)
         {
-          const int rel = j * NT + tid - off;
-          if (rel >= -halo)
-            xq[j] = tile[pl * TW + kHalo + rel];
+          if (glob[j])
+            xq[j] = ld_ring(ring + gi[j]);
           else
-            xq[j] = ld_ring(ring + pl * R + ((tabs0 + (uint32_t)rel) & L.ring_mask));
+            xq[j] = *sp[j];
+          sp[j] += TW;
+          gi[j] += (uint32_t)R;
         }
 #pragma unroll
         for (int i = 0; i < 4; i++)
         {
-          const float* __restrict__ w_row = wk + (pl * 4 + i) * C;
 #pragma unroll
           for (int j = 0; j < S; j++)
           {
             const float xs = (i == 0) ? xq[j].x : (i == 1) ? xq[j].y : (i == 2) ? xq[j].z : xq[j].w;
             axpy_row<C>(acc[j], w_row, xs);
           }
+          w_row += C;
         }
       }
     }
@@ -253,43 +310,40 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
     {
 #pragma unroll
       for (int q = 0; q < C / 2; q++)
-      {
-        a[j][2 * q] = acc[j][q].x;
-        a[j][2 * q + 1] = acc[j][q].y;
-      }
-      apply_activation<C>(a[j], L, w_slopes);
+        unpack2(acc[j][q], a[j][2 * q], a[j][2 * q + 1]);
+      apply_activation<C>(a[j], Ld, w_slopes);
 #pragma unroll
       for (int q = 0; q < C / 2; q++)
-        head[j][q] = __fadd2_rn(head[j][q], make_float2(a[j][2 * q], a[j][2 * q + 1])); // model.cpp:530
+        add2_acc(head[j][q], pack2(a[j][2 * q], a[j][2 * q + 1])); // model.cpp:530
     }
     __syncthreads(); // B1: every tap read of this layer's input is done
 
     // ---- phase 2: persist the tail of h_l, then h_{l+1} = h_l + p + P a  (model.cpp:243,376)
     const bool last = (li + 1 == A.n_layers);
-    float2 hn[S][C / 2];
+    u64 hn[S][C / 2];
 #pragma unroll
     for (int j = 0; j < S; j++)
     {
       const int trel = j * NT + tid;
-      const bool keep = (trel < Tv) && (trel >= Tv - L.lookback);
+      const bool keep = (trel < Tv) && (trel >= Tv - lookback);
 #pragma unroll
       for (int pl = 0; pl < P; pl++)
       {
         const float4 own = tile[pl * TW + kHalo + trel];
         if (keep)
-          st_ring(ring + pl * R + ((tabs0 + (uint32_t)trel) & L.ring_mask), own);
+          st_ring(ring + pl * R + ((tabs0 + (uint32_t)trel) & ring_mask), own);
         const float4 pb = *reinterpret_cast<const float4*>(w_pb + 4 * pl);
-        hn[j][2 * pl] = make_float2(own.x + pb.x, own.y + pb.y);
-        hn[j][2 * pl + 1] = make_float2(own.z + pb.z, own.w + pb.w);
+        hn[j][2 * pl] = pack2(own.x + pb.x, own.y + pb.y);
+        hn[j][2 * pl + 1] = pack2(own.z + pb.z, own.w + pb.w);
       }
     }
 #pragma unroll
     for (int i = 0; i < C; i++)
     {
-      const float* __restrict__ w_row = w_p + i * C;
+      const float* __restrict__ p_row = w_p + i * C;
 #pragma unroll
       for (int j = 0; j < S; j++)
-        axpy_row<C>(hn[j], w_row, a[j][i]);
+        axpy_row<C>(hn[j], p_row, a[j][i]);
     }
 #pragma unroll
     for (int j = 0; j < S; j++)
@@ -299,17 +353,18 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
       {
 #pragma unroll
         for (int pl = 0; pl < P; pl++)
-          tile[pl * TW + kHalo + trel] =
-            make_float4(hn[j][2 * pl].x, hn[j][2 * pl].y, hn[j][2 * pl + 1].x, hn[j][2 * pl + 1].y);
+        {
+          float4 v;
+          unpack2(hn[j][2 * pl], v.x, v.y);
+          unpack2(hn[j][2 * pl + 1], v.z, v.w);
+          tile[pl * TW + kHalo + trel] = v;
+        }
       }
       else
       {
 #pragma unroll
         for (int q = 0; q < C / 2; q++)
-        {
-          hout[j][2 * q] = hn[j][q].x;
-          hout[j][2 * q + 1] = hn[j][q].y;
-        }
+          unpack2(hn[j][q], hout[j][2 * q], hout[j][2 * q + 1]);
       }
     }
   }
@@ -319,43 +374,41 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
 #pragma unroll
   for (int j = 0; j < S; j++)
   {
+    float hd[C];
+#pragma unroll
+    for (int q = 0; q < C / 2; q++)
+      unpack2(head[j][q], hd[2 * q], hd[2 * q + 1]);
     if constexpr (HOUT == 1)
     {
       float s = 0.0f;
 #pragma unroll
-      for (int q = 0; q < C / 2; q++)
-      {
-        s = fmaf(wh[2 * q], head[j][q].x, s);
-        s = fmaf(wh[2 * q + 1], head[j][q].y, s);
-      }
+      for (int i = 0; i < C; i++)
+        s = fmaf(wh[i], hd[i], s);
       headout[j][0] = s + wh[C];
     }
     else
     {
-      float2 ho[HOUT / 2];
+      u64 ho[HOUT / 2];
 #pragma unroll
-      for (int q = 0; q < HOUT / 2; q++)
-        ho[q] = make_float2(0.0f, 0.0f);
-#pragma unroll
-      for (int q = 0; q < C / 2; q++)
+      for (int q = 0; q < HOUT / 4; q++)
       {
-        axpy_row<HOUT>(ho, wh + (2 * q) * HOUT, head[j][q].x);
-        axpy_row<HOUT>(ho, wh + (2 * q + 1) * HOUT, head[j][q].y);
+        const float4 g = *reinterpret_cast<const float4*>(wh + C * HOUT + 4 * q);
+        ho[2 * q] = pack2(g.x, g.y);
+        ho[2 * q + 1] = pack2(g.z, g.w);
       }
 #pragma unroll
+      for (int i = 0; i < C; i++)
+        axpy_row<HOUT>(ho, wh + i * HOUT, hd[i]);
+#pragma unroll
       for (int q = 0; q < HOUT / 2; q++)
-      {
-        const float2 g = *reinterpret_cast<const float2*>(wh + C * HOUT + 2 * q);
-        headout[j][2 * q] = ho[q].x + g.x;
-        headout[j][2 * q + 1] = ho[q].y + g.y;
-      }
+        unpack2(ho[q], headout[j][2 * q], headout[j][2 * q + 1]);
     }
   }
 }
 
 // One persistent CTA per stream-slot.  C1 == 0: single layer array.
-template <int C0, int C1, int S, int NT>
-__global__ void __launch_bounds__(NT) wavenet_fused_kernel(const __grid_constant__ WaveNetKernelParams p)
+template <int C0, int C1, int S, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_constant__ WaveNetKernelParams p)
 {
   constexpr int T = S * NT;
   constexpr int CMAX = (C0 > C1) ? C0 : C1;
@@ -396,12 +449,12 @@ __global__ void __launch_bounds__(NT) wavenet_fused_kernel(const __grid_constant
       float y[S];
       if constexpr (C1 == 0)
       {
-        float2 head0[S][C0 / 2];
+        u64 head0[S][C0 / 2];
 #pragma unroll
         for (int j = 0; j < S; j++)
 #pragma unroll
           for (int q = 0; q < C0 / 2; q++)
-            head0[j][q] = make_float2(0.0f, 0.0f); // model.cpp:469
+            head0[j][q] = 0ull; // model.cpp:469
         float hout0[S][C0], ho0[S][1];
         array_forward<1, C0, 1, S, NT>(p, p.arrays[0], sw, tile, state, tabs0, Tv, x, cond, head0, hout0, ho0);
 #pragma unroll
@@ -412,22 +465,22 @@ __global__ void __launch_bounds__(NT) wavenet_fused_kernel(const __grid_constant
       {
         float hout0[S][C0], ho0[S][C1];
         {
-          float2 head0[S][C0 / 2];
+          u64 head0[S][C0 / 2];
 #pragma unroll
           for (int j = 0; j < S; j++)
 #pragma unroll
             for (int q = 0; q < C0 / 2; q++)
-              head0[j][q] = make_float2(0.0f, 0.0f);
+              head0[j][q] = 0ull;
           array_forward<1, C0, C1, S, NT>(p, p.arrays[0], sw, tile, state, tabs0, Tv, x, cond, head0, hout0, ho0);
         }
         // second array: layer input = previous array's layer output, head accumulator starts from
         // the previous array's head output (model.cpp:846-848, :473-486)
-        float2 head1[S][C1 / 2];
+        u64 head1[S][C1 / 2];
 #pragma unroll
         for (int j = 0; j < S; j++)
 #pragma unroll
           for (int q = 0; q < C1 / 2; q++)
-            head1[j][q] = make_float2(ho0[j][2 * q], ho0[j][2 * q + 1]);
+            head1[j][q] = pack2(ho0[j][2 * q], ho0[j][2 * q + 1]);
         float hout1[S][C1], ho1[S][1];
         array_forward<C0, C1, 1, S, NT>(p, p.arrays[1], sw, tile, state, tabs0, Tv, hout0, cond, head1, hout1, ho1);
 #pragma unroll

@@ -240,7 +240,8 @@ class DSP:
             _raise(rc, self._lib)
 
 
-def _options(lib, batch: int, device: int, prewarm: Optional[bool], fast_tanh: Optional[bool], ctas_per_sm: int):
+def _options(lib, batch: int, device: int, prewarm: Optional[bool], fast_tanh: Optional[bool], ctas_per_sm: int,
+             kernel_geometry: int = 0):
     o = _capi.Options()
     lib.nam_b200_default_options(C.byref(o))
     o.device = int(device)
@@ -248,11 +249,12 @@ def _options(lib, batch: int, device: int, prewarm: Optional[bool], fast_tanh: O
     o.fast_tanh = int(_using_fast_tanh if fast_tanh is None else bool(fast_tanh))
     o.prewarm_on_reset = 1 if prewarm is None else int(bool(prewarm))
     o.ctas_per_sm = int(ctas_per_sm)
+    o.kernel_geometry = int(kernel_geometry)
     return o
 
 
 def get_dsp(config, batch: int = 1, device: int = -1, prewarm: Optional[bool] = None,
-            fast_tanh: Optional[bool] = None, ctas_per_sm: int = 0) -> DSP:
+            fast_tanh: Optional[bool] = None, ctas_per_sm: int = 0, kernel_geometry: int = 0) -> DSP:
     """nam::get_dsp: `config` is a path to a .nam file, a dict (parsed .nam) or a JSON string.
 
     batch      number of independent streams the handle carries (the reference: one DSP object each)
@@ -262,7 +264,7 @@ def get_dsp(config, batch: int = 1, device: int = -1, prewarm: Optional[bool] = 
     import json
 
     lib = _capi.load()
-    o = _options(lib, batch, device, prewarm, fast_tanh, ctas_per_sm)
+    o = _options(lib, batch, device, prewarm, fast_tanh, ctas_per_sm, kernel_geometry)
     h = C.c_void_p()
     if isinstance(config, (str, os.PathLike)) and not (isinstance(config, str) and config.lstrip().startswith("{")):
         rc = lib.nam_b200_create_from_file(str(Path(config)).encode(), C.byref(o), C.byref(h))
