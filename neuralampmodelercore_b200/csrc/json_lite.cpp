@@ -1,6 +1,7 @@
 #include "json_lite.h"
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -300,6 +301,89 @@ Value Value::parse(const std::string& text)
 {
   Parser p(text);
   return p.parse_document();
+}
+
+namespace
+{
+void dump_string(const std::string& s, std::string& out)
+{
+  out.push_back('"');
+  for (const char ch : s)
+  {
+    switch (ch)
+    {
+      case '"': out += "\\\""; break;
+      case '\\': out += "\\\\"; break;
+      case '\n': out += "\\n"; break;
+      case '\r': out += "\\r"; break;
+      case '\t': out += "\\t"; break;
+      default:
+        if ((unsigned char)ch < 0x20)
+        {
+          char buf[8];
+          std::snprintf(buf, sizeof(buf), "\\u%04x", (unsigned)(unsigned char)ch);
+          out += buf;
+        }
+        else
+          out.push_back(ch);
+    }
+  }
+  out.push_back('"');
+}
+
+void dump_value(const Value& v, std::string& out)
+{
+  switch (v.type())
+  {
+    case Value::Type::Null: out += "null"; break;
+    case Value::Type::Bool: out += v.as_bool() ? "true" : "false"; break;
+    case Value::Type::Number:
+    {
+      char buf[40];
+      std::snprintf(buf, sizeof(buf), "%.17g", v.as_double());
+      out += buf;
+      break;
+    }
+    case Value::Type::String: dump_string(v.as_string(), out); break;
+    case Value::Type::Array:
+    {
+      out.push_back('[');
+      bool first = true;
+      for (const auto& it : v.items())
+      {
+        if (!first)
+          out.push_back(',');
+        first = false;
+        dump_value(it, out);
+      }
+      out.push_back(']');
+      break;
+    }
+    case Value::Type::Object:
+    {
+      out.push_back('{');
+      bool first = true;
+      for (const auto& kv : v.members())
+      {
+        if (!first)
+          out.push_back(',');
+        first = false;
+        dump_string(kv.first, out);
+        out.push_back(':');
+        dump_value(kv.second, out);
+      }
+      out.push_back('}');
+      break;
+    }
+  }
+}
+} // namespace
+
+std::string Value::dump() const
+{
+  std::string out;
+  dump_value(*this, out);
+  return out;
 }
 
 bool Value::as_bool(const char* what) const

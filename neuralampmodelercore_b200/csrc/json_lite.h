@@ -70,6 +70,8 @@ public:
   bool value_bool(const std::string& key, bool dflt) const;
 
   static Value parse(const std::string& text);
+  /// Compact JSON text of this value (numbers printed with enough digits to round-trip a double).
+  std::string dump() const;
 
 private:
   friend class Parser;

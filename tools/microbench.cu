@@ -52,20 +52,26 @@ __global__ void fma_peak(float* out, int iters, float seed)
     out[0] = s;
 }
 
-constexpr int kRows = 1024; // weight rows of 16 floats (64 KB would be the whole a1 model; 1024 rows = 64 KB)
-__constant__ float4 c_weights[kRows * 4 / 4 * 1]; // 1024 float4 = 16 KB (constant memory variant uses 256 rows)
+constexpr int kRows = 1024; // weight rows of 16 floats in the shared-memory variant (64 KB)
+constexpr int kConstRows = 896; // 896 rows x 16 floats = 56 KB: the size of the a1_standard weight blob
+__constant__ float4 c_weights[kConstRows * 4];
 
 // S time steps per thread, 16 output channels (8 float2 accumulators per time step)
-template <int S, bool FROM_CONST>
+// TAPS: every 4 rows (one plane of 4 input channels) each thread also fetches its S input vectors with
+// per-lane LDS.128 (4 wavefronts each), like the real kernel's dilated-tap reads.
+template <int S, bool FROM_CONST, bool TAPS>
 __global__ void __launch_bounds__(128) inner_loop(const float4* __restrict__ w, float* out, int rows, int iters)
 {
   extern __shared__ float4 sw[];
+  __shared__ float4 taps[4 * 160];
   if (!FROM_CONST)
   {
     for (int i = threadIdx.x; i < rows * 4; i += blockDim.x)
       sw[i] = w[i];
-    __syncthreads();
   }
+  for (int i = threadIdx.x; i < 4 * 160; i += blockDim.x)
+    taps[i] = make_float4(1e-3f * i, 2e-3f * i, -1e-3f * i, 1e-4f * i);
+  __syncthreads();
   float2 acc[S][8];
   float x[S];
 #pragma unroll
@@ -81,10 +87,19 @@ __global__ void __launch_bounds__(128) inner_loop(const float4* __restrict__ w, 
 #pragma unroll 4
     for (int r = 0; r < rows; r++)
     {
+      if (TAPS && (r & 3) == 0)
+      {
+#pragma unroll
+        for (int j = 0; j < S; j++)
+        {
+          const float4 t = taps[((r >> 2) & 3) * 160 + ((threadIdx.x + 8 * j + it) & 127)];
+          x[j] = t.x + t.y + t.z + t.w;
+        }
+      }
       float4 wq[4];
 #pragma unroll
       for (int q = 0; q < 4; q++)
-        wq[q] = FROM_CONST ? c_weights[(r & 255) * 4 + q] : sw[r * 4 + q];
+        wq[q] = FROM_CONST ? c_weights[r * 4 + q] : sw[r * 4 + q];
 #pragma unroll
       for (int j = 0; j < S; j++)
       {
@@ -159,13 +174,14 @@ int main()
   float4* dw;
   CK(cudaMalloc(&dw, hw.size() * sizeof(float4)));
   CK(cudaMemcpy(dw, hw.data(), hw.size() * sizeof(float4), cudaMemcpyHostToDevice));
-  CK(cudaMemcpyToSymbol(c_weights, hw.data(), sizeof(float4) * 1024));
-  const int rows = 1024, iters = 64;
-  const size_t smem = rows * 4 * sizeof(float4); // 64 KB
-#define RUN_INNER(SVAL, CONSTV)                                                                                      \
-  for (int ctas_per_sm : {1, 2, 3})                                                                                  \
+  CK(cudaMemcpyToSymbol(c_weights, hw.data(), sizeof(float4) * kConstRows * 4));
+  const int iters = 64;
+  const size_t smem = kRows * 4 * sizeof(float4); // 64 KB
+#define RUN_INNER(SVAL, CONSTV, TAPSV)                                                                               \
+  for (int ctas_per_sm : {1, 2, 3, 4})                                                                               \
   {                                                                                                                  \
-    auto kern = inner_loop<SVAL, CONSTV>;                                                                            \
+    const int rows = CONSTV ? kConstRows : kRows;                                                                    \
+    auto kern = inner_loop<SVAL, CONSTV, TAPSV>;                                                                     \
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
     const int blocks = sms * ctas_per_sm;                                                                            \
     double best = 1e30;                                                                                              \
@@ -177,15 +193,16 @@ int main()
       best = fmin(best, time_ms(e0, e1));                                                                            \
     }                                                                                                                \
     const double fma = 16.0 * SVAL * rows * (double)iters * blocks * 128;                                            \
-    printf("{\"test\": \"inner_loop\", \"S\": %d, \"weights\": \"%s\", \"ctas_per_sm\": %d, \"tflops\": %.2f, "       \
+    printf("{\"test\": \"inner_loop\", \"S\": %d, \"weights\": \"%s\", \"taps\": %d, \"ctas_per_sm\": %d, \"tflops\": %.2f, " \
            "\"fma_per_clk_per_sm_at_max_clock\": %.1f}\n",                                                           \
-           SVAL, CONSTV ? "constant" : "shared", ctas_per_sm, 2 * fma / (best * 1e-3) / 1e12,                        \
+           SVAL, CONSTV ? "constant" : "shared", (int)TAPSV, ctas_per_sm, 2 * fma / (best * 1e-3) / 1e12,            \
            fma / (best * 1e-3) / sms / (clock_khz * 1e3));                                                           \
   }
-  RUN_INNER(1, false)
-  RUN_INNER(2, false)
-  RUN_INNER(4, false)
-  RUN_INNER(2, true)
-  RUN_INNER(4, true)
+  RUN_INNER(2, false, false)
+  RUN_INNER(2, false, true)
+  RUN_INNER(4, false, true)
+  RUN_INNER(2, true, false)
+  RUN_INNER(2, true, true)
+  RUN_INNER(4, true, true)
   return 0;
 }
