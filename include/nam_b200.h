@@ -55,7 +55,9 @@ typedef struct nam_b200_options
   int32_t fast_tanh; /* 1 = Activation::enable_fast_tanh() was called before loading (benchmodel default) */
   int32_t prewarm_on_reset; /* 1 (reference default) = reset() prewarms; 0 = SetPrewarmOnReset(false) */
   int32_t ctas_per_sm; /* 0 = library default; tuning knob for the persistent WaveNet kernel */
-  int32_t kernel_geometry; /* 0 = library default; 1 = 128-thread CTAs (tile 256), 2 = 256-thread CTAs (tile 512) */
+  int32_t kernel_geometry; /* WaveNet kernel: 0 = library default; 1 = FP32 FFMA2 kernel, 128-thread CTAs (tile 256);
+                              2 = FP32 FFMA2 kernel, 256-thread CTAs (tile 512); 3 = tensor-core kernel (tcgen05,
+                              3xTF32 split, tile 128) */
   int32_t reserved[7];
 } nam_b200_options;
 

@@ -18,6 +18,7 @@
 #include "nam_model_spec.h"
 #include "wavenet_fused.cuh"
 #include "wavenet_pack.h"
+#include "wavenet_tc.cuh"
 
 using namespace namb200;
 
@@ -327,7 +328,8 @@ struct nam_b200_model
   WaveNetPlan plan;
   int variant = 0;
   int wn_ctas_per_sm = 0; // resident CTAs per SM of the fused kernel (occupancy query, cached)
-  int wn_geometry = 1; // index into kWnGeom
+  int wn_geometry = 1; // 0 / 1: index into kWnGeom (FFMA kernel); 2: tensor-core kernel (wavenet_tc.cuh)
+  float* d_tc_blob = nullptr; // per-layer B-operand images of the tensor-core kernel
   // LSTM / Linear packed weights
   std::vector<float> host_weights;
   float* d_weights = nullptr;
@@ -349,6 +351,8 @@ struct nam_b200_model
     cudaSetDevice(device);
     if (d_weights)
       cudaFree(d_weights);
+    if (d_tc_blob)
+      cudaFree(d_tc_blob);
     if (d_state)
       cudaFree(d_state);
     if (d_state_tmp)
@@ -449,6 +453,59 @@ size_t wavenet_smem_bytes(const WaveNetPlan& plan, int geom)
   return (plan.blob.size() + 3) / 4 * 16 + tile4 * 16;
 }
 
+// ---- tensor-core variant dispatch ---------------------------------------------------------------
+size_t tc_smem_bytes(const WaveNetPlan& plan)
+{
+  const int cmax = std::max(plan.cp[0], plan.cp[1]);
+  const size_t pm = cmax / 4;
+  const size_t wimg4 = (size_t)(plan.tc_max_image_floats + 3) / 4;
+  return (2 * wimg4 + 2 * pm * kTcTW + 4 * pm * kTcM) * 16;
+}
+
+template <int C0, int C1>
+void launch_tc_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem, cudaStream_t st)
+{
+  auto kern = wavenet_tc_kernel<C0, C1>;
+  // the kernel also has a few bytes of static shared memory (mbarriers), so ask for what is needed, not the maximum
+  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kTcM, smem, st>>>(kp, (int)((m->plan.tc_max_image_floats + 3) / 4), (int)m->plan.layers.size());
+  CUDA_CHECK(cudaGetLastError());
+}
+
+template <int C0, int C1>
+int occupancy_tc_variant(size_t smem)
+{
+  auto kern = wavenet_tc_kernel<C0, C1>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kTcM, smem) != cudaSuccess)
+    return 1;
+  return n > 0 ? n : 1;
+}
+
+#define TC_DISPATCH(FN, ...)                                                                                         \
+  switch (c0 * 100 + c1)                                                                                             \
+  {                                                                                                                  \
+    case 800: return FN<8, 0>(__VA_ARGS__);                                                                          \
+    case 1600: return FN<16, 0>(__VA_ARGS__);                                                                        \
+    case 808: return FN<8, 8>(__VA_ARGS__);                                                                          \
+    case 816: return FN<8, 16>(__VA_ARGS__);                                                                         \
+    case 1608: return FN<16, 8>(__VA_ARGS__);                                                                        \
+    case 1616: return FN<16, 16>(__VA_ARGS__);                                                                       \
+    default: throw std::runtime_error("no tensor-core WaveNet kernel for channel pair " + std::to_string(c0) + "/"   \
+                                      + std::to_string(c1));                                                         \
+  }
+
+void launch_tc_dispatch(int c0, int c1, nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem,
+                        cudaStream_t st)
+{
+  TC_DISPATCH(launch_tc_variant, m, kp, grid, smem, st)
+}
+int occupancy_tc_dispatch(int c0, int c1, size_t smem)
+{
+  TC_DISPATCH(occupancy_tc_variant, smem)
+}
+
 void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batch, int n_frames, long in_stride,
                     long out_stride, cudaStream_t st)
 {
@@ -472,8 +529,27 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
   for (size_t i = 0; i < plan.layers.size(); i++)
     kp.layers[i] = plan.layers[i];
   const int geom = m->wn_geometry;
-  const size_t smem = wavenet_smem_bytes(plan, geom);
   const int c0 = plan.cp[0], c1 = plan.n_arrays > 1 ? plan.cp[1] : 0;
+  if (geom == 2)
+  {
+    // tensor-core variant (wavenet_tc.cuh)
+    kp.tc_blob = m->d_tc_blob;
+    for (size_t i = 0; i < plan.layers.size(); i++)
+    {
+      kp.tc_off[i] = plan.tc_off[i];
+      kp.tc_floats[i] = plan.tc_floats[i];
+    }
+    const size_t smem_tc = tc_smem_bytes(plan);
+    if (m->wn_ctas_per_sm <= 0)
+      m->wn_ctas_per_sm = m->opts.ctas_per_sm > 0 ? m->opts.ctas_per_sm : occupancy_tc_dispatch(c0, c1, smem_tc);
+    int grid_tc = std::min(batch, m->wn_ctas_per_sm * m->sm_count);
+    if (grid_tc < 1)
+      grid_tc = 1;
+    launch_tc_dispatch(c0, c1, m, kp, grid_tc, smem_tc, st);
+    m->launches++;
+    return;
+  }
+  const size_t smem = wavenet_smem_bytes(plan, geom);
   if (m->wn_ctas_per_sm <= 0)
     m->wn_ctas_per_sm = m->opts.ctas_per_sm > 0 ? m->opts.ctas_per_sm : occupancy_wavenet_dispatch(c0, c1, geom, smem);
   const int per_sm = m->wn_ctas_per_sm;
@@ -708,8 +784,21 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
         m->state_stride = m->plan.state_floats;
         m->flops_per_frame = 2.0 * m->plan.macs_per_frame;
         m->variant = m->plan.cp[0] * 100 + (m->plan.n_arrays > 1 ? m->plan.cp[1] : 0);
-        m->wn_geometry = (m->opts.kernel_geometry == 1) ? 0 : 1; // option: 0 default, 1 = 128-thread, 2 = 256-thread
-        if (wavenet_smem_bytes(m->plan, m->wn_geometry) > 227 * 1024)
+        // option: 0 default, 1 = FFMA 128-thread, 2 = FFMA 256-thread, 3 = tensor-core (tcgen05)
+        if (m->opts.kernel_geometry == 3)
+        {
+          if (!m->plan.tc_eligible)
+            return fail(NAM_B200_ERR_UNSUPPORTED, "tensor-core kernel not available for this model: " + m->plan.tc_why_not);
+          m->wn_geometry = 2;
+          if (tc_smem_bytes(m->plan) > 227 * 1024)
+            return fail(NAM_B200_ERR_UNSUPPORTED, "tensor-core kernel: tiles do not fit in shared memory");
+          CUDA_CHECK(cudaMalloc(&m->d_tc_blob, m->plan.tc_blob.size() * sizeof(float)));
+          CUDA_CHECK(cudaMemcpy(m->d_tc_blob, m->plan.tc_blob.data(), m->plan.tc_blob.size() * sizeof(float),
+                                cudaMemcpyHostToDevice));
+        }
+        else
+          m->wn_geometry = (m->opts.kernel_geometry == 1) ? 0 : 1;
+        if (m->wn_geometry < 2 && wavenet_smem_bytes(m->plan, m->wn_geometry) > 227 * 1024)
           return fail(NAM_B200_ERR_UNSUPPORTED, "WaveNet weights do not fit in shared memory");
         break;
       }
