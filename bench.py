@@ -44,7 +44,7 @@ CPU_BLOCK = 64  # AUDIO_BUFFER_SIZE of tools/benchmodel.cpp:18
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="streams per GPU")
@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--tanh", default="fast", choices=["fast", "exact"],
                     help="fast = tools/benchmodel.cpp default (enable_fast_tanh); exact = library default")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
-    ap.add_argument("--geometry", type=int, default=0, help="0 default, 1 = 128-thread CTAs, 2 = 256-thread CTAs")
+    ap.add_argument("--geometry", type=int, default=0, help="0 default, 1 = FP32 kernel 128-thread CTAs, 2 = FP32 kernel 256-thread CTAs, 3 = tensor-core kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--gather", action="store_true", help="also time an NCCL all_gather of one step's outputs")

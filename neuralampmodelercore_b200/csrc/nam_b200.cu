@@ -468,7 +468,8 @@ void launch_tc_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int gri
   auto kern = wavenet_tc_kernel<C0, C1>;
   // the kernel also has a few bytes of static shared memory (mbarriers), so ask for what is needed, not the maximum
   CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kTcM, smem, st>>>(kp, (int)((m->plan.tc_max_image_floats + 3) / 4), (int)m->plan.layers.size());
+  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  kern<<<grid, kTcThreads, smem, st>>>(kp, (int)((m->plan.tc_max_image_floats + 3) / 4), (int)m->plan.layers.size());
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -477,10 +478,10 @@ int occupancy_tc_variant(size_t smem)
 {
   auto kern = wavenet_tc_kernel<C0, C1>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kTcM, smem) != cudaSuccess)
-    return 1;
-  return n > 0 ? n : 1;
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  // shared memory decides (227 KB per SM, 1 KB reserved per CTA); registers allow 3 (launch bounds)
+  const int by_smem = (int)((227 * 1024) / (smem + 1024 + 64));
+  return std::max(1, std::min(3, by_smem));
 }
 
 #define TC_DISPATCH(FN, ...)                                                                                         \

@@ -1,28 +1,34 @@
 // wavenet_tc.cuh -- tensor-core (tcgen05 / TMEM) variant of the fused WaveNet kernel for sm_100a.
 //
 // Same reference code replaced as wavenet_fused.cuh (NAM/wavenet/model.cpp:183-393,463-549,822-910,
-// NAM/conv1d.cpp:163-183,666-683, NAM/dsp.cpp:436-836), same per-stream ring state, same thread <-> time-step
-// ownership -- but the two matrix products of a layer run on the 5th-generation tensor cores:
+// NAM/conv1d.cpp:163-183,666-683, NAM/dsp.cpp:436-836), same per-stream ring state -- but the two matrix
+// products of a layer run on the 5th-generation tensor cores:
 //
 //   Z[128 x 16] = sum_taps  H_l[t - off, :] . W_tap          conv   (tcgen05.mma kind::tf32, D in TMEM)
 //   D[128 x 16] = act(Z) . P                                 layer1x1
 //
-// with M = 128 = time steps of the CTA's tile (TMEM lane == thread == time step), N = 16 output channels,
-// K = 8 input channels per instruction.  The activation layout "planes of 4 channels, [C/4][time][4 floats]"
-// is exactly the UMMA K-major no-swizzle canonical layout (core matrix = 8 consecutive time steps x 16 B), so a
-// dilated tap is nothing but a shared-memory descriptor whose start address is shifted by `off` rows: no
-// im2col, no copies -- all taps accumulate into one TMEM tile.
+// with M = 128 = time steps of the CTA's tile (TMEM lane == time step), N = 16 output channels, K = 8 input
+// channels per instruction.  The activation layout "planes of 4 channels, [C/4][time][4 floats]" is exactly the
+// UMMA K-major no-swizzle canonical layout (core matrix = 8 consecutive time steps x 16 B), so a dilated tap is
+// nothing but a shared-memory descriptor whose start address is shifted by `off` rows: no im2col, no copies --
+// all taps accumulate into one TMEM tile.
 //
 // Precision: 1e-5 parity forbids single-pass TF32 (1.7e-3 error, profiles/r01_tc_probe_tf32_split.jsonl).
-// Each product is split x = hi + lo (hi = cvt.rna.tf32(x), lo = x - hi) and evaluated as
+// Each product is split x = hi + lo (hi = x rounded to TF32, lo = x - hi) and evaluated as
 // lo*hi + hi*lo + hi*hi with fp32 accumulation in TMEM: measured 2.4e-7 rms / 1e-6 max on O(1) outputs,
 // ~3x the rounding noise of an fp32 FMA chain.  The residual stream, head accumulator, bias/mixin adds and the
 // activations stay in fp32 registers, so errors do not compound through the tensor core.
 //
-// Per layer: [stage far taps] -> barrier -> thread 0 issues the conv MMAs -> commit -> all threads: tcgen05.ld
-// Z, +bias +mixin, activation, head += a, write a (hi/lo) to shared -> barrier -> 1x1 MMAs -> tcgen05.ld,
-// residual add in registers, write h_{l+1} (hi/lo) to the tile.  Weights of layer l+1 stream in with cp.async
-// while layer l computes (the hi/lo images of all layers, 110 KB, do not fit next to the tiles).
+// Threads: 256 per CTA, two per time step.  Thread (row, half) owns channels [half*C/2, (half+1)*C/2) of its
+// row: warps w and w+4 read the same 32 TMEM lanes, different columns.  That halves every epilogue and doubles
+// the warps available to hide the L2 / TMEM / MUFU latencies (the first version, one thread per row, sat at 29 %
+// issue-active: profiles/r01c_tc_kernel_v1.json).
+//
+// Per layer:  barrier -> thread 0 issues the conv MMAs -> commit;   meanwhile all threads stream in the next
+// layer's weights (cp.async), persist the tail of h_l to the ring and fetch the next layer's halo columns into
+// registers ->  wait -> tcgen05.ld Z, +bias +mixin, activation, head += a, write a (hi/lo) to shared ->
+// barrier -> 1x1 MMAs;  meanwhile fetch the next layer's far taps (off > 64) from the rings into registers ->
+// wait -> tcgen05.ld D, residual add in registers, write h_{l+1} (hi/lo) to the tile, store the staged taps.
 #pragma once
 
 #include "wavenet_fused.cuh"
@@ -30,7 +36,8 @@
 namespace namb200
 {
 
-constexpr int kTcM = 128; // threads per CTA = TMEM lanes = frames per tile
+constexpr int kTcM = 128; // frames per tile = TMEM lanes
+constexpr int kTcThreads = 256; // two threads per frame
 constexpr int kTcTW = kHalo + kTcM; // tile columns per 4-channel plane
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -38,29 +45,33 @@ __device__ __forceinline__ uint32_t tc_smem_u32(const void* p)
 {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
-// shared-memory matrix descriptor: K-major, SWIZZLE_NONE, version 1 (sm_100)
-__device__ __forceinline__ uint64_t tc_desc(const void* p, uint32_t lbo_bytes, uint32_t sbo_bytes)
+// Shared-memory matrix descriptor (K-major, SWIZZLE_NONE, version 1 = sm_100).  Low word: start address >> 4
+// in bits 0-13, leading-dimension byte offset >> 4 in bits 16-29; moving the start by n float4 is `lo + n`.
+// High word: stride-dimension byte offset (128 B between 8-row core matrices) >> 4, version bit 46.
+__device__ __forceinline__ uint32_t tc_desc_lo(const void* p, uint32_t lbo_bytes)
 {
-  const uint32_t a = tc_smem_u32(p);
-  return (uint64_t)((a & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32)
-         | (1ull << 46);
+  return ((tc_smem_u32(p) & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
 }
+constexpr uint32_t kTcDescHi = (128u >> 4) | (1u << 14);
 // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
 
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate)
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint32_t da_lo, uint32_t db_lo, uint32_t accumulate)
 {
   asm volatile(
     "{\n\t"
     ".reg .pred p;\n\t"
+    ".reg .b64 da, db;\n\t"
+    "mov.b64 da, {%1, %6};\n\t"
+    "mov.b64 db, {%2, %6};\n\t"
     "setp.ne.b32 p, %4, 0;\n\t"
-    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+    "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, {%5, %5, %5, %5}, p;\n\t"
     "}\n" ::"r"(tmem_d),
-    "l"(da), "l"(db), "r"(kTcIdesc), "r"(accumulate), "r"(0u)
+    "r"(da_lo), "r"(db_lo), "r"(kTcIdesc), "r"(accumulate), "r"(0u), "r"(kTcDescHi)
     : "memory");
 }
 // one logical product A.B as three TF32 MMAs, smallest terms first
-__device__ __forceinline__ void tc_mma3(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+__device__ __forceinline__ void tc_mma3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                         uint32_t accumulate)
 {
   tc_mma(tmem_d, a_lo, b_hi, accumulate);
@@ -72,15 +83,20 @@ __device__ __forceinline__ void tc_commit(uint64_t* mbar)
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(mbar))
                : "memory");
 }
+// One lane per warp polls the barrier (a polling warp costs issue slots that co-resident CTAs need).
 __device__ __forceinline__ void tc_mbar_wait(uint64_t* mbar, uint32_t parity)
 {
-  uint32_t done = 0;
-  while (!done)
-    asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(tc_smem_u32(mbar)), "r"(parity)
-      : "memory");
+  if ((threadIdx.x & 31) == 0)
+  {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(tc_smem_u32(mbar)), "r"(parity)
+        : "memory");
+  }
+  __syncwarp();
 }
 __device__ __forceinline__ void tc_fence_before()
 {
@@ -97,28 +113,26 @@ __device__ __forceinline__ void tc_fence_async_smem()
 template <int N>
 __device__ __forceinline__ void tc_ld(uint32_t taddr, float (&v)[N])
 {
-  static_assert(N == 8 || N == 16, "tcgen05.ld width");
-  uint32_t r[16];
-  if constexpr (N == 16)
-    asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  else
+  static_assert(N == 4 || N == 8, "tcgen05.ld width");
+  uint32_t r[8];
+  if constexpr (N == 8)
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+  else
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                  : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < N; i++)
     v[i] = __uint_as_float(r[i]);
 }
+// round to TF32, ties away from zero (what cvt.rna.tf32.f32 does, minus its Inf/NaN special-casing which
+// costs three more instructions per element and cannot matter: a non-finite input stays non-finite)
 __device__ __forceinline__ float tc_hi(float x)
 {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void tc_split4(const float4& v, float4& hi, float4& lo)
 {
@@ -138,6 +152,8 @@ struct TcSmem
   float4* tile_hi; // [P][kTcTW]
   float4* tile_lo;
   float4* ubuf; // a_hi [P][128] | a_lo [P][128]   aliased with   stage[2 slots][hi|lo][P][128]
+  float4* xch; // end of a layer array: the full fp32 residual rows [P][128] for the next array's rechannel ...
+  float4* hx; // ... and the partner thread's head-rechannel partial sums (both alias ubuf)
   uint64_t* mbar_z;
   uint64_t* mbar_h;
   uint32_t tmem;
@@ -149,118 +165,229 @@ __device__ __forceinline__ void tc_prefetch_weights(const WaveNetKernelParams& p
   const float4* src = reinterpret_cast<const float4*>(p.tc_blob + p.tc_off[gl]);
   float4* dst = sm.wbuf + buf * sm.wimg4;
   const int n4 = p.tc_floats[gl] >> 2;
-  for (int i = threadIdx.x; i < n4; i += kTcM)
+  for (int i = threadIdx.x; i < n4; i += kTcThreads)
     tc_cp_async16(dst + i, src + i);
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-template <int C>
-__device__ __forceinline__ void tc_store_column(float4* __restrict__ hi_base, float4* __restrict__ lo_base, int stride,
-                                                int col, const float (&v)[C])
+// this thread's PH planes of one column, split into hi / lo
+template <int PH>
+__device__ __forceinline__ void tc_store_planes(float4* __restrict__ hi_base, float4* __restrict__ lo_base, int stride,
+                                                int pl0, int col, const float (&v)[4 * PH])
 {
 #pragma unroll
-  for (int pl = 0; pl < C / 4; pl++)
+  for (int q = 0; q < PH; q++)
   {
     float4 hi, lo;
-    tc_split4(make_float4(v[4 * pl], v[4 * pl + 1], v[4 * pl + 2], v[4 * pl + 3]), hi, lo);
-    hi_base[pl * stride + col] = hi;
-    lo_base[pl * stride + col] = lo;
+    tc_split4(make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), hi, lo);
+    hi_base[(pl0 + q) * stride + col] = hi;
+    lo_base[(pl0 + q) * stride + col] = lo;
   }
 }
 
-// ring tail [t0 - halo, t0) of layer L -> halo columns of the tile (split into hi / lo on the way)
+// Halo columns [t0 - halo, t0) of layer L's input come from its ring: one (plane, column) item per thread.
+struct TcHaloItem
+{
+  bool valid;
+  int dst; // float4 index into the tile
+  float4 v;
+};
 template <int C>
-__device__ __forceinline__ void tc_halo_fill(const LayerDesc& L, const TcSmem& sm, const float* __restrict__ state,
+__device__ __forceinline__ void tc_halo_load(TcHaloItem& it, const LayerDesc& L, const float* __restrict__ state,
                                              uint32_t tabs0)
 {
   constexpr int P = C / 4;
   const int halo = L.lookback < kHalo ? L.lookback : kHalo;
-  const float4* __restrict__ ring = reinterpret_cast<const float4*>(state + L.ring_off);
-  const int R = L.ring_mask + 1;
-  for (int idx = threadIdx.x; idx < halo * P; idx += kTcM)
+  const int col = threadIdx.x & (kHalo - 1), pl = threadIdx.x >> 6; // kHalo == 64
+  it.valid = (pl < P) && (col >= kHalo - halo);
+  it.dst = pl * kTcTW + col;
+  if (it.valid)
   {
-    const int pl = idx / halo, col = idx - pl * halo;
-    const float4 v = ld_ring(ring + pl * R + ((tabs0 - (uint32_t)halo + (uint32_t)col) & (uint32_t)L.ring_mask));
+    const float4* __restrict__ ring = reinterpret_cast<const float4*>(state + L.ring_off);
+    it.v = ld_ring(ring + pl * (L.ring_mask + 1) + ((tabs0 - (uint32_t)kHalo + (uint32_t)col) & (uint32_t)L.ring_mask));
+  }
+}
+__device__ __forceinline__ void tc_halo_store(const TcHaloItem& it, const TcSmem& sm)
+{
+  if (it.valid)
+  {
     float4 hi, lo;
-    tc_split4(v, hi, lo);
-    sm.tile_hi[pl * kTcTW + kHalo - halo + col] = hi;
-    sm.tile_lo[pl * kTcTW + kHalo - halo + col] = lo;
+    tc_split4(it.v, hi, lo);
+    sm.tile_hi[it.dst] = hi;
+    sm.tile_lo[it.dst] = lo;
   }
 }
 
+// Taps whose window [t0 - off, t0 - off + 128) is not inside halo + tile (off > 64) are staged as their own
+// A operand, at most two per layer (wavenet_pack.cpp refuses more), in tap order.  The part of the window that
+// lies before t0 comes from the ring (fetched early, into registers); the part inside the current tile (only
+// when 64 < off < 128) is copied from the tile once it is complete.
+__device__ __forceinline__ void tc_staged_offsets(const LayerDesc& L, int (&off)[2])
+{
+  off[0] = off[1] = 0;
+  int n = 0;
+  for (int k = 0; k < L.kernel - 1; k++)
+  {
+    const int o = (L.kernel - 1 - k) * L.dilation;
+    if (o > kHalo)
+    {
+      if (n == 0)
+        off[0] = o;
+      else if (n == 1)
+        off[1] = o;
+      n++;
+    }
+  }
+}
+template <int PH>
+struct TcStage
+{
+  int off[2]; // 0 = slot unused
+  float4 v[2][PH];
+};
+template <int C>
+__device__ __forceinline__ void tc_stage_load(TcStage<C / 8>& s, const LayerDesc& L, const float* __restrict__ state,
+                                              uint32_t tabs0, int row, int pl0)
+{
+  constexpr int PH = C / 8;
+  tc_staged_offsets(L, s.off);
+  const float4* __restrict__ ring = reinterpret_cast<const float4*>(state + L.ring_off);
+  const int R = L.ring_mask + 1;
+#pragma unroll
+  for (int slot = 0; slot < 2; slot++)
+  {
+    const int rel = row - s.off[slot];
+    if (s.off[slot] != 0 && rel < 0)
+    {
+#pragma unroll
+      for (int q = 0; q < PH; q++)
+        s.v[slot][q] = ld_ring(ring + (pl0 + q) * R + ((tabs0 + (uint32_t)rel) & (uint32_t)L.ring_mask));
+    }
+  }
+}
+// returns true when some rows still have to be copied from the tile (tc_stage_copy, after a barrier)
+template <int C>
+__device__ __forceinline__ bool tc_stage_store(const TcStage<C / 8>& s, const TcSmem& sm, int row, int pl0)
+{
+  constexpr int PH = C / 8, P = C / 4;
+  bool reads_tile = false;
+#pragma unroll
+  for (int slot = 0; slot < 2; slot++)
+  {
+    const int off = s.off[slot];
+    reads_tile |= (off != 0) && (off < kTcM);
+    if (off != 0 && row - off < 0)
+    {
+      float4* st_hi = sm.ubuf + slot * (2 * P * kTcM);
+      float4* st_lo = st_hi + P * kTcM;
+#pragma unroll
+      for (int q = 0; q < PH; q++)
+      {
+        float4 hi, lo;
+        tc_split4(s.v[slot][q], hi, lo);
+        st_hi[(pl0 + q) * kTcM + row] = hi;
+        st_lo[(pl0 + q) * kTcM + row] = lo;
+      }
+    }
+  }
+  return reads_tile;
+}
+template <int C>
+__device__ __forceinline__ void tc_stage_copy(const TcStage<C / 8>& s, const TcSmem& sm, int row, int pl0)
+{
+  constexpr int PH = C / 8, P = C / 4;
+#pragma unroll
+  for (int slot = 0; slot < 2; slot++)
+  {
+    const int rel = row - s.off[slot];
+    if (s.off[slot] != 0 && rel >= 0)
+    {
+      float4* st_hi = sm.ubuf + slot * (2 * P * kTcM);
+      float4* st_lo = st_hi + P * kTcM;
+#pragma unroll
+      for (int q = 0; q < PH; q++)
+      {
+        st_hi[(pl0 + q) * kTcM + row] = sm.tile_hi[(pl0 + q) * kTcTW + kHalo + rel];
+        st_lo[(pl0 + q) * kTcM + row] = sm.tile_lo[(pl0 + q) * kTcTW + kHalo + rel];
+      }
+    }
+  }
+}
+
+// One layer array on one tile.  `head` (this thread's half of the head accumulator) comes in holding the
+// previous array's head output, `headout` leaves with this array's: HOUT == 1 -> the model output (valid in the
+// half == 0 thread of each row), else this thread's half of the next array's head input.  For CIN > 1 the input
+// rows are read from sm.xch, where the previous array left them; if HOUT > 1 this array leaves its own there.
 template <int CIN, int C, int HOUT>
 __device__ __forceinline__ void tc_array_forward(const WaveNetKernelParams& p, const ArrayDesc& A, const TcSmem& sm,
                                                  float* __restrict__ state, const uint32_t tabs0, const int Tv,
                                                  const int total_layers, uint32_t& par_z, uint32_t& par_h,
-                                                 const float (&hin)[CIN], const float cond, float (&head)[C],
-                                                 float (&hout)[C], float (&headout)[HOUT])
+                                                 const float x, float (&head)[C / 2],
+                                                 float (&headout)[HOUT == 1 ? 1 : HOUT / 2])
 {
   constexpr int P = C / 4; // planes
+  constexpr int CH = C / 2; // channels per thread
+  constexpr int PH = C / 8; // planes per thread
   constexpr int KS = C / 8; // K-steps (8 input channels each) per tap
   const int tid = threadIdx.x;
+  const int row = tid & (kTcM - 1), hf = tid >> 7;
+  const int pl0 = hf * PH, ch0 = hf * CH;
+  const uint32_t tlane = sm.tmem + ((uint32_t)(row & ~31) << 16) + (uint32_t)ch0;
   const float* __restrict__ gw = p.weights; // FFMA blob: rechannel / head weights (uniform, L1-resident)
 
-  // ---- rechannel (Conv1x1 without bias, model.cpp:492), thread-local
-  float hres[C];
+  // ---- rechannel (Conv1x1 without bias, model.cpp:492), thread-local on this thread's output channels
+  float hres[CH];
 #pragma unroll
-  for (int o = 0; o < C; o++)
+  for (int o = 0; o < CH; o++)
     hres[o] = 0.0f;
+  if constexpr (CIN == 1)
+  {
 #pragma unroll
-  for (int i = 0; i < CIN; i++)
+    for (int o = 0; o < CH; o++)
+      hres[o] = __ldg(gw + A.rech_off + ch0 + o) * x;
+  }
+  else
+  {
 #pragma unroll
-    for (int o = 0; o < C; o++)
-      hres[o] = fmaf(__ldg(gw + A.rech_off + i * C + o), hin[i], hres[o]);
-  tc_store_column<C>(sm.tile_hi, sm.tile_lo, kTcTW, kHalo + tid, hres);
-  tc_halo_fill<C>(p.layers[A.layer0], sm, state, tabs0);
+    for (int pi = 0; pi < CIN / 4; pi++)
+    {
+      const float4 v = sm.xch[pi * kTcM + row];
+      const float in4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int o = 0; o < CH; o++)
+          hres[o] = fmaf(__ldg(gw + A.rech_off + (4 * pi + i) * C + ch0 + o), in4[i], hres[o]);
+    }
+  }
+  __syncthreads(); // xch / hx (aliases of ubuf) have been consumed by every thread; ubuf may be rewritten
+  tc_store_planes<PH>(sm.tile_hi, sm.tile_lo, kTcTW, pl0, kHalo + row, hres);
+  {
+    const LayerDesc& L0 = p.layers[A.layer0];
+    TcHaloItem it;
+    tc_halo_load<C>(it, L0, state, tabs0);
+    TcStage<PH> st;
+    tc_stage_load<C>(st, L0, state, tabs0, row, pl0);
+    tc_halo_store(it, sm);
+    if (tc_stage_store<C>(st, sm, row, pl0))
+    {
+      __syncthreads();
+      tc_stage_copy<C>(st, sm, row, pl0);
+    }
+  }
 
 #pragma unroll 1
   for (int li = 0; li < A.n_layers; li++)
   {
     const int gl = A.layer0 + li;
     const LayerDesc& Ld = p.layers[gl];
-    const int K = Ld.kernel, dil = Ld.dilation, lookback = Ld.lookback;
-    const uint32_t ring_mask = (uint32_t)Ld.ring_mask;
-    const int R = Ld.ring_mask + 1;
-    float4* __restrict__ ring = reinterpret_cast<float4*>(state + Ld.ring_off);
+    const bool has_next = li + 1 < A.n_layers;
+    const LayerDesc& Ln = p.layers[has_next ? gl + 1 : gl];
+    const int K = Ld.kernel, dil = Ld.dilation;
     const uint32_t wsel = par_z; // weight double buffer: toggles once per processed layer, like the Z barrier phase
     const float4* __restrict__ img = sm.wbuf + wsel * sm.wimg4;
-    const float* __restrict__ vec = reinterpret_cast<const float*>(img) + (2 * K * KS + 2 * KS) * kTcTile;
+    const float4* __restrict__ vec4 = img + ((2 * K * KS + 2 * KS) * kTcTile) / 4 + pl0; // b | M | p | slopes
 
-    // ---- stage the taps whose window [t0-off, t0-off+128) is not inside halo + tile (off > 64)
-    {
-      // a staged window that reaches into the current tile (64 < off < 128) reads columns other threads
-      // wrote in the previous epilogue: order those writes first (uniform condition)
-      bool reads_tile = false;
-      for (int k = 0; k < K - 1; k++)
-        reads_tile |= ((K - 1 - k) * dil > kHalo) && ((K - 1 - k) * dil < kTcM);
-      if (reads_tile)
-        __syncthreads();
-      int slot = 0;
-      for (int k = 0; k < K - 1; k++)
-      {
-        const int off = (K - 1 - k) * dil;
-        if (off <= kHalo)
-          continue;
-        float4* st_hi = sm.ubuf + slot * (2 * P * kTcM);
-        float4* st_lo = st_hi + P * kTcM;
-        const int rel = tid - off; // frame of this thread's staging column, relative to the tile start
-#pragma unroll
-        for (int pl = 0; pl < P; pl++)
-        {
-          float4 hi, lo;
-          if (rel >= 0)
-          {
-            hi = sm.tile_hi[pl * kTcTW + kHalo + rel];
-            lo = sm.tile_lo[pl * kTcTW + kHalo + rel];
-          }
-          else
-            tc_split4(ld_ring(ring + pl * R + ((tabs0 + (uint32_t)rel) & ring_mask)), hi, lo);
-          st_hi[pl * kTcM + tid] = hi;
-          st_lo[pl * kTcM + tid] = lo;
-        }
-        slot++;
-      }
-    }
     asm volatile("cp.async.wait_group 0;" ::: "memory"); // this layer's B image has landed
     tc_fence_async_smem();
     tc_fence_before();
@@ -270,63 +397,76 @@ __device__ __forceinline__ void tc_array_forward(const WaveNetKernelParams& p, c
     if (tid == 0)
     {
       tc_fence_after();
+      const uint32_t a_tile_hi = tc_desc_lo(sm.tile_hi, kTcTW * 16), a_tile_lo = tc_desc_lo(sm.tile_lo, kTcTW * 16);
+      uint32_t a_st = tc_desc_lo(sm.ubuf, kTcM * 16);
+      uint32_t b_hi = tc_desc_lo(img, 256);
+      const uint32_t b_lo_off = (uint32_t)(K * KS * kTcTile / 4);
       uint32_t acc = 0;
-      int slot = 0;
       for (int k = 0; k < K; k++)
       {
         const int off = (K - 1 - k) * dil;
-        const float4* a_hi;
-        const float4* a_lo;
-        uint32_t lbo;
+        uint32_t ah, al, step;
         if (off <= kHalo)
         {
-          a_hi = sm.tile_hi + kHalo - off;
-          a_lo = sm.tile_lo + kHalo - off;
-          lbo = kTcTW * 16;
+          ah = a_tile_hi + (uint32_t)(kHalo - off);
+          al = a_tile_lo + (uint32_t)(kHalo - off);
+          step = 2 * kTcTW;
         }
         else
         {
-          a_hi = sm.ubuf + slot * (2 * P * kTcM);
-          a_lo = a_hi + P * kTcM;
-          lbo = kTcM * 16;
-          slot++;
+          ah = a_st;
+          al = a_st + P * kTcM;
+          step = 2 * kTcM;
+          a_st += 2 * P * kTcM;
         }
-        const int plane_stride = (off <= kHalo) ? kTcTW : kTcM;
+#pragma unroll
         for (int s = 0; s < KS; s++)
         {
-          const float4* b_hi = img + ((k * KS + s) * kTcTile) / 4;
-          const float4* b_lo = b_hi + (K * KS * kTcTile) / 4;
-          tc_mma3(sm.tmem, tc_desc(a_hi + 2 * s * plane_stride, lbo, 128), tc_desc(a_lo + 2 * s * plane_stride, lbo, 128),
-                  tc_desc(b_hi, 256, 128), tc_desc(b_lo, 256, 128), acc);
+          tc_mma3(sm.tmem, ah + s * step, al + s * step, b_hi, b_hi + b_lo_off, acc);
           acc = 1;
+          b_hi += kTcTile / 4;
         }
       }
       tc_commit(sm.mbar_z);
     }
-    // ---- while the tensor core works: stream in the next layer's weights, persist the tail of h_l
+    // ---- while the tensor core works: stream in the next layer's weights, persist the tail of h_l, fetch the
+    //      next layer's halo
     tc_prefetch_weights(p, sm, (gl + 1 == total_layers) ? 0 : gl + 1, wsel ^ 1u);
-    if (tid < Tv && tid >= Tv - lookback)
+    if (row < Tv && row >= Tv - Ld.lookback)
     {
+      float4* __restrict__ ring = reinterpret_cast<float4*>(state + Ld.ring_off);
+      const int R = Ld.ring_mask + 1;
 #pragma unroll
-      for (int pl = 0; pl < P; pl++)
-        st_ring(ring + pl * R + ((tabs0 + (uint32_t)tid) & ring_mask),
-                make_float4(hres[4 * pl], hres[4 * pl + 1], hres[4 * pl + 2], hres[4 * pl + 3]));
+      for (int q = 0; q < PH; q++)
+        st_ring(ring + (pl0 + q) * R + ((tabs0 + (uint32_t)row) & (uint32_t)Ld.ring_mask),
+                make_float4(hres[4 * q], hres[4 * q + 1], hres[4 * q + 2], hres[4 * q + 3]));
     }
+    TcHaloItem halo_next;
+    halo_next.valid = false;
+    if (has_next)
+      tc_halo_load<C>(halo_next, Ln, state, tabs0);
     tc_mbar_wait(sm.mbar_z, par_z);
     par_z ^= 1u;
     tc_fence_after();
+    tc_halo_store(halo_next, sm); // the conv MMAs were the last readers of the old halo
 
     // ---- epilogue 1: z = Z + b + M c ; a = act(z) ; head += a ; a -> shared (hi / lo)
-    float a[C];
-    tc_ld<C>(sm.tmem + ((uint32_t)(tid & ~31) << 16), a);
+    float a[CH];
+    tc_ld<CH>(tlane, a);
 #pragma unroll
-    for (int o = 0; o < C; o++)
-      a[o] = a[o] + fmaf(vec[16 + o], cond, vec[o]);
-    apply_activation<C>(a, Ld, vec + 48);
+    for (int q = 0; q < PH; q++)
+    {
+      const float4 b4 = vec4[q], m4 = vec4[4 + q];
+      a[4 * q + 0] += fmaf(m4.x, x, b4.x);
+      a[4 * q + 1] += fmaf(m4.y, x, b4.y);
+      a[4 * q + 2] += fmaf(m4.z, x, b4.z);
+      a[4 * q + 3] += fmaf(m4.w, x, b4.w);
+    }
+    apply_activation<CH>(a, Ld, reinterpret_cast<const float*>(vec4 + 12));
 #pragma unroll
-    for (int o = 0; o < C; o++)
+    for (int o = 0; o < CH; o++)
       head[o] += a[o]; // model.cpp:530
-    tc_store_column<C>(sm.ubuf, sm.ubuf + P * kTcM, kTcM, tid, a);
+    tc_store_planes<PH>(sm.ubuf, sm.ubuf + P * kTcM, kTcM, pl0, row, a);
     tc_fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -335,54 +475,106 @@ __device__ __forceinline__ void tc_array_forward(const WaveNetKernelParams& p, c
     if (tid == 0)
     {
       tc_fence_after();
-      const float4* a_hi = sm.ubuf;
-      const float4* a_lo = sm.ubuf + P * kTcM;
+      const uint32_t a_hi = tc_desc_lo(sm.ubuf, kTcM * 16);
+      const uint32_t b_hi = tc_desc_lo(img + (2 * K * KS * kTcTile) / 4, 256);
+#pragma unroll
       for (int s = 0; s < KS; s++)
-      {
-        const float4* b_hi = img + ((2 * K * KS + s) * kTcTile) / 4;
-        const float4* b_lo = b_hi + (KS * kTcTile) / 4;
-        tc_mma3(sm.tmem + 16, tc_desc(a_hi + 2 * s * kTcM, kTcM * 16, 128), tc_desc(a_lo + 2 * s * kTcM, kTcM * 16, 128),
-                tc_desc(b_hi, 256, 128), tc_desc(b_lo, 256, 128), s > 0 ? 1u : 0u);
-      }
+        tc_mma3(sm.tmem + 16, a_hi + s * 2 * kTcM, a_hi + P * kTcM + s * 2 * kTcM, b_hi + s * (kTcTile / 4),
+                b_hi + (KS + s) * (kTcTile / 4), s > 0 ? 1u : 0u);
       tc_commit(sm.mbar_h);
     }
+    // ---- meanwhile: the next layer's far taps, ring part
+    TcStage<PH> stage_next;
+    if (has_next)
+      tc_stage_load<C>(stage_next, Ln, state, tabs0, row, pl0);
     tc_mbar_wait(sm.mbar_h, par_h);
     par_h ^= 1u;
     tc_fence_after();
 
     // ---- epilogue 2: h_{l+1} = h_l + p + D   (model.cpp:243,376), fp32 in registers
-    float d[C];
-    tc_ld<C>(sm.tmem + 16 + ((uint32_t)(tid & ~31) << 16), d);
+    float d[CH];
+    tc_ld<CH>(tlane + 16, d);
 #pragma unroll
-    for (int o = 0; o < C; o++)
-      hres[o] = hres[o] + (vec[32 + o] + d[o]);
-    if (li + 1 < A.n_layers)
+    for (int q = 0; q < PH; q++)
     {
-      tc_store_column<C>(sm.tile_hi, sm.tile_lo, kTcTW, kHalo + tid, hres);
-      tc_halo_fill<C>(p.layers[gl + 1], sm, state, tabs0);
+      const float4 p4 = vec4[8 + q];
+      hres[4 * q + 0] += p4.x + d[4 * q + 0];
+      hres[4 * q + 1] += p4.y + d[4 * q + 1];
+      hres[4 * q + 2] += p4.z + d[4 * q + 2];
+      hres[4 * q + 3] += p4.w + d[4 * q + 3];
+    }
+    if (has_next)
+    {
+      tc_store_planes<PH>(sm.tile_hi, sm.tile_lo, kTcTW, pl0, kHalo + row, hres);
+      if (tc_stage_store<C>(stage_next, sm, row, pl0))
+      {
+        __syncthreads(); // the rows copied from the tile were written by other threads just now
+        tc_stage_copy<C>(stage_next, sm, row, pl0);
+      }
     }
   }
-#pragma unroll
-  for (int o = 0; o < C; o++)
-    hout[o] = hres[o];
 
-  // ---- head rechannel (kernel size 1; model.cpp:548), thread-local
+  // ---- head rechannel (kernel size 1; model.cpp:548): partial sums over this thread's channels, the partner
+  //      thread of the row supplies the other half through shared memory
   const float* __restrict__ wh = gw + A.head_off;
-#pragma unroll
-  for (int ho = 0; ho < HOUT; ho++)
+  if constexpr (HOUT == 1)
   {
     float s = 0.0f;
 #pragma unroll
-    for (int i = 0; i < C; i++)
-      s = fmaf(__ldg(wh + i * HOUT + ho), head[i], s);
-    headout[ho] = s + __ldg(wh + C * HOUT + ho);
+    for (int i = 0; i < CH; i++)
+      s = fmaf(__ldg(wh + ch0 + i), head[i], s);
+    float* hx = reinterpret_cast<float*>(sm.hx);
+    if (hf == 1)
+      hx[row] = s;
+    __syncthreads();
+    headout[0] = (hf == 0) ? (s + hx[row]) + __ldg(wh + C) : 0.0f;
+  }
+  else
+  {
+    constexpr int HH = HOUT / 2, PHN = HOUT / 8;
+    float part[HOUT];
+#pragma unroll
+    for (int ho = 0; ho < HOUT; ho++)
+      part[ho] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < CH; i++)
+#pragma unroll
+      for (int ho = 0; ho < HOUT; ho++)
+        part[ho] = fmaf(__ldg(wh + (ch0 + i) * HOUT + ho), head[i], part[ho]);
+    // leave the partner's channels in hx, this array's residual rows in xch
+#pragma unroll
+    for (int q = 0; q < PHN; q++)
+    {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (hf == 0)
+        v = make_float4(part[HH + 4 * q], part[HH + 4 * q + 1], part[HH + 4 * q + 2], part[HH + 4 * q + 3]);
+      else
+        v = make_float4(part[4 * q], part[4 * q + 1], part[4 * q + 2], part[4 * q + 3]);
+      sm.hx[((1 - hf) * PHN + q) * kTcM + row] = v;
+    }
+#pragma unroll
+    for (int q = 0; q < PH; q++)
+      sm.xch[(pl0 + q) * kTcM + row] = make_float4(hres[4 * q], hres[4 * q + 1], hres[4 * q + 2], hres[4 * q + 3]);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < PHN; q++)
+    {
+      const float4 o4 = sm.hx[(hf * PHN + q) * kTcM + row];
+      const float oth[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+      {
+        const float own = (hf == 0) ? part[4 * q + i] : part[HH + 4 * q + i];
+        headout[4 * q + i] = (own + oth[i]) + __ldg(wh + C * HOUT + hf * HH + 4 * q + i);
+      }
+    }
   }
 }
 
-// One persistent CTA (128 threads, one 128-frame tile at a time) per stream slot.
+// One persistent CTA (256 threads, one 128-frame tile at a time) per stream slot.
 template <int C0, int C1>
-__global__ void __launch_bounds__(kTcM, 3) wavenet_tc_kernel(const __grid_constant__ WaveNetKernelParams p,
-                                                             const int wimg4, const int total_layers)
+__global__ void __launch_bounds__(kTcThreads, 3) wavenet_tc_kernel(const __grid_constant__ WaveNetKernelParams p,
+                                                                   const int wimg4, const int total_layers)
 {
   constexpr int CMAX = (C0 > C1) ? C0 : C1;
   constexpr int PM = CMAX / 4;
@@ -395,9 +587,12 @@ __global__ void __launch_bounds__(kTcM, 3) wavenet_tc_kernel(const __grid_consta
   sm.tile_hi = sm.wbuf + 2 * wimg4;
   sm.tile_lo = sm.tile_hi + PM * kTcTW;
   sm.ubuf = sm.tile_lo + PM * kTcTW; // 2 slots x (hi|lo) x PM planes x 128
+  sm.xch = sm.ubuf;
+  sm.hx = sm.ubuf + PM * kTcM;
   sm.mbar_z = &mbar[0];
   sm.mbar_h = &mbar[1];
   const int tid = threadIdx.x;
+  const int row = tid & (kTcM - 1);
 
   if (tid == 0)
   {
@@ -426,37 +621,32 @@ __global__ void __launch_bounds__(kTcM, 3) wavenet_tc_kernel(const __grid_consta
     {
       const int Tv = min(kTcM, p.n_frames - t0);
       const uint32_t tabs0 = p.t_base + (uint32_t)t0;
-      float x[1];
-      x[0] = (tid < Tv) ? __ldg(xin + t0 + tid) : 0.0f;
-      const float cond = x[0]; // no condition_dsp: condition == input (model.cpp:781)
+      // no condition_dsp: condition == input (model.cpp:781)
+      const float x = (row < Tv) ? __ldg(xin + t0 + row) : 0.0f;
       float y;
       if constexpr (C1 == 0)
       {
-        float head0[C0], hout0[C0], ho0[1];
+        float head0[C0 / 2], ho0[1];
 #pragma unroll
-        for (int o = 0; o < C0; o++)
+        for (int o = 0; o < C0 / 2; o++)
           head0[o] = 0.0f;
-        tc_array_forward<1, C0, 1>(p, p.arrays[0], sm, state, tabs0, Tv, total_layers, par_z, par_h, x, cond, head0,
-                                   hout0, ho0);
+        tc_array_forward<1, C0, 1>(p, p.arrays[0], sm, state, tabs0, Tv, total_layers, par_z, par_h, x, head0, ho0);
         y = ho0[0];
       }
       else
       {
-        float hout0[C0], ho0[C1];
+        float ho0[C1 / 2], ho1[1];
         {
-          float head0[C0];
+          float head0[C0 / 2];
 #pragma unroll
-          for (int o = 0; o < C0; o++)
+          for (int o = 0; o < C0 / 2; o++)
             head0[o] = 0.0f;
-          tc_array_forward<1, C0, C1>(p, p.arrays[0], sm, state, tabs0, Tv, total_layers, par_z, par_h, x, cond, head0,
-                                      hout0, ho0);
+          tc_array_forward<1, C0, C1>(p, p.arrays[0], sm, state, tabs0, Tv, total_layers, par_z, par_h, x, head0, ho0);
         }
-        float hout1[C1], ho1[1];
-        tc_array_forward<C0, C1, 1>(p, p.arrays[1], sm, state, tabs0, Tv, total_layers, par_z, par_h, hout0, cond, ho0,
-                                    hout1, ho1);
+        tc_array_forward<C0, C1, 1>(p, p.arrays[1], sm, state, tabs0, Tv, total_layers, par_z, par_h, x, ho0, ho1);
         y = ho1[0];
       }
-      if (tid < Tv)
+      if (tid < Tv) // tid < 128: the half-0 thread of the row holds the output
         yout[t0 + tid] = p.head_scale * y; // model.cpp:888-897
     }
   }
