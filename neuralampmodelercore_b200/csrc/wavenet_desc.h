@@ -43,7 +43,11 @@ struct ArrayDesc
 {
   int layer0, n_layers;
   int rech_off; // [CIN][C]
-  int head_off; // [C][HOUT] | bias[HOUT]
+  int head_off; // [HK][C][HOUT] | bias[HOUT]
+  // head rechannel = Conv1D over the head accumulator (model.cpp:397-400,548); kernel 1 in the classic models,
+  // 16 in the A2 family.  HK > 1 keeps the last (HK-1)*dilation head columns of a stream in their own ring.
+  int head_kernel, head_dilation;
+  int head_ring_off, head_ring_mask;
 };
 
 struct WaveNetKernelParams

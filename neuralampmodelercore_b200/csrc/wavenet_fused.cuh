@@ -376,8 +376,76 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
     }
   }
 
-  // ---- head rechannel (kernel size 1; model.cpp:548): headout = H head (+ g)
   const float* __restrict__ wh = sw + A.head_off;
+  if (A.head_kernel > 1)
+  {
+    // ---- head rechannel as a causal convolution over the head accumulator (A2 family: kernel 16;
+    //      model.cpp:397-400,548): the accumulator columns go through the tile so that every thread can
+    //      read its predecessors', the last (HK-1)*dilation columns of a stream live in the head ring
+    const int HK = A.head_kernel, hdil = A.head_dilation, HL = (HK - 1) * hdil;
+    const uint32_t hmask = (uint32_t)A.head_ring_mask;
+    const int HR = A.head_ring_mask + 1;
+    float4* __restrict__ hring = reinterpret_cast<float4*>(state + A.head_ring_off);
+    const float* __restrict__ w_hb = wh + HK * C * HOUT;
+#pragma unroll
+    for (int j = 0; j < S; j++)
+#pragma unroll
+      for (int pl = 0; pl < P; pl++)
+      {
+        float4 v;
+        unpack2(head[j][2 * pl], v.x, v.y);
+        unpack2(head[j][2 * pl + 1], v.z, v.w);
+        tile[pl * TW + kHalo + j * NT + tid] = v;
+      }
+    for (int idx = tid; idx < HL * P; idx += NT)
+    {
+      const int pl = idx / HL, col = idx - pl * HL;
+      tile[pl * TW + kHalo - HL + col] = ld_ring(hring + pl * HR + ((tabs0 - (uint32_t)HL + (uint32_t)col) & hmask));
+    }
+    __syncthreads(); // accumulator columns + halo visible; all ring reads done before the ring is rewritten
+#pragma unroll
+    for (int j = 0; j < S; j++)
+    {
+      const int trel = j * NT + tid;
+      if ((trel < Tv) && (trel >= Tv - HL))
+      {
+#pragma unroll
+        for (int pl = 0; pl < P; pl++)
+          st_ring(hring + pl * HR + ((tabs0 + (uint32_t)trel) & hmask), tile[pl * TW + kHalo + trel]);
+      }
+      float out[HOUT];
+#pragma unroll
+      for (int ho = 0; ho < HOUT; ho++)
+        out[ho] = w_hb[ho];
+      const float* __restrict__ w_row = wh; // walks [k][in][HOUT] linearly
+#pragma unroll 1
+      for (int k = 0; k < HK; k++)
+      {
+        const float4* sp = tile + kHalo + trel - (HK - 1 - k) * hdil;
+#pragma unroll
+        for (int pl = 0; pl < P; pl++)
+        {
+          const float4 xq = sp[pl * TW];
+          const float xs[4] = {xq.x, xq.y, xq.z, xq.w};
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+          {
+#pragma unroll
+            for (int ho = 0; ho < HOUT; ho++)
+              out[ho] = fmaf(w_row[ho], xs[i], out[ho]);
+            w_row += HOUT;
+          }
+        }
+      }
+#pragma unroll
+      for (int ho = 0; ho < HOUT; ho++)
+        headout[j][ho] = out[ho];
+    }
+    __syncthreads(); // the next array / tile rewrites the tile columns
+    return;
+  }
+
+  // ---- head rechannel (kernel size 1; model.cpp:548): headout = H head (+ g)
 #pragma unroll
   for (int j = 0; j < S; j++)
   {

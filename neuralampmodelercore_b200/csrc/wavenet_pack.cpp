@@ -79,6 +79,12 @@ void pack_tc(const ModelSpec& ms, WaveNetPlan& plan)
       plan.tc_why_not = "fewer than 5 channels";
       return;
     }
+  for (const ArraySpec& A : wn.arrays)
+    if (A.head_kernel != 1)
+    {
+      plan.tc_why_not = "head kernel size " + std::to_string(A.head_kernel);
+      return;
+    }
   size_t li = 0;
   for (size_t a = 0; a < wn.arrays.size(); a++)
   {
@@ -168,8 +174,9 @@ WaveNetPlan plan_wavenet(const ModelSpec& ms)
       return no(where + "layer1x1 inactive");
     if (A.h1x1_active)
       return no(where + "head1x1");
-    if (A.head_kernel != 1)
-      return no(where + "head kernel size " + std::to_string(A.head_kernel));
+    if ((A.head_kernel - 1) * A.head_dilation > kHalo)
+      return no(where + "head convolution looks back " + std::to_string((A.head_kernel - 1) * A.head_dilation)
+                + " frames (max " + std::to_string(kHalo) + ")");
     const int expect_in = (a == 0) ? 1 : wn.arrays[a - 1].channels;
     if (A.input_size != expect_in)
       return no(where + "input_size " + std::to_string(A.input_size) + " (expected " + std::to_string(expect_in) + ")");
@@ -276,16 +283,32 @@ WaveNetPlan plan_wavenet(const ModelSpec& ms)
       macs += (double)K * Cr * Cr + Cr + (double)Cr * Cr;
       plan.layers.push_back(ld);
     }
-    // head rechannel [C(in)][HOUT] + bias[HOUT], padded to a multiple of 4 floats
+    // head rechannel [HK][C(in)][HOUT] + bias[HOUT], padded to a multiple of 4 floats
+    const int HK = A.head_kernel;
+    ad.head_kernel = HK;
+    ad.head_dilation = A.head_dilation;
     ad.head_off = (int)blob.size();
-    blob.resize(blob.size() + align4((size_t)C * HOUT + HOUT), 0.0f);
-    for (int i = 0; i < Cr; i++)
-      for (int o = 0; o < HOUTr; o++)
-        blob[ad.head_off + (size_t)i * HOUT + o] = A.head_rechannel.w[(size_t)o * Cr + i]; // kernel 1: [0][o][i]
+    blob.resize(blob.size() + align4((size_t)HK * C * HOUT + HOUT), 0.0f);
+    for (int k = 0; k < HK; k++)
+      for (int i = 0; i < Cr; i++)
+        for (int o = 0; o < HOUTr; o++)
+          blob[ad.head_off + ((size_t)k * C + i) * HOUT + o] = A.head_rechannel.w[((size_t)k * HOUTr + o) * Cr + i];
     if (A.head_rechannel.bias)
       for (int o = 0; o < HOUTr; o++)
-        blob[ad.head_off + (size_t)C * HOUT + o] = A.head_rechannel.b[o];
-    macs += (double)Cr * HOUTr;
+        blob[ad.head_off + (size_t)HK * C * HOUT + o] = A.head_rechannel.b[o];
+    macs += (double)HK * Cr * HOUTr;
+    ad.head_ring_off = 0;
+    ad.head_ring_mask = 0;
+    if (HK > 1)
+    {
+      const int hl = (HK - 1) * A.head_dilation;
+      const int R = next_pow2(hl);
+      ad.head_ring_off = (int)ring_off;
+      ad.head_ring_mask = R - 1;
+      ring_off += (long)C * R;
+      if (hl > plan.max_lookback)
+        plan.max_lookback = hl;
+    }
     plan.arrays.push_back(ad);
   }
   blob.resize(align4(blob.size()), 0.0f);

@@ -70,7 +70,7 @@ def make_wavenet_nam(layers: list[dict], weights, head_scale: float = 1.0, versi
 
 
 def random_wavenet(channels=(16, 8), kernel_size=3, dilations=None, activation="Tanh", seed=0, scale=0.3,
-                   head_bias_last=True, kernel_sizes=None) -> dict:
+                   head_bias_last=True, kernel_sizes=None, head_kernel=None, head_dilation=None) -> dict:
     """Random-weight plain WaveNet in the a1 family (tools/create_wavenet.py-style), weights U(-scale, scale)
     like tools/test/test_a2_fast.cpp:109-117."""
     from oracle import nam_config
@@ -89,6 +89,10 @@ def random_wavenet(channels=(16, 8), kernel_size=3, dilations=None, activation="
             "gated": False,
             "head_bias": bool(last and head_bias_last),
         }
+        if head_kernel is not None:  # A2-style nested head config (model.cpp:961-1036)
+            lc["head"] = {"out_channels": lc.pop("head_size"), "kernel_size": int(head_kernel), "bias": lc.pop("head_bias")}
+            if head_dilation is not None:
+                lc["head"]["head_dilation"] = int(head_dilation)
         if kernel_sizes is not None:
             lc["kernel_sizes"] = list(kernel_sizes[a])
         else:

@@ -59,7 +59,12 @@ def test_kernel_selection_and_algorithmic_work():
     assert w["kernel"] == "fused" and w["flops_per_frame"] == 226 and w["kernel_variant"] == 404
     assert nb.inspect(fx.load_model("lstm"))["kernel"] == "lstm"
     assert nb.inspect(fx.load_model("lstm"))["flops_per_frame"] == 102
-    for name, why in (("wavenet_a2_max", "condition_dsp"), ("a2_full", "head kernel size")):
+    # A2 family (23 layers, kernel-16 head convolution): SURVEY.md section 8 table, 11,776 MACs for A2-Full
+    a2 = nb.inspect(fx.load_model("a2_full"))
+    assert a2["kernel"] == "fused" and a2["kernel_variant"] == 800 and a2["flops_per_frame"] == 23552
+    assert a2["prewarm_samples"] == 6347
+    assert nb.inspect(fx.load_model("a2_lite"))["kernel_variant"] == 400
+    for name, why in (("wavenet_a2_max", "condition_dsp"),):
         info = nb.inspect(fx.load_model(name))
         assert info["kernel"] == "unsupported" and why in info["reason"]
 
