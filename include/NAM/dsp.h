@@ -115,7 +115,7 @@ public:
   void Reset(const double sampleRate, const int maxBufferSize) override;
   nam_b200_model* Handle() { return mHandle; }
 
-private:
+protected:
   nam_b200_model* mHandle;
   int mPrewarmSamples;
 };

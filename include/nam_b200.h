@@ -14,6 +14,8 @@
  *   nam_b200_get_info           <->  NumInputChannels/NumOutputChannels/GetExpectedSampleRate/
  *                                    GetPrewarmSamples/Has*,Get* level & loudness          NAM/dsp.h:100-231
  *   nam_b200_set_fast_tanh      <->  nam::activations::Activation::enable/disable_fast_tanh NAM/activations.h:163-164
+ *   nam_b200_set_slimmable_size <->  nam::SlimmableModel::SetSlimmableSize (ContainerModel)     NAM/slimmable.h:17, NAM/container.cpp:99-122
+ *   nam_b200_slimmable_breakpoints <-> GetSlimmableSizeBreakpoints                              NAM/container.cpp:124-133
  *   nam_b200_last_error         <->  the what() of the exception the reference would throw
  *   nam_b200_destroy            <->  ~unique_ptr<nam::DSP>
  *
@@ -114,6 +116,15 @@ int nam_b200_process_f32_planar(nam_b200_model* m, const float* const* input, fl
 
 /* LSTM reads the fast-tanh switch at run time (NAM/lstm.cpp:48); WaveNet captured it at load. */
 int nam_b200_set_fast_tanh(nam_b200_model* m, int enabled);
+
+/* nam::SlimmableModel (NAM/slimmable.h:13-29) for "SlimmableContainer" files (NAM/container.cpp:88-133): pick the
+ * sub-model whose max_value is the first one above `value` (the last one if none is); a newly selected sub-model is
+ * reset + prewarmed with the settings of the container's last reset before it takes over.  Every other call on the
+ * handle (process, info, prewarm ...) is served by the active sub-model.  Returns 1 if another sub-model became
+ * active, 0 if the active one already matched; not slimmable -> NAM_B200_ERR_UNSUPPORTED. */
+int nam_b200_set_slimmable_size(nam_b200_model* m, double value);
+/* GetSlimmableSizeBreakpoints(): writes up to `capacity` thresholds, returns how many there are (0 = not slimmable). */
+int nam_b200_slimmable_breakpoints(const nam_b200_model* m, double* out, int capacity);
 
 /* Block until all work queued on the handle's stream has finished. */
 int nam_b200_synchronize(nam_b200_model* m);

@@ -346,6 +346,12 @@ struct nam_b200_model
   size_t h_pin_floats = 0;
   double flops_per_frame = 0.0;
 
+  // SlimmableContainer (NAM/container.cpp): the handle owns one complete sub-handle per sub-model and forwards
+  // every call to the active one; it holds no device memory itself
+  std::vector<std::unique_ptr<nam_b200_model>> subs;
+  int active_sub = -1;
+  double ext_sample_rate = -1.0;
+
   ~nam_b200_model()
   {
     cudaSetDevice(device);
@@ -752,6 +758,38 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
   m->spec = std::move(spec);
   m->fast_tanh_runtime = m->opts.fast_tanh;
 
+  if (m->spec.arch == Arch::Container)
+  {
+    // ContainerConfig::create (container.cpp:146-169): every sub-model goes through get_dsp() on its own
+    LoadOptions lo;
+    lo.fast_tanh = m->opts.fast_tanh != 0;
+    for (const auto& sub : m->spec.submodels)
+    {
+      nam_b200_model* h = nullptr;
+      int rc;
+      try
+      {
+        rc = create_common(model_spec_from_text(sub.model_json, lo), &m->opts, &h);
+      }
+      catch (const std::exception& ex)
+      {
+        return fail(NAM_B200_ERR_MODEL, ex.what());
+      }
+      if (rc != NAM_B200_OK)
+        return rc;
+      m->subs.emplace_back(h);
+      // container.cpp:35-46
+      const double sr = h->spec.sample_rate, want = m->spec.sample_rate;
+      if (sr != want && sr != -1.0 && want != -1.0)
+        return fail(NAM_B200_ERR_MODEL, "ContainerModel: submodel sample rate mismatch (expected " + std::to_string(want)
+                                          + ", got " + std::to_string(sr) + ")");
+    }
+    m->active_sub = (int)m->subs.size() - 1; // default to full size (container.cpp:49)
+    m->device = m->subs.back()->device;
+    *out = m.release();
+    return NAM_B200_OK;
+  }
+
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -893,6 +931,16 @@ int check_process_args(nam_b200_model* m, const void* in, const void* out, int b
   return NAM_B200_OK;
 }
 
+// SlimmableContainer handles forward to their active sub-model (ContainerModel::process etc., container.cpp:52-63)
+nam_b200_model* active_model(nam_b200_model* m)
+{
+  return (m && m->active_sub >= 0) ? m->subs[(size_t)m->active_sub].get() : m;
+}
+const nam_b200_model* active_model(const nam_b200_model* m)
+{
+  return (m && m->active_sub >= 0) ? m->subs[(size_t)m->active_sub].get() : m;
+}
+
 } // namespace
 
 // =================================================================================================
@@ -980,6 +1028,21 @@ static int inspect_spec(const ModelSpec& spec, char* out, int64_t capacity)
   double flops = 0.0;
   long state_floats = 0;
   int variant = 0;
+  if (spec.arch == Arch::Container)
+  {
+    // describe the default (largest) sub-model; the container itself only dispatches
+    LoadOptions lo;
+    const int rc = inspect_spec(model_spec_from_text(spec.submodels.back().model_json, lo), out, capacity);
+    if (rc != NAM_B200_OK)
+      return rc;
+    std::string text(out);
+    const std::string tag = "{\"architecture\": \"";
+    if (text.compare(0, tag.size(), tag) == 0)
+      text = "{\"container\": \"SlimmableContainer\", \"submodels\": " + std::to_string(spec.submodels.size())
+             + ", \"architecture\": \"" + text.substr(tag.size());
+    std::snprintf(out, (size_t)capacity, "%s", text.c_str());
+    return NAM_B200_OK;
+  }
   if (spec.in_channels != 1 || spec.out_channels != 1)
     reason = "CUDA path is mono in / mono out";
   else if (spec.arch == Arch::WaveNet)
@@ -1075,6 +1138,7 @@ int nam_b200_inspect_file(const char* nam_path, int fast_tanh, char* out, int64_
 
 int nam_b200_get_info(const nam_b200_model* m, nam_b200_info* info)
 {
+  m = active_model(m);
   if (!m || !info)
     return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null argument");
   nam_b200_info r;
@@ -1106,7 +1170,17 @@ int nam_b200_get_info(const nam_b200_model* m, nam_b200_info* info)
 
 int nam_b200_reset(nam_b200_model* m, double sample_rate, int max_frames)
 {
-  (void)sample_rate; // like the reference, the external rate is recorded but does not change the arithmetic
+  // like the reference, the external rate is recorded but does not change the arithmetic
+  if (m && m->active_sub >= 0)
+  {
+    // ContainerModel::Reset (container.cpp:73-86): remember the settings, reset only the active sub-model
+    if (max_frames < 1)
+      return fail(NAM_B200_ERR_INVALID_ARGUMENT, "max_frames must be >= 1");
+    m->ext_sample_rate = sample_rate;
+    m->max_frames = max_frames;
+    m->is_reset = true;
+    m = active_model(m);
+  }
   return guarded(m, [&]() -> int {
     if (max_frames < 1)
       return fail(NAM_B200_ERR_INVALID_ARGUMENT, "max_frames must be >= 1");
@@ -1127,6 +1201,7 @@ int nam_b200_reset(nam_b200_model* m, double sample_rate, int max_frames)
 
 int nam_b200_prewarm(nam_b200_model* m)
 {
+  m = active_model(m);
   return guarded(m, [&]() -> int {
     if (!m->is_reset)
       return fail(NAM_B200_ERR_STATE, "prewarm called before reset");
@@ -1138,6 +1213,7 @@ int nam_b200_prewarm(nam_b200_model* m)
 int nam_b200_process_f32_device(nam_b200_model* m, const float* in_device, float* out_device, int batch, int n_frames,
                                 int64_t in_stride, int64_t out_stride, void* cuda_stream)
 {
+  m = active_model(m);
   return guarded(m, [&]() -> int {
     const int rc = check_process_args(m, in_device, out_device, batch, n_frames);
     if (rc != NAM_B200_OK)
@@ -1156,6 +1232,7 @@ int nam_b200_process_f32_device(nam_b200_model* m, const float* in_device, float
 int nam_b200_process_f32(nam_b200_model* m, const float* in, float* out, int batch, int n_frames, int64_t in_stride,
                          int64_t out_stride)
 {
+  m = active_model(m);
   return guarded(m, [&]() -> int {
     const int rc = check_process_args(m, in, out, batch, n_frames);
     if (rc != NAM_B200_OK)
@@ -1187,6 +1264,7 @@ int nam_b200_process_f32_planar(nam_b200_model* m, const float* const* input, fl
 
 int nam_b200_process_f64_planar(nam_b200_model* m, const double* const* input, double* const* output, int n_frames)
 {
+  m = active_model(m);
   return guarded(m, [&]() -> int {
     if (!input || !output)
       return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null channel array");
@@ -1217,11 +1295,54 @@ int nam_b200_set_fast_tanh(nam_b200_model* m, int enabled)
   if (!m)
     return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null model handle");
   m->fast_tanh_runtime = enabled ? 1 : 0; // only the LSTM kernel reads it (lstm.cpp:48)
+  for (auto& sub : m->subs)
+    sub->fast_tanh_runtime = m->fast_tanh_runtime;
   return NAM_B200_OK;
+}
+
+int nam_b200_set_slimmable_size(nam_b200_model* m, double value)
+{
+  if (!m)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null model handle");
+  if (m->active_sub < 0)
+    return fail(NAM_B200_ERR_UNSUPPORTED, "model is not slimmable (not a SlimmableContainer)");
+  // ContainerModel::_get_index_for_slimmable_size / SetSlimmableSize (container.cpp:88-122)
+  int idx = (int)m->subs.size() - 1;
+  for (size_t i = 0; i < m->subs.size(); i++)
+    if (value < m->spec.submodels[i].max_value)
+    {
+      idx = (int)i;
+      break;
+    }
+  if (idx == m->active_sub)
+    return NAM_B200_OK;
+  if (m->is_reset)
+  {
+    // the newly selected sub-model is reset (and prewarmed) before it becomes the active one
+    const double sr = m->ext_sample_rate;
+    const int rc = nam_b200_reset(m->subs[(size_t)idx].get(), sr, m->max_frames);
+    if (rc != NAM_B200_OK)
+      return rc;
+  }
+  m->active_sub = idx;
+  return 1; // switched
+}
+
+int nam_b200_slimmable_breakpoints(const nam_b200_model* m, double* out, int capacity)
+{
+  if (!m)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null model handle");
+  if (m->active_sub < 0)
+    return 0;
+  const int n = (int)m->subs.size() - 1; // container.cpp:124-133
+  for (int i = 0; i < n && i < capacity && out; i++)
+    out[i] = m->spec.submodels[(size_t)i].max_value;
+  return n;
 }
 
 int nam_b200_synchronize(nam_b200_model* m)
 {
+  m = active_model(m);
   return guarded(m, [&]() -> int {
     CUDA_CHECK(cudaStreamSynchronize(m->stream));
     return NAM_B200_OK;
@@ -1230,11 +1351,17 @@ int nam_b200_synchronize(nam_b200_model* m)
 
 int64_t nam_b200_launch_count(const nam_b200_model* m)
 {
-  return m ? m->launches : -1;
+  if (!m)
+    return -1;
+  int64_t n = m->launches;
+  for (const auto& sub : m->subs)
+    n += sub->launches;
+  return n;
 }
 
 double nam_b200_last_kernel_ms(nam_b200_model* m)
 {
+  m = active_model(m);
   if (!m || !m->timing_valid)
     return -1.0;
   cudaSetDevice(m->device);

@@ -234,6 +234,36 @@ void nam::B200DSP::process(NAM_SAMPLE** input, NAM_SAMPLE** output, const int nu
     throw_last_error(rc); // the reference only asserts here; a CUDA failure must not pass silently
 }
 
+// ---- B200SlimmableDSP (ContainerModel::SetSlimmableSize, NAM/container.cpp:99-133) ----------------------
+void nam::B200SlimmableDSP::SetSlimmableSize(const double val)
+{
+  const int rc = nam_b200_set_slimmable_size(mHandle, val);
+  if (rc < 0)
+    throw_last_error(rc);
+  // the newly active sub-model was Reset; the prewarm that DSP::Reset implies is driven from here because shim
+  // handles are created with prewarm_on_reset = 0 (container.cpp:117-118, dsp.cpp:130-140)
+  if (rc == 1 && mPrewarmOnReset && mHaveExternalSampleRate)
+  {
+    const int rc2 = nam_b200_prewarm(mHandle);
+    if (rc2 != NAM_B200_OK)
+      throw_last_error(rc2);
+  }
+  nam_b200_info info;
+  std::memset(&info, 0, sizeof(info));
+  info.struct_size = sizeof(info);
+  if (nam_b200_get_info(mHandle, &info) == NAM_B200_OK)
+    mPrewarmSamples = info.prewarm_samples; // GetPrewarmSamples() follows the active sub-model
+}
+
+std::vector<double> nam::B200SlimmableDSP::GetSlimmableSizeBreakpoints() const
+{
+  const int n = nam_b200_slimmable_breakpoints(mHandle, nullptr, 0);
+  std::vector<double> out((size_t)(n > 0 ? n : 0));
+  if (n > 0)
+    nam_b200_slimmable_breakpoints(mHandle, out.data(), n);
+  return out;
+}
+
 // ---- get_dsp -----------------------------------------------------------------------------------------
 namespace
 {
@@ -248,8 +278,15 @@ std::unique_ptr<nam::DSP> wrap_handle(nam_b200_model* h)
     nam_b200_destroy(h);
     throw_last_error(rc);
   }
-  auto dsp = std::make_unique<nam::B200DSP>(h, info.in_channels, info.out_channels, info.expected_sample_rate,
-                                            info.prewarm_samples);
+  // a SlimmableContainer handle accepts a size (1.0 = the default, full-size sub-model: a no-op here)
+  const bool slimmable = nam_b200_set_slimmable_size(h, 1.0) >= 0;
+  std::unique_ptr<nam::B200DSP> dsp;
+  if (slimmable)
+    dsp = std::make_unique<nam::B200SlimmableDSP>(h, info.in_channels, info.out_channels, info.expected_sample_rate,
+                                                  info.prewarm_samples);
+  else
+    dsp = std::make_unique<nam::B200DSP>(h, info.in_channels, info.out_channels, info.expected_sample_rate,
+                                         info.prewarm_samples);
   // apply_metadata (reference NAM/get_dsp.cpp:205-213)
   if (info.has_loudness)
     dsp->SetLoudness(info.loudness);

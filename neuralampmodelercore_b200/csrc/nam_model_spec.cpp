@@ -635,6 +635,27 @@ ModelSpec build_spec(const json::Value& root, const LoadOptions& opts)
     ms.arch = Arch::Linear;
     build_linear(ms, config, weights);
   }
+  else if (ms.architecture == "SlimmableContainer")
+  {
+    // ContainerConfig::create + ContainerModel ctor (container.cpp:19-47,146-169): the container has no
+    // weights of its own, every entry of config.submodels is {max_value, model: <a whole .nam document>}
+    ms.arch = Arch::Container;
+    const json::Value& subs = config.get("submodels");
+    if (!subs.is_array() || subs.size() == 0)
+      throw std::runtime_error("SlimmableContainer: 'submodels' must be a non-empty array");
+    for (const auto& entry : subs.items("submodels"))
+    {
+      ModelSpec::Submodel sm;
+      sm.max_value = entry.at("max_value").as_double("max_value");
+      sm.model_json = entry.at("model").dump();
+      ms.submodels.push_back(std::move(sm));
+    }
+    for (size_t i = 1; i < ms.submodels.size(); i++)
+      if (ms.submodels[i].max_value <= ms.submodels[i - 1].max_value)
+        throw std::runtime_error("ContainerModel: submodels must be sorted by ascending max_value");
+    if (ms.submodels.back().max_value < 1.0)
+      throw std::runtime_error("ContainerModel: last submodel max_value must be >= 1.0");
+  }
   else
     throw std::runtime_error("No config parser registered for architecture: " + ms.architecture);
   if (ms.in_channels <= 0 || ms.out_channels <= 0)

@@ -33,7 +33,8 @@ enum class Arch
 {
   WaveNet = 1,
   LSTM = 2,
-  Linear = 3
+  Linear = 3,
+  Container = 4 // "SlimmableContainer": N complete sub-models, one active at a time (NAM/container.cpp)
 };
 
 // Order of nam::activations::ActivationType (NAM/activations.h:26-39)
@@ -193,6 +194,14 @@ struct ModelSpec
   WaveNetSpec wavenet;
   LstmSpec lstm;
   LinearSpec linear;
+  // Arch::Container: (max_value, the sub-model's complete .nam document re-serialised); ascending max_value,
+  // the last one >= 1.0 (ContainerModel ctor, container.cpp:19-47)
+  struct Submodel
+  {
+    double max_value = 0.0;
+    std::string model_json;
+  };
+  std::vector<Submodel> submodels;
 };
 
 enum class VersionSupport

@@ -186,6 +186,22 @@ class DSP:
         """LSTM reads the switch at run time (NAM/lstm.cpp:48)."""
         self._lib.nam_b200_set_fast_tanh(self._h, int(bool(enabled)))
 
+    # ---- nam::SlimmableModel (NAM/slimmable.h:13-29; ContainerModel, NAM/container.cpp:88-133) ---------
+    def SetSlimmableSize(self, val: float) -> None:
+        """0.0 = smallest, 1.0 = full size.  Only "SlimmableContainer" files are slimmable."""
+        rc = self._lib.nam_b200_set_slimmable_size(self._h, float(val))
+        if rc < 0:
+            _raise(rc, self._lib)
+        self._refresh_info()
+
+    def GetSlimmableSizeBreakpoints(self) -> list:
+        n = self._lib.nam_b200_slimmable_breakpoints(self._h, None, 0)
+        if n <= 0:
+            return []
+        buf = (_capi.C.c_double * n)()
+        self._lib.nam_b200_slimmable_breakpoints(self._h, buf, n)
+        return list(buf)
+
     # ---- nam::DSP::process ----------------------------------------------------------------------
     def process(self, input, output, num_frames: int) -> None:
         """DSP::process(NAM_SAMPLE** input, NAM_SAMPLE** output, num_frames) for stream 0.

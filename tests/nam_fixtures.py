@@ -105,3 +105,17 @@ def random_wavenet(channels=(16, 8), kernel_size=3, dilations=None, activation="
     w[-1] = 0.02  # head_scale is the last weight
     nam["weights"] = [float(v) for v in w]
     return nam
+
+
+def make_container(submodels, version: str = "0.7.0", sample_rate: float | None = 48000.0) -> dict:
+    """A "SlimmableContainer" document (NAM/container.cpp:146-169; example_models/A2.nam has this form):
+    `submodels` = [(max_value, nam_dict), ...]."""
+    nam = {
+        "version": version,
+        "architecture": "SlimmableContainer",
+        "config": {"submodels": [{"max_value": float(v), "model": m} for v, m in submodels]},
+        "weights": [],
+    }
+    if sample_rate is not None:
+        nam["sample_rate"] = sample_rate
+    return nam

@@ -87,3 +87,32 @@ def test_head_lookback_beyond_the_tile_halo_is_refused():
     nam = fx.random_wavenet(channels=(4,), dilations=[[1, 2]], head_kernel=16, head_dilation=5, seed=1)
     with pytest.raises(nb.UnsupportedModelError):
         nb.get_dsp(nam)
+
+
+def test_slimmable_container_dispatch():
+    """example_models/A2.nam is a SlimmableContainer of A2-Lite (max_value 0.5) and A2-Full (1.0): the full size is
+    active by default, SetSlimmableSize switches, the newly active sub-model starts from its own prewarmed state
+    (NAM/container.cpp:49,88-133)."""
+    lite, full = fx.load_model("a2_lite"), fx.load_model("a2_full")
+    nam = fx.make_container([(0.5, lite), (1.0, full)])
+    x = fx.synthetic_batch(3, 1500, seed=12)
+    d = nb.get_dsp(nam, batch=3)
+    assert d.GetSlimmableSizeBreakpoints() == [0.5]
+    d.Reset(48000.0, 500)
+    y_full = np.concatenate([d.process_batch(np.ascontiguousarray(x[:, p:p + 500])) for p in (0, 500)], axis=1)
+    assert np.max(np.abs(y_full - _oracle(full, x[:, :1000]))) <= TOL
+    d.SetSlimmableSize(0.2)
+    y_lite = np.concatenate([d.process_batch(np.ascontiguousarray(x[:, p:p + 500])) for p in (0, 500, 1000)], axis=1)
+    assert np.max(np.abs(y_lite - _oracle(lite, x))) <= TOL
+    d.SetSlimmableSize(0.5)  # 0.5 is not < 0.5: back to the full model, freshly reset
+    y2 = d.process_batch(np.ascontiguousarray(x[:, :500]))
+    assert np.max(np.abs(y2 - _oracle(full, x[:, :500]))) <= TOL
+    d.SetSlimmableSize(0.99)  # already active: no reset, the stream continues
+    y3 = d.process_batch(np.ascontiguousarray(x[:, 500:1000]))
+    assert np.max(np.abs(y3 - _oracle(full, x[:, :1000])[:, 500:])) <= TOL
+    d.close()
+    plain = nb.get_dsp(full)
+    with pytest.raises(nb.UnsupportedModelError):
+        plain.SetSlimmableSize(0.3)
+    assert plain.GetSlimmableSizeBreakpoints() == []
+    plain.close()

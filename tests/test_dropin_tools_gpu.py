@@ -91,3 +91,28 @@ def test_own_cxx_tool_over_the_c_abi(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["batch"] == 64 and out["msamples_per_s"] > 0 and np.isfinite(out["last_output"])
+
+
+def test_reference_tools_on_a_slimmable_container(tmp_path):
+    """tools/benchmodel.cpp --slim / tools/render.cpp --slim dynamic_cast the model to nam::SlimmableModel
+    (benchmodel.cpp:93-100): a SlimmableContainer file must load as one, a plain model must be refused."""
+    exe = _need("benchmodel")
+    cont = tmp_path / "a2.nam"
+    cont.write_text(json.dumps(fx.make_container([(0.5, fx.load_model("a2_lite")), (1.0, fx.load_model("a2_full"))])))
+    r = subprocess.run([str(exe), str(cont), "--slim", "0.25"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Setting slimmable size to 0.25" in r.stdout and "Finished" in r.stdout
+    r = subprocess.run([str(exe), str(_write_nam(tmp_path, "wavenet")), "--slim", "0.25"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode != 0 and "SlimmableModel" in (r.stdout + r.stderr)
+    # render through the container at the small size == the oracle of the small model
+    rexe = _need("render")
+    x = fx.input_wav()[44000:52000]
+    wav_in, wav_out = tmp_path / "in.wav", tmp_path / "out.wav"
+    _write_wav24(wav_in, x)
+    r = subprocess.run([str(rexe), str(cont), str(wav_in), str(wav_out), "--slim", "0.25"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = oracle.OracleModel.from_dict(fx.load_model("a2_lite"))
+    m.reset(48000.0, 64)
+    assert np.max(np.abs(_read_wav_f32(wav_out) - m.run(x, 64))) <= 1e-5

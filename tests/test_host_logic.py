@@ -144,3 +144,22 @@ def test_synthetic_signal_definition():
     b = fx.synthetic_batch(4, 256)
     assert np.array_equal(a, b) and a.dtype == np.float32
     assert not np.array_equal(a[0], a[1]) and np.abs(a).max() < 0.5
+
+
+def test_slimmable_container_parsing():
+    """SlimmableContainer documents (NAM/container.cpp:19-47,146-169): described through their default (largest)
+    sub-model; the ContainerModel constructor checks are reproduced with the reference's messages."""
+    lite, full = fx.load_model("a2_lite"), fx.load_model("a2_full")
+    info = nb.inspect(fx.make_container([(0.5, lite), (1.0, full)]))
+    assert info["container"] == "SlimmableContainer" and info["submodels"] == 2
+    assert info["architecture"] == "WaveNet" and info["kernel"] == "fused" and info["n_weights"] == 12146
+    with pytest.raises(RuntimeError, match="ascending max_value"):
+        nb.inspect(fx.make_container([(1.0, lite), (0.5, full)]))
+    with pytest.raises(RuntimeError, match="max_value must be >= 1.0"):
+        nb.inspect(fx.make_container([(0.5, lite), (0.9, full)]))
+    with pytest.raises(RuntimeError, match="non-empty array"):
+        nb.inspect(fx.make_container([]))
+    # a broken sub-model surfaces its own loader error
+    bad = dict(full, weights=full["weights"][:-3])
+    with pytest.raises(RuntimeError):
+        nb.inspect(fx.make_container([(1.0, bad)]))
