@@ -16,7 +16,7 @@ LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libnam_b200.so"
 INCLUDE = PKG.parent / "include"
 
-SOURCES = ["nam_b200.cu", "nam_model_spec.cpp", "json_lite.cpp", "wavenet_pack.cpp", "nam_dsp_shim.cpp"]
+SOURCES = ["nam_b200.cu", "nam_model_spec.cpp", "json_lite.cpp", "wavenet_pack.cpp", "generic_pack.cpp", "nam_dsp_shim.cpp"]
 
 NVCC_FLAGS = [
     "-gencode",

@@ -1,0 +1,91 @@
+// generic_desc.h -- plain-data description of a WaveNet with the reference's full option set, shared by
+// the host packer (generic_pack.cpp) and the general kernel (wavenet_generic.cuh).
+//
+// The fused kernels (wavenet_fused.cuh, wavenet_tc.cuh) cover the model families that matter for throughput
+// (SURVEY.md 8a, 8f-1).  Everything else the reference's WaveNet can express -- gated / blended activations,
+// bottleneck != channels, grouped convolutions, head1x1, the eight FiLM sites, a condition_dsp sub-model, the
+// post-stack head (NAM/wavenet/model.cpp:19-103,183-393,777-910; NAM/film.h; NAM/gating_activations.h) -- runs
+// through this description: every matrix dense (grouped ones are block diagonal with explicit zeros, which adds
+// exact zeros to the sums), one thread per stream, one frame at a time.
+#pragma once
+
+#include <stdint.h>
+
+namespace namb200
+{
+
+constexpr int kGenMaxVec = 64; // widest per-frame vector (channels, 2 x bottleneck, condition, head sizes)
+constexpr int kGenMaxArrays = 4;
+constexpr int kGenMaxHeadConvs = 8;
+constexpr int kGenFilmSites = 8;
+
+// y = W x (+ b): W (out x in) row-major at weights[w_off]; b at weights[b_off] or b_off < 0
+struct GMat
+{
+  int in, out, w_off, b_off;
+};
+
+// causal dilated convolution; weights [k][out][in], tap 0 = oldest.  The ring keeps the convolution's INPUT
+// vectors of the last ring_mask + 1 frames of a stream: element (slot, i) at state index ring_off + slot * in + i
+struct GConv
+{
+  int in, out, kernel, dilation, w_off, b_off, ring_off, ring_mask;
+};
+
+struct GAct
+{
+  int type; // ActType
+  float p0, p1, p2, p3; // LeakyReLU slope | LeakyHardtanh min_val, max_val, min_slope, max_slope
+  int slopes_off, n_slopes; // PReLU
+};
+
+struct GFilm
+{
+  int active, shift, dim;
+  GMat css; // condition -> (shift ? 2 : 1) * dim, with bias
+};
+
+struct GLayer
+{
+  int channels, bottleneck, zrows, gating, has_l1x1, has_h1x1;
+  GConv conv; // channels -> zrows
+  GMat mixin; // condition -> zrows
+  GMat l1x1; // bottleneck -> channels
+  GMat h1x1; // bottleneck -> head1x1 out
+  GAct act, sec;
+  GFilm film[kGenFilmSites]; // FilmSite order (nam_model_spec.h)
+};
+
+struct GArray
+{
+  int input_size, channels, head_out_size, head_size, layer0, n_layers;
+  GMat rechannel; // input_size -> channels, no bias
+  GConv head; // head_out_size -> head_size (LayerArray head rechannel)
+};
+
+struct GNet
+{
+  int in_channels, out_channels, n_arrays, with_head, n_head_convs;
+  float head_scale;
+  GAct head_act;
+  GArray arrays[kGenMaxArrays];
+  GConv head_convs[kGenMaxHeadConvs]; // post-stack head (model.cpp:19-103)
+};
+
+struct GenericKernelParams
+{
+  const float* weights;
+  const GLayer* layers;
+  GNet net;
+  GNet cond; // condition_dsp sub-model (valid when has_cond)
+  int has_cond;
+  float* state; // element idx of stream s at state[idx * state_streams + s]
+  long state_streams; // max_batch of the handle
+  const float* in;
+  float* out;
+  long in_stride, out_stride;
+  int batch, n_frames;
+  uint32_t t_base;
+};
+
+} // namespace namb200

@@ -1,0 +1,215 @@
+#include "generic_pack.h"
+
+#include <algorithm>
+
+namespace namb200
+{
+
+namespace
+{
+
+struct Packer
+{
+  GenericPlan& plan;
+  std::string err;
+
+  int put(const std::vector<float>& v)
+  {
+    const int off = (int)plan.weights.size();
+    plan.weights.insert(plan.weights.end(), v.begin(), v.end());
+    return off;
+  }
+  bool width(int n, const char* what)
+  {
+    if (n < 1 || n > kGenMaxVec)
+    {
+      if (err.empty())
+        err = std::string(what) + " " + std::to_string(n) + " (general kernel handles 1.." + std::to_string(kGenMaxVec) + ")";
+      return false;
+    }
+    return true;
+  }
+  GMat mat(const Conv1x1W& m)
+  {
+    GMat g{};
+    g.in = m.in;
+    g.out = m.out;
+    g.w_off = put(m.w);
+    g.b_off = m.bias ? put(m.b) : -1;
+    width(m.in, "matrix input width");
+    width(m.out, "matrix output width");
+    if ((long)m.w.size() != (long)m.in * m.out && err.empty())
+      err = "internal: 1x1 weight count";
+    plan.macs_per_frame += (double)m.in * m.out / std::max(m.groups, 1);
+    return g;
+  }
+  GConv conv(const Conv1DW& v)
+  {
+    GConv g{};
+    g.in = v.in;
+    g.out = v.out;
+    g.kernel = v.kernel;
+    g.dilation = v.dilation;
+    g.w_off = put(v.w);
+    g.b_off = v.bias ? put(v.b) : -1;
+    width(v.in, "convolution input width");
+    width(v.out, "convolution output width");
+    if ((long)v.w.size() != (long)v.kernel * v.in * v.out && err.empty())
+      err = "internal: conv weight count";
+    long r = 1;
+    while (r < v.lookback() + 1)
+      r <<= 1;
+    g.ring_mask = (int)(r - 1);
+    g.ring_off = (int)plan.state_floats;
+    plan.state_floats += r * v.in;
+    plan.macs_per_frame += (double)v.kernel * v.in * v.out / std::max(v.groups, 1);
+    return g;
+  }
+  GAct act(const ActSpec& a)
+  {
+    GAct g{};
+    g.type = (int)a.type;
+    g.slopes_off = 0;
+    g.n_slopes = 0;
+    if (a.type == ActType::LeakyReLU)
+      g.p0 = a.slope;
+    else if (a.type == ActType::LeakyHardtanh)
+    {
+      g.p0 = a.min_val;
+      g.p1 = a.max_val;
+      g.p2 = a.min_slope;
+      g.p3 = a.max_slope;
+    }
+    else if (a.type == ActType::PReLU)
+    {
+      g.slopes_off = put(a.slopes);
+      g.n_slopes = (int)a.slopes.size();
+      if (a.slopes.empty() && err.empty())
+        err = "PReLU without slopes";
+    }
+    return g;
+  }
+  GFilm film(const FilmSpec& f)
+  {
+    GFilm g{};
+    g.active = f.active ? 1 : 0;
+    if (!f.active)
+      return g;
+    g.shift = f.shift ? 1 : 0;
+    g.dim = f.dim;
+    width(f.dim, "FiLM width");
+    g.css = mat(f.css);
+    plan.macs_per_frame += f.dim;
+    return g;
+  }
+
+  bool net(const WaveNetSpec& wn, int out_channels, GNet& N)
+  {
+    N = GNet{};
+    N.in_channels = wn.in_channels;
+    N.out_channels = out_channels;
+    N.head_scale = wn.head_scale;
+    if (wn.arrays.empty() || (int)wn.arrays.size() > kGenMaxArrays)
+    {
+      err = std::to_string(wn.arrays.size()) + " layer arrays (general kernel handles 1.." + std::to_string(kGenMaxArrays) + ")";
+      return false;
+    }
+    N.n_arrays = (int)wn.arrays.size();
+    for (size_t a = 0; a < wn.arrays.size(); a++)
+    {
+      const ArraySpec& A = wn.arrays[a];
+      GArray& G = N.arrays[a];
+      G.input_size = A.input_size;
+      G.channels = A.channels;
+      G.head_out_size = A.head_out_size();
+      G.head_size = A.head_size;
+      G.layer0 = (int)plan.layers.size();
+      G.n_layers = (int)A.layers.size();
+      width(A.condition_size, "condition size");
+      width(A.head_size, "head size");
+      if (a > 0 && wn.arrays[a - 1].head_size != A.head_out_size() && err.empty())
+        err = "head size of array " + std::to_string(a - 1) + " does not feed array " + std::to_string(a);
+      G.rechannel = mat(A.rechannel);
+      for (const LayerSpec& L : A.layers)
+      {
+        GLayer g{};
+        g.channels = A.channels;
+        g.bottleneck = A.bottleneck;
+        g.gating = (int)L.gating;
+        g.zrows = L.conv.out;
+        g.has_l1x1 = L.has_l1x1 ? 1 : 0;
+        g.has_h1x1 = L.has_h1x1 ? 1 : 0;
+        g.conv = conv(L.conv);
+        g.mixin = mat(L.mixin);
+        if (L.has_l1x1)
+          g.l1x1 = mat(L.l1x1);
+        if (L.has_h1x1)
+          g.h1x1 = mat(L.h1x1);
+        g.act = act(L.act);
+        g.sec = act(L.sec_act);
+        for (int f = 0; f < kGenFilmSites; f++)
+          g.film[f] = film(L.film[f]);
+        plan.layers.push_back(g);
+      }
+      G.head = conv(A.head_rechannel);
+    }
+    N.with_head = wn.with_head ? 1 : 0;
+    if (wn.with_head)
+    {
+      if ((int)wn.post_head.convs.size() > kGenMaxHeadConvs)
+      {
+        err = "post-stack head with " + std::to_string(wn.post_head.convs.size()) + " convolutions";
+        return false;
+      }
+      N.n_head_convs = (int)wn.post_head.convs.size();
+      N.head_act = act(wn.post_head.act);
+      for (size_t i = 0; i < wn.post_head.convs.size(); i++)
+        N.head_convs[i] = conv(wn.post_head.convs[i]);
+    }
+    return err.empty();
+  }
+};
+
+} // namespace
+
+GenericPlan plan_generic(const ModelSpec& ms)
+{
+  GenericPlan plan;
+  auto no = [&plan](const std::string& why) {
+    plan.eligible = false;
+    plan.why_not = why;
+    return plan;
+  };
+  if (ms.arch != Arch::WaveNet)
+    return no("not a WaveNet");
+  const WaveNetSpec& wn = ms.wavenet;
+  if (wn.in_channels != 1 || ms.out_channels != 1)
+    return no("CUDA path is mono in / mono out (in_channels " + std::to_string(wn.in_channels) + ", out_channels "
+              + std::to_string(ms.out_channels) + ")");
+  Packer pk{plan, {}};
+  if (!pk.net(wn, ms.out_channels, plan.net))
+    return no(pk.err);
+  if (wn.condition_dsp)
+  {
+    const ModelSpec& cm = *wn.condition_dsp;
+    if (cm.arch != Arch::WaveNet)
+      return no("condition_dsp is not a WaveNet");
+    if (cm.wavenet.condition_dsp)
+      return no("nested condition_dsp");
+    if (cm.wavenet.in_channels != 1)
+      return no("condition_dsp with " + std::to_string(cm.wavenet.in_channels) + " input channels");
+    if (!pk.net(cm.wavenet, cm.out_channels, plan.cond))
+      return no("condition_dsp: " + pk.err);
+    if (!pk.width(cm.out_channels, "condition_dsp output width"))
+      return no(pk.err);
+    plan.has_cond = true;
+  }
+  if (!pk.err.empty())
+    return no(pk.err);
+  plan.weights.resize((plan.weights.size() + 3) & ~(size_t)3, 0.0f);
+  plan.state_floats = (plan.state_floats + 3) & ~3L;
+  plan.eligible = true;
+  return plan;
+}
+
+} // namespace namb200

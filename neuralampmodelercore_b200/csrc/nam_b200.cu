@@ -19,6 +19,8 @@
 #include "wavenet_fused.cuh"
 #include "wavenet_pack.h"
 #include "wavenet_tc.cuh"
+#include "generic_pack.h"
+#include "wavenet_generic.cuh"
 
 using namespace namb200;
 
@@ -330,6 +332,10 @@ struct nam_b200_model
   int wn_ctas_per_sm = 0; // resident CTAs per SM of the fused kernel (occupancy query, cached)
   int wn_geometry = 1; // 0 / 1: index into kWnGeom (FFMA kernel); 2: tensor-core kernel (wavenet_tc.cuh)
   float* d_tc_blob = nullptr; // per-layer B-operand images of the tensor-core kernel
+  // general WaveNet kernel (wavenet_generic.cuh): every option the fused kernels do not specialise
+  bool use_generic = false;
+  GenericPlan gplan;
+  GLayer* d_glayers = nullptr;
   // LSTM / Linear packed weights
   std::vector<float> host_weights;
   float* d_weights = nullptr;
@@ -359,6 +365,8 @@ struct nam_b200_model
       cudaFree(d_weights);
     if (d_tc_blob)
       cudaFree(d_tc_blob);
+    if (d_glayers)
+      cudaFree(d_glayers);
     if (d_state)
       cudaFree(d_state);
     if (d_state_tmp)
@@ -516,6 +524,28 @@ int occupancy_tc_dispatch(int c0, int c1, size_t smem)
 void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batch, int n_frames, long in_stride,
                     long out_stride, cudaStream_t st)
 {
+  if (m->use_generic)
+  {
+    GenericKernelParams gp{};
+    gp.weights = m->d_weights;
+    gp.layers = m->d_glayers;
+    gp.net = m->gplan.net;
+    gp.cond = m->gplan.cond;
+    gp.has_cond = m->gplan.has_cond ? 1 : 0;
+    gp.state = m->d_state;
+    gp.state_streams = m->opts.max_batch;
+    gp.in = d_in;
+    gp.out = d_out;
+    gp.in_stride = in_stride;
+    gp.out_stride = out_stride;
+    gp.batch = batch;
+    gp.n_frames = n_frames;
+    gp.t_base = m->t_base;
+    wavenet_generic_kernel<<<(batch + 63) / 64, 64, 0, st>>>(gp);
+    CUDA_CHECK(cudaGetLastError());
+    m->launches++;
+    return;
+  }
   const WaveNetPlan& plan = m->plan;
   WaveNetKernelParams kp{};
   kp.weights = m->d_weights;
@@ -712,6 +742,15 @@ void broadcast_state(nam_b200_model* m)
   const int batch = m->opts.max_batch;
   if (batch <= 1 || m->state_stride == 0)
     return;
+  if (m->use_generic)
+  {
+    const long total = m->state_stride * (long)batch;
+    const int blocks = (int)std::min<long>((total + 255) / 256, 4096);
+    generic_broadcast_state_kernel<<<blocks, 256, 0, m->stream>>>(m->d_state, m->state_stride, batch);
+    CUDA_CHECK(cudaGetLastError());
+    m->launches++;
+    return;
+  }
   dim3 grid((unsigned)std::min<long>((m->state_stride / 4 + 255) / 256, 1024), (unsigned)std::min(batch - 1, 64));
   if (grid.x < 1)
     grid.x = 1;
@@ -817,8 +856,24 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
       case Arch::WaveNet:
       {
         m->plan = plan_wavenet(m->spec);
-        if (!m->plan.eligible)
-          return fail(NAM_B200_ERR_UNSUPPORTED, "WaveNet option not implemented on the CUDA path yet: " + m->plan.why_not);
+        if (!m->plan.eligible || m->opts.kernel_geometry == 4)
+        {
+          // outside the fused families (or asked for explicitly): the general kernel
+          m->gplan = plan_generic(m->spec);
+          if (!m->gplan.eligible)
+            return fail(NAM_B200_ERR_UNSUPPORTED,
+                        "WaveNet not supported on the CUDA path: fused kernel: "
+                          + (m->plan.eligible ? std::string("(eligible)") : m->plan.why_not) + "; general kernel: " + m->gplan.why_not);
+          m->use_generic = true;
+          blob = m->gplan.weights;
+          m->state_stride = m->gplan.state_floats;
+          m->flops_per_frame = 2.0 * m->gplan.macs_per_frame;
+          m->variant = 9000;
+          CUDA_CHECK(cudaMalloc(&m->d_glayers, std::max<size_t>(m->gplan.layers.size(), 1) * sizeof(GLayer)));
+          CUDA_CHECK(cudaMemcpy(m->d_glayers, m->gplan.layers.data(), m->gplan.layers.size() * sizeof(GLayer),
+                                cudaMemcpyHostToDevice));
+          break;
+        }
         blob = m->plan.blob;
         m->state_stride = m->plan.state_floats;
         m->flops_per_frame = 2.0 * m->plan.macs_per_frame;
@@ -1056,7 +1111,19 @@ static int inspect_spec(const ModelSpec& spec, char* out, int64_t capacity)
       variant = plan.cp[0] * 100 + (plan.n_arrays > 1 ? plan.cp[1] : 0);
     }
     else
-      reason = plan.why_not;
+    {
+      const GenericPlan gp = plan_generic(spec);
+      if (gp.eligible)
+      {
+        kernel = "generic";
+        flops = 2.0 * gp.macs_per_frame;
+        state_floats = gp.state_floats;
+        variant = 9000;
+        reason = "fused kernel: " + plan.why_not;
+      }
+      else
+        reason = plan.why_not + "; general kernel: " + gp.why_not;
+    }
   }
   else if (spec.arch == Arch::LSTM)
   {

@@ -1,0 +1,269 @@
+// wavenet_generic.cuh -- the general WaveNet kernel: every option of the reference's WaveNet
+// (NAM/wavenet/model.cpp:183-393 Layer::Process, :463-549 LayerArray, :777-910 WaveNet::process with
+// condition_dsp and the post-stack head :19-103; NAM/film.h:76-190; NAM/gating_activations.h:100-113,209-227),
+// driven by the descriptors of generic_desc.h.
+//
+// One thread per stream, one frame at a time, all vectors in per-thread scratch: the models that need this
+// path are tiny (example_models/wavenet_a2_max.nam: 818 + 1,052 weights) and exist for their features, not
+// their throughput -- the throughput families have the fused kernels.  State (the input rings of every
+// convolution) is laid out frame-vector-major / stream-minor, so the 32 streams of a warp touch consecutive
+// addresses; weights are read through the read-only path at warp-uniform addresses.
+#pragma once
+
+#include "generic_desc.h"
+#include "wavenet_fused.cuh" // activations
+
+namespace namb200
+{
+
+struct GenThread
+{
+  const float* __restrict__ w;
+  float* __restrict__ st; // already offset to this thread's stream
+  long B; // stream stride
+  uint32_t t; // absolute frame index
+};
+
+__device__ __forceinline__ float g_act1(const GenThread& c, const GAct& A, float x, int ch)
+{
+  switch (A.type)
+  {
+    case KACT_TANH: return tanhf(x);
+    case KACT_FASTTANH: return act_fast_tanh(x);
+    case KACT_HARDTANH: return fminf(fmaxf(x, -1.0f), 1.0f);
+    case KACT_RELU: return x > 0.0f ? x : 0.0f;
+    case KACT_LEAKYRELU: return x > 0.0f ? x : A.p0 * x;
+    case KACT_PRELU: return x > 0.0f ? x : __ldg(c.w + A.slopes_off + (A.n_slopes == 1 ? 0 : ch)) * x;
+    case KACT_SIGMOID: return act_sigmoid(x);
+    case KACT_SILU: return x * act_sigmoid(x);
+    case KACT_HARDSWISH:
+    {
+      const float t = x + 3.0f;
+      const float cl = t < 0.0f ? 0.0f : (t > 6.0f ? 6.0f : t);
+      return x * cl * (1.0f / 6.0f);
+    }
+    case KACT_LEAKYHARDTANH: return x < A.p0 ? (x - A.p0) * A.p2 + A.p0 : (x > A.p1 ? (x - A.p1) * A.p3 + A.p1 : x);
+    case KACT_SOFTSIGN: return x * rcp_approx(1.0f + fabsf(x));
+    default: return x;
+  }
+}
+
+// y = W x (+ b)
+__device__ __forceinline__ void g_matvec(const GenThread& c, const GMat& M, const float* x, float* y)
+{
+  for (int o = 0; o < M.out; o++)
+  {
+    const float* __restrict__ wr = c.w + M.w_off + o * M.in;
+    float acc = 0.0f;
+    for (int i = 0; i < M.in; i++)
+      acc = fmaf(__ldg(wr + i), x[i], acc);
+    y[o] = (M.b_off >= 0) ? acc + __ldg(c.w + M.b_off + o) : acc;
+  }
+}
+
+// causal dilated convolution of the stream: persist x[t], read x[t - off] from the ring (zeros before the reset)
+__device__ __forceinline__ void g_conv(const GenThread& c, const GConv& V, const float* x, float* y)
+{
+  const int K = V.kernel;
+  if (K > 1)
+  {
+    const long base = V.ring_off + (long)(c.t & (uint32_t)V.ring_mask) * V.in;
+    for (int i = 0; i < V.in; i++)
+      c.st[(base + i) * c.B] = x[i];
+  }
+  for (int o = 0; o < V.out; o++)
+    y[o] = 0.0f;
+  float tap[kGenMaxVec];
+  for (int k = 0; k < K; k++)
+  {
+    const int off = (K - 1 - k) * V.dilation;
+    const float* src = x;
+    if (off != 0)
+    {
+      const long base = V.ring_off + (long)((c.t - (uint32_t)off) & (uint32_t)V.ring_mask) * V.in;
+      for (int i = 0; i < V.in; i++)
+        tap[i] = c.st[(base + i) * c.B];
+      src = tap;
+    }
+    const float* __restrict__ wk = c.w + V.w_off + (long)k * V.out * V.in;
+    for (int o = 0; o < V.out; o++)
+    {
+      float acc = y[o];
+      for (int i = 0; i < V.in; i++)
+        acc = fmaf(__ldg(wk + o * V.in + i), src[i], acc);
+      y[o] = acc;
+    }
+  }
+  if (V.b_off >= 0)
+    for (int o = 0; o < V.out; o++)
+      y[o] += __ldg(c.w + V.b_off + o);
+}
+
+// FiLM (film.h:76-190): out = in * scale(cond) (+ shift(cond)); in place is allowed (out == in)
+__device__ __forceinline__ void g_film(const GenThread& c, const GFilm& F, const float* in, const float* cond, float* out)
+{
+  float ss[2 * kGenMaxVec];
+  g_matvec(c, F.css, cond, ss);
+  if (F.shift)
+    for (int i = 0; i < F.dim; i++)
+      out[i] = in[i] * ss[i] + ss[F.dim + i];
+  else
+    for (int i = 0; i < F.dim; i++)
+      out[i] = in[i] * ss[i];
+}
+
+// Layer::Process for one frame (model.cpp:183-393): x (channels) -> x_next (channels), head contribution
+// (head_out_size) added to head_acc
+__device__ __forceinline__ void g_layer(const GenThread& c, const GLayer& L, float* x, const float* cond, float* head_acc)
+{
+  const int C = L.channels, Bn = L.bottleneck, Z = L.zrows;
+  float z[2 * kGenMaxVec], u[2 * kGenMaxVec];
+  // input convolution with optional pre / post FiLM (:189-204)
+  if (L.film[0].active)
+  {
+    g_film(c, L.film[0], x, cond, u);
+    g_conv(c, L.conv, u, z);
+  }
+  else
+    g_conv(c, L.conv, x, z);
+  if (L.film[1].active)
+    g_film(c, L.film[1], z, cond, z);
+  // input mixin (:206-219)
+  if (L.film[2].active)
+  {
+    float cf[kGenMaxVec];
+    g_film(c, L.film[2], cond, cond, cf);
+    g_matvec(c, L.mixin, cf, u);
+  }
+  else
+    g_matvec(c, L.mixin, cond, u);
+  if (L.film[3].active)
+    g_film(c, L.film[3], u, cond, u);
+  for (int i = 0; i < Z; i++)
+    z[i] += u[i]; // :220-221
+  if (L.film[4].active)
+    g_film(c, L.film[4], z, cond, z);
+
+  // activation (:234-288); the activated block is the first `bottleneck` entries of z
+  if (L.gating == 0)
+  {
+    for (int i = 0; i < Z; i++)
+      z[i] = g_act1(c, L.act, z[i], i);
+  }
+  else
+  {
+    for (int i = 0; i < Bn; i++)
+    {
+      const float a = g_act1(c, L.act, z[i], i);
+      const float g = g_act1(c, L.sec, z[Bn + i], i);
+      z[i] = (L.gating == 1) ? a * g : g * a + (1.0f - g) * z[i]; // gating_activations.h:100-113 | :209-227
+    }
+  }
+  if (L.film[5].active)
+    g_film(c, L.film[5], z, cond, z);
+  // head output (:290-352)
+  if (L.has_h1x1)
+  {
+    g_matvec(c, L.h1x1, z, u);
+    if (L.film[7].active)
+      g_film(c, L.film[7], u, cond, u);
+    for (int i = 0; i < L.h1x1.out; i++)
+      head_acc[i] += u[i];
+  }
+  else
+    for (int i = 0; i < Bn; i++)
+      head_acc[i] += z[i];
+  // layer1x1 + residual (:243,279-287,354-392); reference quirk: layer1x1_post_film is applied only in
+  // BLENDED mode
+  if (L.has_l1x1)
+  {
+    g_matvec(c, L.l1x1, z, u);
+    if (L.gating == 2 && L.film[6].active)
+      g_film(c, L.film[6], u, cond, u);
+    for (int i = 0; i < C; i++)
+      x[i] += u[i];
+  }
+}
+
+// one frame through a whole network: in (in_channels), cond (its condition vector) -> out (out_channels)
+__device__ __forceinline__ void g_net(const GenThread& c, const GNet& N, const GLayer* __restrict__ layers,
+                                      const float* in, const float* cond, float* out)
+{
+  float x[kGenMaxVec], xin[kGenMaxVec], head[kGenMaxVec], hout[kGenMaxVec];
+  for (int i = 0; i < N.in_channels; i++)
+    xin[i] = in[i];
+  for (int a = 0; a < N.n_arrays; a++)
+  {
+    const GArray& A = N.arrays[a];
+    // head accumulator: zeros for the first array, the previous array's head output after (model.cpp:469-486)
+    for (int i = 0; i < A.head_out_size; i++)
+      head[i] = (a == 0) ? 0.0f : hout[i];
+    g_matvec(c, A.rechannel, xin, x);
+    for (int l = 0; l < A.n_layers; l++)
+      g_layer(c, layers[A.layer0 + l], x, cond, head);
+    g_conv(c, A.head, head, hout);
+    for (int i = 0; i < A.channels; i++)
+      xin[i] = x[i];
+  }
+  const GArray& last = N.arrays[N.n_arrays - 1];
+  if (N.with_head)
+  {
+    // post-stack head (model.cpp:854-883, Head::process :87-103): repeated activation -> Conv1D
+    float cur[kGenMaxVec], nxt[kGenMaxVec];
+    for (int i = 0; i < last.head_size; i++)
+      cur[i] = N.head_scale * hout[i];
+    for (int h = 0; h < N.n_head_convs; h++)
+    {
+      const GConv& V = N.head_convs[h];
+      for (int i = 0; i < V.in; i++)
+        cur[i] = g_act1(c, N.head_act, cur[i], i);
+      g_conv(c, V, cur, nxt);
+      for (int i = 0; i < V.out; i++)
+        cur[i] = nxt[i];
+    }
+    for (int i = 0; i < N.out_channels; i++)
+      out[i] = cur[i];
+  }
+  else
+    for (int i = 0; i < N.out_channels; i++)
+      out[i] = N.head_scale * hout[i];
+}
+
+// mono in / mono out streams (the C ABI's batched entry); one thread per stream
+__global__ void __launch_bounds__(64) wavenet_generic_kernel(const __grid_constant__ GenericKernelParams p)
+{
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= p.batch)
+    return;
+  GenThread c;
+  c.w = p.weights;
+  c.st = p.state + s;
+  c.B = p.state_streams;
+  const float* __restrict__ xin = p.in + (size_t)s * p.in_stride;
+  float* __restrict__ yout = p.out + (size_t)s * p.out_stride;
+  for (int f = 0; f < p.n_frames; f++)
+  {
+    c.t = p.t_base + (uint32_t)f;
+    float in[1] = {xin[f]}, out[kGenMaxVec], cond[kGenMaxVec];
+    if (p.has_cond)
+      g_net(c, p.cond, p.layers, in, in, cond); // _process_condition (model.cpp:777-807)
+    else
+      cond[0] = in[0];
+    g_net(c, p.net, p.layers, in, cond, out);
+    yout[f] = out[0];
+  }
+}
+
+// after prewarming stream 0: copy its state to every other stream (stream-minor layout)
+__global__ void generic_broadcast_state_kernel(float* __restrict__ state, long n_idx, long streams)
+{
+  const long total = n_idx * streams;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x)
+  {
+    const long idx = e / streams, s = e - idx * streams;
+    if (s != 0)
+      state[e] = state[idx * streams];
+  }
+}
+
+} // namespace namb200

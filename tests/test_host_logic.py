@@ -64,9 +64,16 @@ def test_kernel_selection_and_algorithmic_work():
     assert a2["kernel"] == "fused" and a2["kernel_variant"] == 800 and a2["flops_per_frame"] == 23552
     assert a2["prewarm_samples"] == 6347
     assert nb.inspect(fx.load_model("a2_lite"))["kernel_variant"] == 400
-    for name, why in (("wavenet_a2_max", "condition_dsp"),):
+    # outside the fused families: the general kernel, with the reason the fused one declined
+    for name, why in (("wavenet_a2_max", "condition_dsp"), ("wavenet_condition_dsp", "condition_dsp")):
         info = nb.inspect(fx.load_model(name))
-        assert info["kernel"] == "unsupported" and why in info["reason"]
+        assert info["kernel"] == "generic" and info["kernel_variant"] == 9000 and why in info["reason"]
+    multi = fx.load_model("wavenet")
+    multi["config"]["in_channels"] = 2
+    multi["config"]["layers"][0]["input_size"] = 2
+    multi["weights"] = multi["weights"] + [0.0] * 3  # rechannel 2 -> 3 instead of 1 -> 3
+    info = nb.inspect(multi)
+    assert info["kernel"] == "unsupported" and "mono" in info["reason"]
 
 
 def test_loader_errors_match_reference_behaviour():
