@@ -144,6 +144,35 @@ def cpu_port_lib():
     return oracle.load_lib("fast"), "-O3 -march=x86-64-v3 -ffast-math"
 
 
+def host_threads() -> int:
+    """Threads this process may really use: cpu_count, the affinity mask and the cgroup CPU quota."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    try:
+        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(n, 1)
+
+
+def best_cpu_port(nam: dict, fast_tanh: bool, frames: int, streams_per_thread: int) -> tuple[float, float, int, int]:
+    """The CPU port at full, half and quarter thread counts (SMT siblings and shared caches often make fewer
+    threads faster on the 196 KB-per-stream working set); returns the best (Msamples/s, seconds, threads, streams)."""
+    t_all = host_threads()
+    best = (0.0, 0.0, t_all, 0)
+    for threads in sorted({t_all, max(t_all // 2, 1), max(t_all // 4, 1)}, reverse=True):
+        streams = streams_per_thread * threads
+        v, secs = time_cpu_port(nam, fast_tanh, frames, streams, threads)
+        if v > best[0]:
+            best = (v, secs, threads, streams)
+    return best
+
+
 def time_cpu_port(nam: dict, fast_tanh: bool, frames: int, streams: int, threads: int, reps: int = 1) -> tuple[float, float]:
     """Returns (Msamples/s, seconds per rep) of the CPU port on `threads` host threads."""
     from oracle import oracle
@@ -167,19 +196,26 @@ def time_cpu_port(nam: dict, fast_tanh: bool, frames: int, streams: int, threads
 
 # ---------------------------------------------------------------------------------------------------
 def run_reference(args) -> None:
-    """--impl reference: the reference's CPU algorithm for the path (oracle port; the reference's own
-    sources need Eigen, absent here) on all host threads, same config/metric/unit."""
+    """--impl reference: the reference's CPU algorithm for the path on the host cores, same config/metric/unit.
+
+    Two CPU implementations exist here: the C restatement (oracle/nam_oracle.c, "port") and the reference's own
+    sources compiled against a stand-in for their missing Eigen submodule (oracle/_ref, validated bit-close against
+    the port in tests/test_reference_build.py).  The stand-in evaluates every Eigen expression into a temporary, so
+    the reference build runs ~5x slower than the port; timing THAT as "the reference" would flatter the GPU.  The
+    line's value is therefore the faster one (the port, built -O3 -march=native -ffast-math like the reference's
+    -Ofast Release build); the reference build's own rate is reported beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     fx = fixtures()
     nam = fx.load_model(args.model)
-    cores = os.cpu_count() or 1
-    streams = 2 * cores  # bounded sample of the 4096-stream batch
     from oracle import oracle
 
     lib, flags = cpu_port_lib()
-    proto = oracle.OracleModel.from_dict(nam, fast_tanh=(args.tanh == "fast"), lib=lib)
+    fast = args.tanh == "fast"
+    # pick the thread count once (short probe), then time exactly K steps at it
+    _, _, cores, streams = best_cpu_port(nam, fast, 2048, 2)
+    proto = oracle.OracleModel.from_dict(nam, fast_tanh=fast, lib=lib)
     proto.reset(48000.0, CPU_BLOCK)
     pool = oracle.OracleBatch(proto, streams)
     x = fx.synthetic_batch(streams, args.frames, seed=99)
@@ -190,12 +226,32 @@ def run_reference(args) -> None:
     for _ in range(args.steps):
         pool.process(x, y, CPU_BLOCK, cores)
     dt = time.perf_counter() - t0
+    pool.close()
     value = streams * args.frames * args.steps / dt / 1e6
     sample = (f"{streams} of {args.batch} streams x {args.frames} frames per step in {CPU_BLOCK}-frame process() calls "
-              f"(tools/benchmodel.cpp protocol), one instance per stream, {cores} threads, gcc {flags}")
+              f"(tools/benchmodel.cpp protocol), one instance per stream, {cores} threads (best of full/half/quarter "
+              f"of the {host_threads()} usable), gcc {flags}")
+    ref_build = None
+    try:
+        from oracle import ref
+
+        if ref.available():
+            r = ref.ReferenceModel.from_dict(nam, fast_tanh=fast)
+            r.reset(48000.0, CPU_BLOCK)
+            xs = np.ascontiguousarray(x[0, :min(args.frames, 24000)])
+            r.run(xs[:1024], CPU_BLOCK)
+            t1 = time.perf_counter()
+            r.run(xs, CPU_BLOCK)
+            d1 = time.perf_counter() - t1
+            r.close()
+            ref_build = {"value_single_thread": len(xs) / d1 / 1e6, "unit": "Msamples/s",
+                         "what": "oracle/_ref/libnam_ref.so: unmodified reference sources, g++ -O2, Eigen stand-in "
+                                 "(oracle/eigen_shim) -- correct but slowed by eager temporaries; not the timed arm"}
+    except Exception as exc:  # the checker is optional on the box
+        ref_build = {"unavailable": str(exc)[:200]}
     line = {
         "impl": "reference",
-        "metric": METRIC,
+        "metric": metric_name(args),
         "value": value,
         "unit": "Msamples/s",
         "n_gpus": args.gpus,
@@ -211,10 +267,16 @@ def run_reference(args) -> None:
         "rtf_48k_aggregate": value * 1e6 / 48000.0,
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU restatement of the reference algorithm (oracle/nam_oracle.c); the reference's own sources "
-                "need the Eigen submodule, which is not vendored and not in this image",
+        "reference_build": ref_build,
+        "note": "CPU restatement of the reference algorithm (oracle/nam_oracle.c), pinned against the reference's own "
+                "sources compiled here (oracle/_ref, tests/test_reference_build.py)",
     }
     print(json.dumps(line), flush=True)
+
+
+def metric_name(args) -> str:
+    """BASELINE.json's metric; other models (secondary workloads) are named in it instead of a1_standard."""
+    return METRIC if args.model == MODEL else METRIC.replace("wavenet_a1_standard.nam", f"{args.model}.nam")
 
 
 def workload_config(args) -> dict:
@@ -367,16 +429,15 @@ def run_b200(args) -> None:
 
     cpu = None
     if not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        streams, cframes = 4 * cores, 24000
-        v, secs = time_cpu_port(nam, fast, cframes, streams, cores)
+        cframes = 12000
+        v, secs, cores, streams = best_cpu_port(nam, fast, cframes, 4)
         _, flags = cpu_port_lib()
         cpu = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port",
                "sample": f"{streams} streams x {cframes} frames ({secs:.1f} s wall on {cores} threads), "
                          f"oracle/nam_oracle.c gcc {flags}, same tanh regime"}
 
     line = {
-        "metric": METRIC,
+        "metric": metric_name(args),
         "value": value,
         "unit": "Msamples/s",
         "n_gpus": world,

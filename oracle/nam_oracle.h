@@ -5,10 +5,12 @@
  * product (neuralampmodelercore_b200/); only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs may use it, and only as the checker / CPU baseline.
  *
- * Parity status: "module-level pinned, whole-model unpinned" -- the reference cannot be
- * compiled in this image (Eigen submodule missing) and ships no
- * whole-model golden outputs; every numeric known-answer its own tests hold for this path
- * is reproduced in tests/test_oracle_pins.py.
+ * Parity status: PINNED.  (1) Module level: every numeric known-answer the reference's own tests
+ * hold for this path is reproduced in tests/test_oracle_pins.py.  (2) Whole-model level: the
+ * reference ships no golden outputs and its Eigen submodule is missing, but its UNMODIFIED
+ * sources compile here against oracle/eigen_shim (make ref -> oracle/_ref/libnam_ref.so), and
+ * tests/test_reference_build.py holds this restatement to that build on all example models, both
+ * tanh regimes, the A2 fast path and container semantics (max difference 0 .. 3e-6).
  *
  * The model is described by three flat arrays produced by oracle/nam_config.py from the
  * .nam JSON (schema documented there): int32 cfg[], float fparams[] (activation
