@@ -286,3 +286,39 @@ def test_error_behaviour():
     with pytest.raises(ValueError):
         d.process_batch(np.zeros((3, 8), np.float32))  # batch > max_batch
     assert d.launch_count() > 0
+
+
+def test_pipelined_host_call_equals_the_single_launch():
+    """Large host-buffer calls are pipelined in chunks of streams (copies of chunk c+1 / c-1 under the kernel of
+    chunk c, nam_b200_process_f32): every stream must come out bit-identical to the un-chunked device-pointer
+    entry, across calls (state carried per stream), and match the oracle on streams from different chunks."""
+    import torch
+
+    nam = fx.load_model("wavenet_a1_standard")
+    B, n = 2700, 1024  # 10.5 MiB per direction: three chunks of 1184 / 1184 / 332 streams on a 148-SM part
+    x = fx.synthetic_batch(B, 2 * n, seed=77)
+    a = nb.get_dsp(nam, batch=B, fast_tanh=True)
+    b = nb.get_dsp(nam, batch=B, fast_tanh=True)
+    a.Reset(48000.0, n)
+    b.Reset(48000.0, n)
+    dev_in = torch.empty((B, n), dtype=torch.float32, device="cuda")
+    dev_out = torch.empty_like(dev_in)
+    outs = []
+    for call in range(2):
+        xs = np.ascontiguousarray(x[:, call * n:(call + 1) * n])
+        ya = a.process_batch(xs)  # host path (pipelined)
+        dev_in.copy_(torch.from_numpy(xs))
+        torch.cuda.synchronize()
+        b.process_batch_device(dev_in.data_ptr(), dev_out.data_ptr(), B, n)
+        b.synchronize()
+        yb = dev_out.cpu().numpy()
+        assert np.array_equal(ya, yb), f"call {call}: pipelined host call differs from the single launch"
+        outs.append(ya)
+    y = np.concatenate(outs, axis=1)
+    pick = [0, 1183, 1184, 2367, 2368, 2699]  # first / last stream of every chunk
+    proto = oracle.OracleModel.from_dict(nam, fast_tanh=True)
+    proto.reset(48000.0, 64)
+    ref = proto.run_batch(np.ascontiguousarray(x[pick]), 64)
+    assert np.max(np.abs(y[pick] - ref)) <= TOL
+    a.close()
+    b.close()
