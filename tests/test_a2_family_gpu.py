@@ -83,10 +83,14 @@ def test_head_convolution_shapes(channels, hk, hd):
         assert err <= TOL, f"{channels} hk={hk} geometry {geom}: {err:.3e}"
 
 
-def test_head_lookback_beyond_the_tile_halo_is_refused():
+def test_head_lookback_beyond_the_tile_halo_goes_to_the_general_kernel():
+    """The fused kernel keeps at most 64 frames of head history in its tile halo; longer head look-backs are served
+    by the general kernel instead (same parity gate)."""
     nam = fx.random_wavenet(channels=(4,), dilations=[[1, 2]], head_kernel=16, head_dilation=5, seed=1)
-    with pytest.raises(nb.UnsupportedModelError):
-        nb.get_dsp(nam)
+    info = nb.inspect(nam)
+    assert info["kernel"] == "generic" and "looks back 75" in info["reason"]
+    x = fx.synthetic_batch(2, 900, seed=4)
+    assert np.max(np.abs(_gpu(nam, x, 300) - _oracle(nam, x))) <= TOL
 
 
 def test_slimmable_container_dispatch():

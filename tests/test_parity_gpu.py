@@ -275,8 +275,12 @@ def test_full_size_linearity_free_properties():
 def test_error_behaviour():
     with pytest.raises(nb.NamFileValidationError):
         nb.get_dsp("/nonexistent/model.nam")
-    with pytest.raises(nb.UnsupportedModelError):
-        nb.get_dsp(fx.load_model("wavenet_a2_max"))
+    multi = fx.load_model("wavenet")  # two input channels: valid .nam, no CUDA kernel serves it (mono only)
+    multi["config"]["in_channels"] = 2
+    multi["config"]["layers"][0]["input_size"] = 2
+    multi["weights"] = multi["weights"] + [0.0] * 3
+    with pytest.raises(nb.UnsupportedModelError, match="mono"):
+        nb.get_dsp(multi)
     d = nb.get_dsp(fx.load_model("wavenet"), batch=2)
     with pytest.raises(RuntimeError):
         d.process_batch(np.zeros((2, 8), np.float32))  # process before Reset
