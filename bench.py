@@ -420,10 +420,13 @@ def run_b200(args) -> None:
         "tensor": {"frac_of_bf16_peak": achieved_tf / peaks["bf16_tflops"], "of": peaks["_source"],
                    "note": "kernel uses the FP32 FMA pipe, not tensor cores (1e-5 parity forbids TF32/BF16 operands)"},
     }
+    # DRAM bytes of one launch from the committed ncu --set full capture of this command's default shape
     prof = ROOT / "profiles" / "r01_traffic.json"
-    if prof.exists():
+    if prof.exists() and args.model == MODEL and (B, n) == (4096, 4096) and args.geometry == 0 and fast:
         try:
-            roofline["traffic"] = json.loads(prof.read_text()).get("dram_bytes_per_launch_at_bench_shape")
+            t = json.loads(prof.read_text())
+            roofline["traffic"] = t.get("dram_bytes_per_launch_at_bench_shape")
+            roofline["traffic_source"] = t.get("source")
         except Exception:
             pass
 
