@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--geometry", type=int, default=0, help="0 default, 1 = FP32 kernel 128-thread CTAs, 2 = FP32 kernel 256-thread CTAs, 3 = tensor-core kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the quick batch-1/256, A2, LSTM, a2_max lines")
     ap.add_argument("--gather", action="store_true", help="also time an NCCL all_gather of one step's outputs")
     return ap.parse_args()
 
@@ -395,6 +396,42 @@ def run_b200(args) -> None:
             dist.destroy_process_group()
         return
 
+    # ---- the other configurations BASELINE.json names, device-resident, a few steps each (N = 1 only) ----
+    secondary = None
+    if world == 1 and not args.no_secondary and args.model == MODEL:
+        secondary = {}
+
+        def quick(name, model_name, b, frames, steps=8):
+            try:
+                m2 = nb.get_dsp(fx.load_model(model_name), batch=b, device=local_rank, fast_tanh=fast)
+                m2.Reset(48000.0, frames)
+                xi = torch.from_numpy(fx.synthetic_batch(b, frames, seed=7)).cuda()
+                yo = torch.empty_like(xi)
+                torch.cuda.synchronize()
+                for _ in range(3):
+                    m2.process_batch_device(xi.data_ptr(), yo.data_ptr(), b, frames, frames, frames, stream.cuda_stream)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(steps):
+                    m2.process_batch_device(xi.data_ptr(), yo.data_ptr(), b, frames, frames, frames, stream.cuda_stream)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                v = b * frames / (ms * 1e-3) / 1e6
+                secondary[name] = {"Msamples_per_s": v, "ms_per_step": ms, "streams": b, "frames_per_step": frames,
+                                   "rtf_48k_per_stream": v * 1e6 / 48000.0 / b,
+                                   "tflops": m2.flops_per_frame * v * 1e6 / 1e12}
+                m2.close()
+            except Exception as exc:  # a secondary workload must never cost the headline line
+                secondary[name] = {"error": str(exc)[:200]}
+
+        quick("wavenet_a1_standard_batch1", MODEL, 1, 4096)
+        quick("wavenet_a1_standard_batch256", MODEL, 256, 4096)
+        quick("wavenet_a1_standard_batch4096_64frame_calls", MODEL, 4096, 64, steps=32)
+        quick("a2_full_batch4096", "a2_full", 4096, 4096, steps=4)
+        quick("lstm_batch4096", "lstm", 4096, 4096, steps=4)
+        quick("wavenet_a2_max_batch4096_general_kernel", "wavenet_a2_max", 4096, 1024, steps=2)
+
     # ---- roofline of the fused kernel (one launch per step) ----
     peaks = load_peaks()
     kernel_ms = statistics.mean(step_ms)  # one kernel per step on this stream: event-to-event == launch duration
@@ -431,7 +468,7 @@ def run_b200(args) -> None:
             pass
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1 and rank == 0:  # reported at N = 1 only
         cframes = 12000
         v, secs, cores, streams = best_cpu_port(nam, fast, cframes, 4)
         _, flags = cpu_port_lib()
@@ -460,6 +497,7 @@ def run_b200(args) -> None:
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "secondary": secondary,
     }
     if gather is not None:
         line["nccl_gather"] = gather
