@@ -469,7 +469,7 @@ def run_b200(args) -> None:
 
     cpu = None
     if not args.no_cpu_baseline and world == 1 and rank == 0:  # reported at N = 1 only
-        cframes = 12000
+        cframes = 96000  # benchmodel's 2 s of audio per stream; ~1 s wall per thread count tried
         v, secs, cores, streams = best_cpu_port(nam, fast, cframes, 4)
         _, flags = cpu_port_lib()
         cpu = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port",

@@ -330,6 +330,7 @@ struct nam_b200_model
   WaveNetPlan plan;
   int variant = 0;
   int wn_ctas_per_sm = 0; // resident CTAs per SM of the fused kernel (occupancy query, cached)
+  int wn_ctas_short = 0; // same for the short-call (multi-stream tile) geometry
   int wn_geometry = 1; // 0 / 1: index into kWnGeom (FFMA kernel); 2: tensor-core kernel (wavenet_tc.cuh)
   float* d_tc_blob = nullptr; // per-layer B-operand images of the tensor-core kernel
   // general WaveNet kernel (wavenet_generic.cuh): every option the fused kernels do not specialise
@@ -406,16 +407,22 @@ namespace
 //               weights (one copy per CTA) cost half the shared memory per warp
 constexpr int kWnS = 2; // time steps per thread
 
+//   geometry 2: 128 threads, the 256-frame tile split into 4 streams x 64 frames (short calls: the reference
+//               tools' 64-frame blocks are latency-bound per stream, so 4 streams share a CTA's layer walk)
 struct WnGeometry
 {
-  int nt, min_ctas;
+  int nt, min_ctas, lq; // lq: log2(frames per sub-tile)
+  int frames_per_subtile() const { return 1 << lq; }
+  int streams_per_tile() const { return (kWnS * nt) >> lq; }
 };
-constexpr WnGeometry kWnGeom[2] = {{128, 3}, {256, 2}};
+constexpr WnGeometry kWnGeom[3] = {{128, 3, 8}, {256, 2, 9}, {128, 3, 6}};
+constexpr int kWnShortGeom = 2;
+constexpr int kWnShortMaxFrames = 96; // calls up to this many frames take the multi-stream geometry
 
-template <int C0, int C1, int NT, int MINB>
+template <int C0, int C1, int NT, int MINB, int LQ>
 void launch_wavenet_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem, cudaStream_t st)
 {
-  auto kern = wavenet_fused_kernel<C0, C1, kWnS, NT, MINB>;
+  auto kern = wavenet_fused_kernel<C0, C1, kWnS, NT, MINB, LQ>;
   static bool configured[64] = {false};
   if (!configured[m->device & 63])
   {
@@ -426,10 +433,10 @@ void launch_wavenet_variant(nam_b200_model* m, const WaveNetKernelParams& kp, in
   CUDA_CHECK(cudaGetLastError());
 }
 
-template <int C0, int C1, int NT, int MINB>
+template <int C0, int C1, int NT, int MINB, int LQ>
 int occupancy_wavenet_variant(size_t smem)
 {
-  auto kern = wavenet_fused_kernel<C0, C1, kWnS, NT, MINB>;
+  auto kern = wavenet_fused_kernel<C0, C1, kWnS, NT, MINB, LQ>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   int n = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, NT, smem) != cudaSuccess)
@@ -439,7 +446,8 @@ int occupancy_wavenet_variant(size_t smem)
 
 #define WN_CASE(C0, C1, FN, ...)                                                                                     \
   case (C0) * 100 + (C1):                                                                                            \
-    return geom == 0 ? FN<C0, C1, 128, 3>(__VA_ARGS__) : FN<C0, C1, 256, 2>(__VA_ARGS__);
+    return geom == 0 ? FN<C0, C1, 128, 3, 8>(__VA_ARGS__)                                                            \
+                     : (geom == 1 ? FN<C0, C1, 256, 2, 9>(__VA_ARGS__) : FN<C0, C1, 128, 3, 6>(__VA_ARGS__));
 
 #define WN_DISPATCH(FN, ...)                                                                                         \
   switch (c0 * 100 + c1)                                                                                             \
@@ -473,7 +481,8 @@ int occupancy_wavenet_dispatch(int c0, int c1, int geom, size_t smem)
 size_t wavenet_smem_bytes(const WaveNetPlan& plan, int geom)
 {
   const int cmax = std::max(plan.cp[0], plan.cp[1]);
-  const size_t tile4 = (size_t)(cmax / 4) * (kHalo + kWnS * kWnGeom[geom].nt);
+  const WnGeometry& g = kWnGeom[geom];
+  const size_t tile4 = (size_t)(cmax / 4) * g.streams_per_tile() * (kHalo + g.frames_per_subtile());
   return (plan.blob.size() + 3) / 4 * 16 + tile4 * 16;
 }
 
@@ -594,6 +603,19 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
     if (grid_tc < 1)
       grid_tc = 1;
     launch_tc_dispatch(c0, c1, m, kp, grid_tc, smem_tc, st);
+    m->launches++;
+    return;
+  }
+  // short calls on more than a handful of streams: several streams per tile (same rings, same arithmetic)
+  if (n_frames <= kWnShortMaxFrames && batch >= 2 * kWnGeom[kWnShortGeom].streams_per_tile()
+      && wavenet_smem_bytes(plan, kWnShortGeom) <= 227 * 1024 && m->opts.kernel_geometry == 0)
+  {
+    const size_t smem_s = wavenet_smem_bytes(plan, kWnShortGeom);
+    if (m->wn_ctas_short <= 0)
+      m->wn_ctas_short = occupancy_wavenet_dispatch(c0, c1, kWnShortGeom, smem_s);
+    const int q = kWnGeom[kWnShortGeom].streams_per_tile();
+    int grid_s = std::min((batch + q - 1) / q, m->wn_ctas_short * m->sm_count);
+    launch_wavenet_dispatch(c0, c1, kWnShortGeom, m, kp, std::max(grid_s, 1), smem_s, st);
     m->launches++;
     return;
   }

@@ -195,17 +195,43 @@ __device__ __forceinline__ void axpy_row(u64 (&acc)[C / 2], const float* __restr
 //   CIN  : channels of the array input (1 for the first array: the raw sample)
 //   C    : channels == bottleneck (padded to a multiple of 4)
 //   HOUT : rows of the head output (next array's C, or 1 for the last array)
-template <int CIN, int C, int HOUT, int S, int NT>
+//   LQ   : log2 of the frames per sub-tile.  (1 << LQ) == S * NT: the CTA's tile is one stream (long calls).
+//          Smaller: the tile holds Q = S*NT >> LQ streams side by side, each with its own 64-column halo --
+//          short calls (the reference tools' 64-frame blocks) are latency-bound per stream (20 layers x 2
+//          barriers x ring loads), so several streams walk the layer chain together and share the weights.
+//   state[j], Tv[j]: ring base and number of valid frames of the stream that owns this thread's j-th frame
+//          (Tv[j] == 0 for a slot beyond the batch); state0 / stream0 / n_streams locate the other sub-tiles' rings
+//          for the halo fill.
+template <int CIN, int C, int HOUT, int S, int NT, int LQ>
 __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, const ArrayDesc& A,
                                               const float* __restrict__ sw, float4* __restrict__ tile,
-                                              float* __restrict__ state, const uint32_t tabs0, const int Tv,
-                                              const float (&hin)[S][CIN], const float (&cond)[S],
+                                              float* const (&state)[S], const int stream0, const uint32_t tabs0,
+                                              const int (&Tv)[S], const float (&hin)[S][CIN], const float (&cond)[S],
                                               u64 (&head)[S][C / 2], float (&hout)[S][C], float (&headout)[S][HOUT])
 {
   constexpr int T = S * NT;
-  constexpr int TW = kHalo + T; // columns per plane in the shared tile
+  constexpr int FQ = 1 << LQ; // frames per sub-tile
+  constexpr int Q = T / FQ; // streams per tile
+  constexpr int SW = kHalo + FQ; // columns of one sub-tile (halo + frames)
+  constexpr int TW = Q * SW; // columns per plane in the shared tile
   constexpr int P = C / 4; // planes
+  static_assert(Q >= 1 && Q * FQ == T && (Q == 1 || FQ <= NT), "sub-tile geometry");
   const int tid = threadIdx.x;
+  // this thread's j-th frame: sub-tile, frame inside it, tile column
+  int fj[S], colj[S];
+#pragma unroll
+  for (int j = 0; j < S; j++)
+  {
+    const int trel = j * NT + tid;
+    fj[j] = trel & (FQ - 1);
+    colj[j] = (trel >> LQ) * SW + kHalo + fj[j];
+  }
+  constexpr int kColStep = (Q == 1) ? NT : (NT >> LQ) * SW; // colj[j] - colj[j-1]
+  const int f_warp = (tid & (FQ - 1)) & ~31; // first frame of this warp inside its sub-tile (same for every j)
+  auto sub_state = [&](int q) -> float* {
+    const int s = min(stream0 + q, p.batch - 1);
+    return p.state + (size_t)s * p.state_stride;
+  };
 
   // ---- rechannel (Conv1x1, no bias; model.cpp:492) -> this thread's columns of the tile
 #pragma unroll
@@ -224,7 +250,7 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
       float4 v;
       unpack2(h[2 * pl], v.x, v.y);
       unpack2(h[2 * pl + 1], v.z, v.w);
-      tile[pl * TW + kHalo + j * NT + tid] = v;
+      tile[pl * TW + colj[j]] = v;
     }
   }
 
@@ -242,14 +268,32 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
     const float* __restrict__ w_p = w_mix + C;
     const float* __restrict__ w_pb = w_p + C * C;
     const float* __restrict__ w_slopes = w_pb + C;
-    float4* __restrict__ ring = reinterpret_cast<float4*>(state + Ld.ring_off);
+    float4* ring[S];
+#pragma unroll
+    for (int j = 0; j < S; j++)
+      ring[j] = reinterpret_cast<float4*>(state[Q == 1 ? 0 : j] + Ld.ring_off);
     const int halo = (lookback <= kHalo) ? lookback : 0; // (a 64-column halo for the longer look-backs costs more than it saves: measured)
 
     // ---- phase 0: small-dilation layers pull their history [t0-L, t0) into the halo
-    for (int idx = tid; idx < halo * P; idx += NT)
+    if constexpr (Q == 1)
     {
-      const int pl = idx / halo, col = idx - pl * halo;
-      tile[pl * TW + kHalo - halo + col] = ld_ring(ring + pl * R + ((tabs0 - (uint32_t)halo + (uint32_t)col) & ring_mask));
+      for (int idx = tid; idx < halo * P; idx += NT)
+      {
+        const int pl = idx / halo, col = idx - pl * halo;
+        tile[pl * TW + kHalo - halo + col] =
+          ld_ring(ring[0] + pl * R + ((tabs0 - (uint32_t)halo + (uint32_t)col) & ring_mask));
+      }
+    }
+    else
+    {
+      for (int idx = tid; idx < Q * P * halo; idx += NT)
+      {
+        const int col = idx % halo, t2 = idx / halo;
+        const int pl = t2 % P, q = t2 / P;
+        const float4* __restrict__ rq = reinterpret_cast<const float4*>(sub_state(q) + Ld.ring_off);
+        tile[pl * TW + q * SW + kHalo - halo + col] =
+          ld_ring(rq + pl * R + ((tabs0 - (uint32_t)halo + (uint32_t)col) & ring_mask));
+      }
     }
     __syncthreads(); // B0: tile columns (previous layer's phase 2) + halo are visible
 
@@ -275,16 +319,16 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
       // Warp-uniform fast path: every lane of this warp finds both of its frames in the shared tile (halo
       // included).  True for all warps of the small-dilation layers and for the later warps of a tile otherwise;
       // the loop below then carries no ring addressing at all (it was ~20 of 110 issued instructions per plane).
-      if (((tid & ~31) - off) >= -halo)
+      if ((f_warp - off) >= -halo)
       {
-        const float4* __restrict__ sp0 = tile + kHalo + tid - off;
+        const float4* __restrict__ sp0 = tile + colj[0] - off;
 #pragma unroll kPlUnroll
         for (int pl = 0; pl < P; pl++)
         {
           float4 xq[S];
 #pragma unroll
           for (int j = 0; j < S; j++)
-            xq[j] = sp0[pl * TW + j * NT];
+            xq[j] = sp0[pl * TW + j * kColStep];
 #pragma unroll
           for (int i = 0; i < 4; i++)
           {
@@ -306,9 +350,9 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
 #pragma unroll
       for (int j = 0; j < S; j++)
       {
-        const int rel = j * NT + tid - off;
+        const int rel = fj[j] - off;
         glob[j] = rel < -halo;
-        sp[j] = tile + kHalo + rel;
+        sp[j] = tile + colj[j] - off;
         gi[j] = (tabs0 + (uint32_t)rel) & ring_mask;
       }
 #pragma unroll kPlUnroll
@@ -319,7 +363,7 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
         for (int j = 0; j < S; j++)
         {
           if (glob[j])
-            xq[j] = ld_ring(ring + gi[j]);
+            xq[j] = ld_ring(ring[j] + gi[j]);
           else
             xq[j] = *sp[j];
           sp[j] += TW;
@@ -358,14 +402,13 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
 #pragma unroll
     for (int j = 0; j < S; j++)
     {
-      const int trel = j * NT + tid;
-      const bool keep = (trel < Tv) && (trel >= Tv - lookback);
+      const bool keep = (fj[j] < Tv[j]) && (fj[j] >= Tv[j] - lookback);
 #pragma unroll
       for (int pl = 0; pl < P; pl++)
       {
-        const float4 own = tile[pl * TW + kHalo + trel];
+        const float4 own = tile[pl * TW + colj[j]];
         if (keep)
-          st_ring(ring + pl * R + ((tabs0 + (uint32_t)trel) & ring_mask), own);
+          st_ring(ring[j] + pl * R + ((tabs0 + (uint32_t)fj[j]) & ring_mask), own);
         const float4 pb = *reinterpret_cast<const float4*>(w_pb + 4 * pl);
         hn[j][2 * pl] = pack2(own.x + pb.x, own.y + pb.y);
         hn[j][2 * pl + 1] = pack2(own.z + pb.z, own.w + pb.w);
@@ -382,7 +425,6 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
 #pragma unroll
     for (int j = 0; j < S; j++)
     {
-      const int trel = j * NT + tid;
       if (!last)
       {
 #pragma unroll
@@ -391,7 +433,7 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
           float4 v;
           unpack2(hn[j][2 * pl], v.x, v.y);
           unpack2(hn[j][2 * pl + 1], v.z, v.w);
-          tile[pl * TW + kHalo + trel] = v;
+          tile[pl * TW + colj[j]] = v;
         }
       }
       else
@@ -412,7 +454,10 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
     const int HK = A.head_kernel, hdil = A.head_dilation, HL = (HK - 1) * hdil;
     const uint32_t hmask = (uint32_t)A.head_ring_mask;
     const int HR = A.head_ring_mask + 1;
-    float4* __restrict__ hring = reinterpret_cast<float4*>(state + A.head_ring_off);
+    float4* hring[S];
+#pragma unroll
+    for (int j = 0; j < S; j++)
+      hring[j] = reinterpret_cast<float4*>(state[Q == 1 ? 0 : j] + A.head_ring_off);
     const float* __restrict__ w_hb = wh + HK * C * HOUT;
 #pragma unroll
     for (int j = 0; j < S; j++)
@@ -422,23 +467,25 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
         float4 v;
         unpack2(head[j][2 * pl], v.x, v.y);
         unpack2(head[j][2 * pl + 1], v.z, v.w);
-        tile[pl * TW + kHalo + j * NT + tid] = v;
+        tile[pl * TW + colj[j]] = v;
       }
-    for (int idx = tid; idx < HL * P; idx += NT)
+    for (int idx = tid; idx < Q * P * HL; idx += NT)
     {
-      const int pl = idx / HL, col = idx - pl * HL;
-      tile[pl * TW + kHalo - HL + col] = ld_ring(hring + pl * HR + ((tabs0 - (uint32_t)HL + (uint32_t)col) & hmask));
+      const int col = idx % HL, t2 = idx / HL;
+      const int pl = t2 % P, q = t2 / P;
+      const float4* __restrict__ rq =
+        (Q == 1) ? hring[0] : reinterpret_cast<const float4*>(sub_state(q) + A.head_ring_off);
+      tile[pl * TW + q * SW + kHalo - HL + col] = ld_ring(rq + pl * HR + ((tabs0 - (uint32_t)HL + (uint32_t)col) & hmask));
     }
     __syncthreads(); // accumulator columns + halo visible; all ring reads done before the ring is rewritten
 #pragma unroll
     for (int j = 0; j < S; j++)
     {
-      const int trel = j * NT + tid;
-      if ((trel < Tv) && (trel >= Tv - HL))
+      if ((fj[j] < Tv[j]) && (fj[j] >= Tv[j] - HL))
       {
 #pragma unroll
         for (int pl = 0; pl < P; pl++)
-          st_ring(hring + pl * HR + ((tabs0 + (uint32_t)trel) & hmask), tile[pl * TW + kHalo + trel]);
+          st_ring(hring[j] + pl * HR + ((tabs0 + (uint32_t)fj[j]) & hmask), tile[pl * TW + colj[j]]);
       }
       float out[HOUT];
 #pragma unroll
@@ -448,7 +495,7 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
 #pragma unroll 1
       for (int k = 0; k < HK; k++)
       {
-        const float4* sp = tile + kHalo + trel - (HK - 1 - k) * hdil;
+        const float4* sp = tile + colj[j] - (HK - 1 - k) * hdil;
 #pragma unroll
         for (int pl = 0; pl < P; pl++)
         {
@@ -508,18 +555,16 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
   }
 }
 
-// One persistent CTA per stream-slot.  C1 == 0: single layer array.
-template <int C0, int C1, int S, int NT, int MINB>
+// One persistent CTA per slot of Q = (S * NT) >> LQ streams.  C1 == 0: single layer array.
+template <int C0, int C1, int S, int NT, int MINB, int LQ>
 __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_constant__ WaveNetKernelParams p)
 {
   constexpr int T = S * NT;
-  constexpr int CMAX = (C0 > C1) ? C0 : C1;
-  constexpr int TW = kHalo + T;
+  constexpr int FQ = 1 << LQ;
+  constexpr int Q = T / FQ;
   extern __shared__ float4 smem4[];
   float* sw = reinterpret_cast<float*>(smem4);
   float4* tile = smem4 + (p.n_weight_floats + 3) / 4;
-  (void)CMAX;
-  (void)TW;
 
   const int tid = threadIdx.x;
   // weights -> shared memory, once per CTA
@@ -530,22 +575,38 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
   }
   __syncthreads();
 
-  for (int stream = blockIdx.x; stream < p.batch; stream += gridDim.x)
+  for (int stream0 = blockIdx.x * Q; stream0 < p.batch; stream0 += gridDim.x * Q)
   {
-    float* __restrict__ state = p.state + (size_t)stream * p.state_stride;
-    const float* __restrict__ xin = p.in + (size_t)stream * p.in_stride;
-    float* __restrict__ yout = p.out + (size_t)stream * p.out_stride;
-
-    for (int t0 = 0; t0 < p.n_frames; t0 += T)
+    // the stream each of this thread's frames belongs to (slots beyond the batch alias the last stream, masked by Tv)
+    float* state[S];
+    const float* xin[S];
+    float* yout[S];
+    bool live[S];
+    int fj[S];
+#pragma unroll
+    for (int j = 0; j < S; j++)
     {
-      const int Tv = min(T, p.n_frames - t0);
+      const int trel = j * NT + tid;
+      const int sj = stream0 + (trel >> LQ);
+      live[j] = sj < p.batch;
+      const size_t sc = (size_t)min(sj, p.batch - 1);
+      state[j] = p.state + sc * p.state_stride;
+      xin[j] = p.in + sc * p.in_stride;
+      yout[j] = p.out + sc * p.out_stride;
+      fj[j] = trel & (FQ - 1);
+    }
+
+    for (int t0 = 0; t0 < p.n_frames; t0 += FQ)
+    {
+      const int tv = min(FQ, p.n_frames - t0);
       const uint32_t tabs0 = p.t_base + (uint32_t)t0;
+      int Tv[S];
       float x[S][1], cond[S];
 #pragma unroll
       for (int j = 0; j < S; j++)
       {
-        const int trel = j * NT + tid;
-        x[j][0] = (trel < Tv) ? __ldg(xin + t0 + trel) : 0.0f;
+        Tv[j] = live[j] ? tv : 0;
+        x[j][0] = (fj[j] < Tv[j]) ? __ldg(xin[j] + t0 + fj[j]) : 0.0f;
         cond[j] = x[j][0]; // no condition_dsp: condition == input (model.cpp:781)
       }
       float y[S];
@@ -558,7 +619,7 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
           for (int q = 0; q < C0 / 2; q++)
             head0[j][q] = 0ull; // model.cpp:469
         float hout0[S][C0], ho0[S][1];
-        array_forward<1, C0, 1, S, NT>(p, p.arrays[0], sw, tile, state, tabs0, Tv, x, cond, head0, hout0, ho0);
+        array_forward<1, C0, 1, S, NT, LQ>(p, p.arrays[0], sw, tile, state, stream0, tabs0, Tv, x, cond, head0, hout0, ho0);
 #pragma unroll
         for (int j = 0; j < S; j++)
           y[j] = ho0[j][0];
@@ -573,7 +634,8 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
 #pragma unroll
             for (int q = 0; q < C0 / 2; q++)
               head0[j][q] = 0ull;
-          array_forward<1, C0, C1, S, NT>(p, p.arrays[0], sw, tile, state, tabs0, Tv, x, cond, head0, hout0, ho0);
+          array_forward<1, C0, C1, S, NT, LQ>(p, p.arrays[0], sw, tile, state, stream0, tabs0, Tv, x, cond, head0, hout0,
+                                              ho0);
         }
         // second array: layer input = previous array's layer output, head accumulator starts from
         // the previous array's head output (model.cpp:846-848, :473-486)
@@ -584,20 +646,18 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
           for (int q = 0; q < C1 / 2; q++)
             head1[j][q] = pack2(ho0[j][2 * q], ho0[j][2 * q + 1]);
         float hout1[S][C1], ho1[S][1];
-        array_forward<C0, C1, 1, S, NT>(p, p.arrays[1], sw, tile, state, tabs0, Tv, hout0, cond, head1, hout1, ho1);
+        array_forward<C0, C1, 1, S, NT, LQ>(p, p.arrays[1], sw, tile, state, stream0, tabs0, Tv, hout0, cond, head1, hout1,
+                                            ho1);
 #pragma unroll
         for (int j = 0; j < S; j++)
           y[j] = ho1[j][0];
       }
 #pragma unroll
       for (int j = 0; j < S; j++)
-      {
-        const int trel = j * NT + tid;
-        if (trel < Tv)
-          yout[t0 + trel] = p.head_scale * y[j]; // model.cpp:888-897
-      }
+        if (fj[j] < Tv[j])
+          yout[j][t0 + fj[j]] = p.head_scale * y[j]; // model.cpp:888-897
     }
-    __syncthreads(); // the next stream reuses the tile
+    __syncthreads(); // the next streams reuse the tile
   }
 }
 

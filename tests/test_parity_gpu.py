@@ -326,3 +326,25 @@ def test_pipelined_host_call_equals_the_single_launch():
     assert np.max(np.abs(y[pick] - ref)) <= TOL
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("name,batch", [("wavenet_a1_standard", 37), ("a2_full", 9), ("wavenet", 16)])
+def test_short_calls_take_the_multi_stream_tiles(name, batch):
+    """Calls of <= 96 frames on >= 8 streams run 4 streams per CTA tile (64-frame sub-tiles with their own halos,
+    wavenet_fused.cuh LQ = 6): the reference tools' 64-frame protocol, odd block sizes, a batch that does not fill
+    the last tile, and long / short calls interleaved on one handle (the rings are shared by both geometries)."""
+    nam = fx.load_model(name)
+    x = fx.synthetic_batch(batch, 1200, seed=13)
+    proto = oracle.OracleModel.from_dict(nam)
+    proto.reset(48000.0, 64)
+    ref = proto.run_batch(x, 64)
+    d = nb.get_dsp(nam, batch=batch)
+    d.Reset(48000.0, 512)
+    outs, pos = [], 0
+    for n in (64, 64, 1, 7, 96, 33, 512, 64, 95, 200, 64):  # 1200 frames in total
+        outs.append(d.process_batch(np.ascontiguousarray(x[:, pos:pos + n])))
+        pos += n
+    assert pos == 1200
+    d.close()
+    err = np.max(np.abs(np.concatenate(outs, axis=1) - ref))
+    assert err <= TOL, f"{name}: {err:.3e}"
