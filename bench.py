@@ -428,6 +428,7 @@ def run_b200(args) -> None:
         quick("wavenet_a1_standard_batch1", MODEL, 1, 4096)
         quick("wavenet_a1_standard_batch256", MODEL, 256, 4096)
         quick("wavenet_a1_standard_batch4096_64frame_calls", MODEL, 4096, 64, steps=32)
+        quick("wavenet_a1_standard_batch4096_128frame_calls", MODEL, 4096, 128, steps=32)
         quick("a2_full_batch4096", "a2_full", 4096, 4096, steps=4)
         quick("lstm_batch4096", "lstm", 4096, 4096, steps=4)
         quick("wavenet_a2_max_batch4096_general_kernel", "wavenet_a2_max", 4096, 1024, steps=2)

@@ -330,7 +330,7 @@ struct nam_b200_model
   WaveNetPlan plan;
   int variant = 0;
   int wn_ctas_per_sm = 0; // resident CTAs per SM of the fused kernel (occupancy query, cached)
-  int wn_ctas_short = 0; // same for the short-call (multi-stream tile) geometry
+  int wn_ctas_short[2] = {0, 0}; // same for the short-call (multi-stream tile) geometries 2 / 3
   int wn_geometry = 1; // 0 / 1: index into kWnGeom (FFMA kernel); 2: tensor-core kernel (wavenet_tc.cuh)
   float* d_tc_blob = nullptr; // per-layer B-operand images of the tensor-core kernel
   // general WaveNet kernel (wavenet_generic.cuh): every option the fused kernels do not specialise
@@ -415,9 +415,10 @@ struct WnGeometry
   int frames_per_subtile() const { return 1 << lq; }
   int streams_per_tile() const { return (kWnS * nt) >> lq; }
 };
-constexpr WnGeometry kWnGeom[3] = {{128, 3, 8}, {256, 2, 9}, {128, 3, 6}};
-constexpr int kWnShortGeom = 2;
-constexpr int kWnShortMaxFrames = 96; // calls up to this many frames take the multi-stream geometry
+//   geometry 3: 256 threads, the 512-frame tile split into 4 streams x 128 frames (calls of 97..192 frames)
+constexpr WnGeometry kWnGeom[4] = {{128, 3, 8}, {256, 2, 9}, {128, 3, 6}, {256, 2, 7}};
+// calls of up to this many frames take the multi-stream geometry 2 / 3
+constexpr int kWnShortMaxFrames[2] = {96, 192};
 
 template <int C0, int C1, int NT, int MINB, int LQ>
 void launch_wavenet_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem, cudaStream_t st)
@@ -447,7 +448,8 @@ int occupancy_wavenet_variant(size_t smem)
 #define WN_CASE(C0, C1, FN, ...)                                                                                     \
   case (C0) * 100 + (C1):                                                                                            \
     return geom == 0 ? FN<C0, C1, 128, 3, 8>(__VA_ARGS__)                                                            \
-                     : (geom == 1 ? FN<C0, C1, 256, 2, 9>(__VA_ARGS__) : FN<C0, C1, 128, 3, 6>(__VA_ARGS__));
+                     : (geom == 1 ? FN<C0, C1, 256, 2, 9>(__VA_ARGS__)                                               \
+                                  : (geom == 2 ? FN<C0, C1, 128, 3, 6>(__VA_ARGS__) : FN<C0, C1, 256, 2, 7>(__VA_ARGS__)));
 
 #define WN_DISPATCH(FN, ...)                                                                                         \
   switch (c0 * 100 + c1)                                                                                             \
@@ -607,15 +609,19 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
     return;
   }
   // short calls on more than a handful of streams: several streams per tile (same rings, same arithmetic)
-  if (n_frames <= kWnShortMaxFrames && batch >= 2 * kWnGeom[kWnShortGeom].streams_per_tile()
-      && wavenet_smem_bytes(plan, kWnShortGeom) <= 227 * 1024 && m->opts.kernel_geometry == 0)
+  for (int sg = 0; sg < 2; sg++)
   {
-    const size_t smem_s = wavenet_smem_bytes(plan, kWnShortGeom);
-    if (m->wn_ctas_short <= 0)
-      m->wn_ctas_short = occupancy_wavenet_dispatch(c0, c1, kWnShortGeom, smem_s);
-    const int q = kWnGeom[kWnShortGeom].streams_per_tile();
-    int grid_s = std::min((batch + q - 1) / q, m->wn_ctas_short * m->sm_count);
-    launch_wavenet_dispatch(c0, c1, kWnShortGeom, m, kp, std::max(grid_s, 1), smem_s, st);
+    const int g = 2 + sg;
+    if (n_frames > kWnShortMaxFrames[sg])
+      continue;
+    if (batch < 2 * kWnGeom[g].streams_per_tile() || wavenet_smem_bytes(plan, g) > 227 * 1024 || m->opts.kernel_geometry != 0)
+      break;
+    const size_t smem_s = wavenet_smem_bytes(plan, g);
+    if (m->wn_ctas_short[sg] <= 0)
+      m->wn_ctas_short[sg] = occupancy_wavenet_dispatch(c0, c1, g, smem_s);
+    const int q = kWnGeom[g].streams_per_tile();
+    const int grid_s = std::min((batch + q - 1) / q, m->wn_ctas_short[sg] * m->sm_count);
+    launch_wavenet_dispatch(c0, c1, g, m, kp, std::max(grid_s, 1), smem_s, st);
     m->launches++;
     return;
   }

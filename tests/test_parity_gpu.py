@@ -341,7 +341,7 @@ def test_short_calls_take_the_multi_stream_tiles(name, batch):
     d = nb.get_dsp(nam, batch=batch)
     d.Reset(48000.0, 512)
     outs, pos = [], 0
-    for n in (64, 64, 1, 7, 96, 33, 512, 64, 95, 200, 64):  # 1200 frames in total
+    for n in (64, 64, 1, 7, 96, 33, 512, 64, 95, 128, 72, 64):  # 1200 frames in total; 128 -> 4 x 128-frame tiles
         outs.append(d.process_batch(np.ascontiguousarray(x[:, pos:pos + n])))
         pos += n
     assert pos == 1200
