@@ -59,8 +59,8 @@ typedef struct nam_b200_options
   int32_t ctas_per_sm; /* 0 = library default; tuning knob for the persistent WaveNet kernel */
   int32_t kernel_geometry; /* WaveNet kernel: 0 = library default; 1 = FP32 FFMA2 kernel, 128-thread CTAs (tile 256);
                               2 = FP32 FFMA2 kernel, 256-thread CTAs (tile 512); 3 = tensor-core kernel (tcgen05,
-                              3xTF32 split, tile 128); 4 = the general kernel (all WaveNet options, one thread per
-                              stream) that otherwise serves only models outside the fused families */
+                              3xTF32 split, tile 128); 4 = the general kernel (all WaveNet options, one CTA per stream,
+                              thread per frame) that otherwise serves only models outside the fused families */
   int32_t reserved[7];
 } nam_b200_options;
 

@@ -6,7 +6,7 @@
 // bottleneck != channels, grouped convolutions, head1x1, the eight FiLM sites, a condition_dsp sub-model, the
 // post-stack head (NAM/wavenet/model.cpp:19-103,183-393,777-910; NAM/film.h; NAM/gating_activations.h) -- runs
 // through this description: every matrix dense (grouped ones are block diagonal with explicit zeros, which adds
-// exact zeros to the sums), one thread per stream, one frame at a time.
+// exact zeros to the sums); one CTA per stream, one thread per frame of a 128-frame tile, layer by layer.
 #pragma once
 
 #include <stdint.h>
@@ -18,6 +18,7 @@ constexpr int kGenMaxVec = 64; // widest per-frame vector (channels, 2 x bottlen
 constexpr int kGenMaxArrays = 4;
 constexpr int kGenMaxHeadConvs = 8;
 constexpr int kGenFilmSites = 8;
+constexpr int kGenTile = 128; // frames per tile == threads per CTA of the general kernel
 
 // y = W x (+ b): W (out x in) row-major at weights[w_off]; b at weights[b_off] or b_off < 0
 struct GMat
@@ -26,7 +27,8 @@ struct GMat
 };
 
 // causal dilated convolution; weights [k][out][in], tap 0 = oldest.  The ring keeps the convolution's INPUT
-// vectors of the last ring_mask + 1 frames of a stream: element (slot, i) at state index ring_off + slot * in + i
+// vectors of the last ring_mask + 1 >= look-back + kGenTile frames of a stream (a whole tile is written before
+// any tap is read): element (slot, i) at float ring_off + slot * in + i of the stream's state
 struct GConv
 {
   int in, out, kernel, dilation, w_off, b_off, ring_off, ring_mask;
@@ -79,8 +81,8 @@ struct GenericKernelParams
   GNet net;
   GNet cond; // condition_dsp sub-model (valid when has_cond)
   int has_cond;
-  float* state; // element idx of stream s at state[idx * state_streams + s]
-  long state_streams; // max_batch of the handle
+  float* state; // [stream][state_stride]
+  long state_stride; // floats
   const float* in;
   float* out;
   long in_stride, out_stride;

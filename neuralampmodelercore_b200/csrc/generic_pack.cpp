@@ -56,12 +56,16 @@ struct Packer
     width(v.out, "convolution output width");
     if ((long)v.w.size() != (long)v.kernel * v.in * v.out && err.empty())
       err = "internal: conv weight count";
-    long r = 1;
-    while (r < v.lookback() + 1)
-      r <<= 1;
-    g.ring_mask = (int)(r - 1);
+    g.ring_mask = 0;
     g.ring_off = (int)plan.state_floats;
-    plan.state_floats += r * v.in;
+    if (v.kernel > 1)
+    {
+      long r = 1;
+      while (r < v.lookback() + kGenTile)
+        r <<= 1;
+      g.ring_mask = (int)(r - 1);
+      plan.state_floats += r * v.in;
+    }
     plan.macs_per_frame += (double)v.kernel * v.in * v.out / std::max(v.groups, 1);
     return g;
   }

@@ -554,8 +554,8 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
     gp.net = m->gplan.net;
     gp.cond = m->gplan.cond;
     gp.has_cond = m->gplan.has_cond ? 1 : 0;
-    gp.state = m->d_state + stream0; // stream-minor layout
-    gp.state_streams = m->opts.max_batch;
+    gp.state = m->d_state + (size_t)stream0 * (size_t)m->state_stride;
+    gp.state_stride = m->state_stride;
     gp.in = d_in;
     gp.out = d_out;
     gp.in_stride = in_stride;
@@ -563,7 +563,7 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
     gp.batch = batch;
     gp.n_frames = n_frames;
     gp.t_base = m->t_base;
-    wavenet_generic_kernel<<<(batch + 63) / 64, 64, 0, st>>>(gp);
+    wavenet_generic_kernel<<<std::min(batch, 16 * m->sm_count), kGenTile, 0, st>>>(gp);
     CUDA_CHECK(cudaGetLastError());
     m->launches++;
     return;
@@ -791,15 +791,6 @@ void broadcast_state(nam_b200_model* m)
   const int batch = m->opts.max_batch;
   if (batch <= 1 || m->state_stride == 0)
     return;
-  if (m->use_generic)
-  {
-    const long total = m->state_stride * (long)batch;
-    const int blocks = (int)std::min<long>((total + 255) / 256, 4096);
-    generic_broadcast_state_kernel<<<blocks, 256, 0, m->stream>>>(m->d_state, m->state_stride, batch);
-    CUDA_CHECK(cudaGetLastError());
-    m->launches++;
-    return;
-  }
   dim3 grid((unsigned)std::min<long>((m->state_stride / 4 + 255) / 256, 1024), (unsigned)std::min(batch - 1, 64));
   if (grid.x < 1)
     grid.x = 1;

@@ -3,11 +3,13 @@
 // condition_dsp and the post-stack head :19-103; NAM/film.h:76-190; NAM/gating_activations.h:100-113,209-227),
 // driven by the descriptors of generic_desc.h.
 //
-// One thread per stream, one frame at a time, all vectors in per-thread scratch: the models that need this
-// path are tiny (example_models/wavenet_a2_max.nam: 818 + 1,052 weights) and exist for their features, not
-// their throughput -- the throughput families have the fused kernels.  State (the input rings of every
-// convolution) is laid out frame-vector-major / stream-minor, so the 32 streams of a warp touch consecutive
-// addresses; weights are read through the read-only path at warp-uniform addresses.
+// One CTA per stream, one thread per frame of a 128-frame tile, the whole network layer by layer for the tile
+// (the net is feed-forward, so the frames of a call are independent within a layer -- the same reframing as the
+// fused kernel, without its specialisations): all vectors of a frame live in the owning thread's scratch, only the
+// dilated taps cross threads, through the convolution's input ring in HBM/L2 (write the tile's columns, barrier,
+// read the taps, barrier).  The models that need this path are small (example_models/wavenet_a2_max.nam:
+// 818 + 1,052 weights) and exist for their features; the throughput families have the fused kernels.  Weights are
+// read through the read-only path at warp-uniform addresses.
 #pragma once
 
 #include "generic_desc.h"
@@ -19,9 +21,9 @@ namespace namb200
 struct GenThread
 {
   const float* __restrict__ w;
-  float* __restrict__ st; // already offset to this thread's stream
-  long B; // stream stride
-  uint32_t t; // absolute frame index
+  float* __restrict__ st; // this CTA's stream
+  uint32_t t; // absolute index of this thread's frame
+  bool valid; // the frame exists (threads beyond the end of a call still take part in the barriers)
 };
 
 __device__ __forceinline__ float g_act1(const GenThread& c, const GAct& A, float x, int ch)
@@ -61,15 +63,21 @@ __device__ __forceinline__ void g_matvec(const GenThread& c, const GMat& M, cons
   }
 }
 
-// causal dilated convolution of the stream: persist x[t], read x[t - off] from the ring (zeros before the reset)
+// causal dilated convolution over the tile: every thread persists its x[t] in the ring, then reads x[t - off]
+// (earlier threads' columns of this tile, or earlier calls'; zeros before the reset).  Called by all threads of the
+// CTA in step (the control flow depends on the descriptors only).
 __device__ __forceinline__ void g_conv(const GenThread& c, const GConv& V, const float* x, float* y)
 {
   const int K = V.kernel;
   if (K > 1)
   {
-    const long base = V.ring_off + (long)(c.t & (uint32_t)V.ring_mask) * V.in;
-    for (int i = 0; i < V.in; i++)
-      c.st[(base + i) * c.B] = x[i];
+    if (c.valid)
+    {
+      float* __restrict__ dst = c.st + V.ring_off + (long)(c.t & (uint32_t)V.ring_mask) * V.in;
+      for (int i = 0; i < V.in; i++)
+        dst[i] = x[i];
+    }
+    __syncthreads();
   }
   for (int o = 0; o < V.out; o++)
     y[o] = 0.0f;
@@ -80,9 +88,9 @@ __device__ __forceinline__ void g_conv(const GenThread& c, const GConv& V, const
     const float* src = x;
     if (off != 0)
     {
-      const long base = V.ring_off + (long)((c.t - (uint32_t)off) & (uint32_t)V.ring_mask) * V.in;
+      const float* __restrict__ rs = c.st + V.ring_off + (long)((c.t - (uint32_t)off) & (uint32_t)V.ring_mask) * V.in;
       for (int i = 0; i < V.in; i++)
-        tap[i] = c.st[(base + i) * c.B];
+        tap[i] = __ldcg(rs + i);
       src = tap;
     }
     const float* __restrict__ wk = c.w + V.w_off + (long)k * V.out * V.in;
@@ -97,6 +105,8 @@ __device__ __forceinline__ void g_conv(const GenThread& c, const GConv& V, const
   if (V.b_off >= 0)
     for (int o = 0; o < V.out; o++)
       y[o] += __ldg(c.w + V.b_off + o);
+  if (K > 1)
+    __syncthreads(); // every tap of this tile is read before the next tile's columns land in the ring
 }
 
 // FiLM (film.h:76-190): out = in * scale(cond) (+ shift(cond)); in place is allowed (out == in)
@@ -229,40 +239,30 @@ __device__ __forceinline__ void g_net(const GenThread& c, const GNet& N, const G
       out[i] = N.head_scale * hout[i];
 }
 
-// mono in / mono out streams (the C ABI's batched entry); one thread per stream
-__global__ void __launch_bounds__(64) wavenet_generic_kernel(const __grid_constant__ GenericKernelParams p)
+// mono in / mono out streams (the C ABI's batched entry); persistent CTAs, one stream at a time
+__global__ void __launch_bounds__(kGenTile) wavenet_generic_kernel(const __grid_constant__ GenericKernelParams p)
 {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= p.batch)
-    return;
   GenThread c;
   c.w = p.weights;
-  c.st = p.state + s;
-  c.B = p.state_streams;
-  const float* __restrict__ xin = p.in + (size_t)s * p.in_stride;
-  float* __restrict__ yout = p.out + (size_t)s * p.out_stride;
-  for (int f = 0; f < p.n_frames; f++)
+  for (int s = blockIdx.x; s < p.batch; s += gridDim.x)
   {
-    c.t = p.t_base + (uint32_t)f;
-    float in[1] = {xin[f]}, out[kGenMaxVec], cond[kGenMaxVec];
-    if (p.has_cond)
-      g_net(c, p.cond, p.layers, in, in, cond); // _process_condition (model.cpp:777-807)
-    else
-      cond[0] = in[0];
-    g_net(c, p.net, p.layers, in, cond, out);
-    yout[f] = out[0];
-  }
-}
-
-// after prewarming stream 0: copy its state to every other stream (stream-minor layout)
-__global__ void generic_broadcast_state_kernel(float* __restrict__ state, long n_idx, long streams)
-{
-  const long total = n_idx * streams;
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x)
-  {
-    const long idx = e / streams, s = e - idx * streams;
-    if (s != 0)
-      state[e] = state[idx * streams];
+    c.st = p.state + (size_t)s * p.state_stride;
+    const float* __restrict__ xin = p.in + (size_t)s * p.in_stride;
+    float* __restrict__ yout = p.out + (size_t)s * p.out_stride;
+    for (int t0 = 0; t0 < p.n_frames; t0 += kGenTile)
+    {
+      const int f = t0 + (int)threadIdx.x;
+      c.valid = f < p.n_frames;
+      c.t = p.t_base + (uint32_t)f;
+      float in[1] = {c.valid ? __ldg(xin + f) : 0.0f}, out[kGenMaxVec], cond[kGenMaxVec];
+      if (p.has_cond)
+        g_net(c, p.cond, p.layers, in, in, cond); // _process_condition (model.cpp:777-807)
+      else
+        cond[0] = in[0];
+      g_net(c, p.net, p.layers, in, cond, out);
+      if (c.valid)
+        yout[f] = out[0];
+    }
   }
 }
 
