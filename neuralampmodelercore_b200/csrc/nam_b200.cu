@@ -330,6 +330,7 @@ struct nam_b200_model
   WaveNetPlan plan;
   int variant = 0;
   int wn_ctas_per_sm = 0; // resident CTAs per SM of the fused kernel (occupancy query, cached)
+  int* d_tile_flags = nullptr; // tile-parallel mode hand-over counters, one per resident CTA
   int wn_ctas_short[2] = {0, 0}; // same for the short-call (multi-stream tile) geometries 2 / 3
   int wn_geometry = 1; // 0 / 1: index into kWnGeom (FFMA kernel); 2: tensor-core kernel (wavenet_tc.cuh)
   float* d_tc_blob = nullptr; // per-layer B-operand images of the tensor-core kernel
@@ -372,6 +373,8 @@ struct nam_b200_model
       cudaFree(d_tc_blob);
     if (d_glayers)
       cudaFree(d_glayers);
+    if (d_tile_flags)
+      cudaFree(d_tile_flags);
     if (d_state)
       cudaFree(d_state);
     if (d_state_tmp)
@@ -629,6 +632,24 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
   if (m->wn_ctas_per_sm <= 0)
     m->wn_ctas_per_sm = m->opts.ctas_per_sm > 0 ? m->opts.ctas_per_sm : occupancy_wavenet_dispatch(c0, c1, geom, smem);
   const int per_sm = m->wn_ctas_per_sm;
+  // Few streams, long calls: one CTA per (stream, tile), tiles of a stream handing their ring columns over layer
+  // by layer (a wavefront over tiles x layers instead of a serial walk).  All CTAs must be co-resident.
+  {
+    const int tile_frames = kWnS * kWnGeom[geom].nt;
+    const int tiles = (n_frames + tile_frames - 1) / tile_frames;
+    const long capacity = (long)per_sm * m->sm_count;
+    if (tiles >= 2 && (long)batch * tiles <= capacity && 2L * batch <= capacity)
+    {
+      if (!m->d_tile_flags)
+        CUDA_CHECK(cudaMalloc(&m->d_tile_flags, (size_t)capacity * sizeof(int)));
+      CUDA_CHECK(cudaMemsetAsync(m->d_tile_flags, 0, (size_t)batch * tiles * sizeof(int), st));
+      kp.tile_flags = m->d_tile_flags;
+      kp.tiles_per_stream = tiles;
+      launch_wavenet_dispatch(c0, c1, geom, m, kp, batch * tiles, smem, st);
+      m->launches++;
+      return;
+    }
+  }
   int grid = std::min(batch, per_sm * m->sm_count);
   if (grid < 1)
     grid = 1;

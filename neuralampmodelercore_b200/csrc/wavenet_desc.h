@@ -65,6 +65,12 @@ struct WaveNetKernelParams
   int n_arrays;
   ArrayDesc arrays[kMaxArrays];
   LayerDesc layers[kMaxLayers];
+  // Tile-parallel mode (few streams, long calls): CTA b handles tile (b % tiles_per_stream) of stream
+  // (b / tiles_per_stream) only; tile_flags[stream][tile] counts the ring hand-overs that tile has published
+  // (one per layer, one per convolutional head), and tile c waits for tile c-1 at every step -- a wavefront over
+  // (tile, layer) instead of a serial walk.  tile_flags == nullptr: the classic mode.
+  int* tile_flags;
+  int tiles_per_stream;
   // tensor-core variant (wavenet_tc.cuh): per-layer shared-memory images of the B operands
   const float* tc_blob;
   int tc_off[kMaxLayers]; // float offset of layer i's image in tc_blob

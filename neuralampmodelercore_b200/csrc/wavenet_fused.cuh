@@ -151,6 +151,39 @@ __device__ __forceinline__ void st_ring(float4* p, const float4& v)
   __stcg(p, v);
 }
 
+// ---- tile-parallel hand-over (WaveNetKernelParams::tile_flags) -------------------------------
+// A tile publishes "my ring columns of step k are in L2" by storing k + 1; its successor polls.
+struct TileSync
+{
+  const int* prev; // flag of the same stream's previous tile (nullptr: nothing to wait for)
+  int* mine; // this tile's flag (nullptr: classic mode)
+};
+__device__ __forceinline__ void tile_wait(const TileSync& ts, int step)
+{
+  if (ts.prev != nullptr) // uniform
+  {
+    if (threadIdx.x == 0)
+    {
+      int v;
+      do
+      {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ts.prev) : "memory");
+      } while (v <= step);
+    }
+    __syncthreads();
+  }
+}
+__device__ __forceinline__ void tile_publish(const TileSync& ts, int step)
+{
+  if (ts.mine != nullptr) // uniform
+  {
+    __threadfence(); // this thread's ring stores are visible device-wide
+    __syncthreads();
+    if (threadIdx.x == 0)
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ts.mine), "r"(step + 1) : "memory");
+  }
+}
+
 // ---- packed fp32 pairs ------------------------------------------------------------------------
 // Accumulators are kept as 64-bit register pairs and updated IN PLACE with fma.rn.f32x2 (SASS
 // FFMA2) through inline PTX: the "+l" constraint pins destination == addend, which stops ptxas
@@ -206,7 +239,8 @@ template <int CIN, int C, int HOUT, int S, int NT, int LQ>
 __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, const ArrayDesc& A,
                                               const float* __restrict__ sw, float4* __restrict__ tile,
                                               float* const (&state)[S], const int stream0, const uint32_t tabs0,
-                                              const int (&Tv)[S], const float (&hin)[S][CIN], const float (&cond)[S],
+                                              const TileSync& ts, const int step0, const int (&Tv)[S],
+                                              const float (&hin)[S][CIN], const float (&cond)[S],
                                               u64 (&head)[S][C / 2], float (&hout)[S][C], float (&headout)[S][HOUT])
 {
   constexpr int T = S * NT;
@@ -273,6 +307,8 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
     for (int j = 0; j < S; j++)
       ring[j] = reinterpret_cast<float4*>(state[Q == 1 ? 0 : j] + Ld.ring_off);
     const int halo = (lookback <= kHalo) ? lookback : 0; // (a 64-column halo for the longer look-backs costs more than it saves: measured)
+
+    tile_wait(ts, step0 + li); // tile-parallel mode: the previous tile's columns of this layer are in the ring
 
     // ---- phase 0: small-dilation layers pull their history [t0-L, t0) into the halo
     if constexpr (Q == 1)
@@ -443,6 +479,7 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
           unpack2(hn[j][q], hout[j][2 * q], hout[j][2 * q + 1]);
       }
     }
+    tile_publish(ts, step0 + li);
   }
 
   const float* __restrict__ wh = sw + A.head_off;
@@ -454,6 +491,7 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
     const int HK = A.head_kernel, hdil = A.head_dilation, HL = (HK - 1) * hdil;
     const uint32_t hmask = (uint32_t)A.head_ring_mask;
     const int HR = A.head_ring_mask + 1;
+    tile_wait(ts, step0 + A.n_layers);
     float4* hring[S];
 #pragma unroll
     for (int j = 0; j < S; j++)
@@ -515,6 +553,7 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
       for (int ho = 0; ho < HOUT; ho++)
         headout[j][ho] = out[ho];
     }
+    tile_publish(ts, step0 + A.n_layers);
     __syncthreads(); // the next array / tile rewrites the tile columns
     return;
   }
@@ -575,7 +614,24 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
   }
   __syncthreads();
 
-  for (int stream0 = blockIdx.x * Q; stream0 < p.batch; stream0 += gridDim.x * Q)
+  // classic mode: persistent CTA, slots of Q streams, all tiles of a call in turn.  Tile-parallel mode (Q == 1):
+  // this CTA owns ONE (stream, tile) and hands its ring columns to the next tile's CTA layer by layer.
+  int s_begin = blockIdx.x * Q, s_end = p.batch, s_step = gridDim.x * Q;
+  int t_begin = 0, t_end = p.n_frames;
+  TileSync ts{nullptr, nullptr};
+  if (Q == 1 && p.tile_flags != nullptr)
+  {
+    const int tile_i = blockIdx.x % p.tiles_per_stream;
+    s_begin = blockIdx.x / p.tiles_per_stream;
+    s_end = min(s_begin + 1, p.batch);
+    t_begin = tile_i * FQ;
+    t_end = min(p.n_frames, t_begin + FQ);
+    ts.mine = p.tile_flags + (size_t)s_begin * p.tiles_per_stream + tile_i;
+    ts.prev = tile_i > 0 ? ts.mine - 1 : nullptr;
+  }
+  const int step1 = p.arrays[0].n_layers + 1; // first hand-over step of the second layer array
+
+  for (int stream0 = s_begin; stream0 < s_end; stream0 += s_step)
   {
     // the stream each of this thread's frames belongs to (slots beyond the batch alias the last stream, masked by Tv)
     float* state[S];
@@ -596,7 +652,7 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
       fj[j] = trel & (FQ - 1);
     }
 
-    for (int t0 = 0; t0 < p.n_frames; t0 += FQ)
+    for (int t0 = t_begin; t0 < t_end; t0 += FQ)
     {
       const int tv = min(FQ, p.n_frames - t0);
       const uint32_t tabs0 = p.t_base + (uint32_t)t0;
@@ -619,7 +675,8 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
           for (int q = 0; q < C0 / 2; q++)
             head0[j][q] = 0ull; // model.cpp:469
         float hout0[S][C0], ho0[S][1];
-        array_forward<1, C0, 1, S, NT, LQ>(p, p.arrays[0], sw, tile, state, stream0, tabs0, Tv, x, cond, head0, hout0, ho0);
+        array_forward<1, C0, 1, S, NT, LQ>(p, p.arrays[0], sw, tile, state, stream0, tabs0, ts, 0, Tv, x, cond, head0, hout0,
+                                           ho0);
 #pragma unroll
         for (int j = 0; j < S; j++)
           y[j] = ho0[j][0];
@@ -634,8 +691,8 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
 #pragma unroll
             for (int q = 0; q < C0 / 2; q++)
               head0[j][q] = 0ull;
-          array_forward<1, C0, C1, S, NT, LQ>(p, p.arrays[0], sw, tile, state, stream0, tabs0, Tv, x, cond, head0, hout0,
-                                              ho0);
+          array_forward<1, C0, C1, S, NT, LQ>(p, p.arrays[0], sw, tile, state, stream0, tabs0, ts, 0, Tv, x, cond, head0,
+                                              hout0, ho0);
         }
         // second array: layer input = previous array's layer output, head accumulator starts from
         // the previous array's head output (model.cpp:846-848, :473-486)
@@ -646,8 +703,8 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
           for (int q = 0; q < C1 / 2; q++)
             head1[j][q] = pack2(ho0[j][2 * q], ho0[j][2 * q + 1]);
         float hout1[S][C1], ho1[S][1];
-        array_forward<C0, C1, 1, S, NT, LQ>(p, p.arrays[1], sw, tile, state, stream0, tabs0, Tv, hout0, cond, head1, hout1,
-                                            ho1);
+        array_forward<C0, C1, 1, S, NT, LQ>(p, p.arrays[1], sw, tile, state, stream0, tabs0, ts, step1, Tv, hout0, cond,
+                                            head1, hout1, ho1);
 #pragma unroll
         for (int j = 0; j < S; j++)
           y[j] = ho1[j][0];
