@@ -945,6 +945,7 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
           if (!m->plan.tc_eligible)
             return fail(NAM_B200_ERR_UNSUPPORTED, "tensor-core kernel not available for this model: " + m->plan.tc_why_not);
           m->wn_geometry = 2;
+          m->state_stride = 2 * m->plan.state_floats; // this kernel's rings hold hi and lo parts (wavenet_tc.cuh)
           if (tc_smem_bytes(m->plan) > 227 * 1024)
             return fail(NAM_B200_ERR_UNSUPPORTED, "tensor-core kernel: tiles do not fit in shared memory");
           CUDA_CHECK(cudaMalloc(&m->d_tc_blob, m->plan.tc_blob.size() * sizeof(float)));

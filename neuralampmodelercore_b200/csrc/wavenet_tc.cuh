@@ -24,11 +24,15 @@
 // the warps available to hide the L2 / TMEM / MUFU latencies (the first version, one thread per row, sat at 29 %
 // issue-active: profiles/r01c_tc_kernel_v1.json).
 //
-// Per layer:  barrier -> thread 0 issues the conv MMAs -> commit;   meanwhile all threads stream in the next
-// layer's weights (cp.async), persist the tail of h_l to the ring and fetch the next layer's halo columns into
-// registers ->  wait -> tcgen05.ld Z, +bias +mixin, activation, head += a, write a (hi/lo) to shared ->
-// barrier -> 1x1 MMAs;  meanwhile fetch the next layer's far taps (off > 64) from the rings into registers ->
-// wait -> tcgen05.ld D, residual add in registers, write h_{l+1} (hi/lo) to the tile, store the staged taps.
+// History: this kernel's rings hold the layer inputs already split (hi planes, then lo planes), so halo columns
+// and far taps move ring -> shared memory with cp.async alone.  Epilogue arithmetic runs on packed f32x2 pairs
+// (the FMA pipe is idle here; issue slots are the scarce resource).
+//
+// Per layer:  wait for the cp.async groups (weights, halo, staged taps) -> barrier -> thread 0 issues the conv
+// MMAs -> commit;   meanwhile all threads stream in the next layer's weights and persist the tail of h_l ->
+// wait -> start the next layer's halo copies -> tcgen05.ld Z, +bias +mixin, activation, head += a, write a (hi/lo)
+// to shared -> barrier -> 1x1 MMAs -> wait -> tcgen05.ld D, residual add in registers, write h_{l+1} (hi/lo) to the
+// tile, start the next layer's far-tap copies.
 #pragma once
 
 #include "wavenet_fused.cuh"
@@ -170,58 +174,103 @@ __device__ __forceinline__ void tc_prefetch_weights(const WaveNetKernelParams& p
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-// this thread's PH planes of one column, split into hi / lo
+// ---- packed fp32 pairs for the epilogues (the FMA pipe is idle in this kernel; issue slots are what count) ----
+__device__ __forceinline__ u64 tc_fma2(u64 a, u64 b, u64 c)
+{
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 tc_mul2(u64 a, u64 b)
+{
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 tc_add2(u64 a, u64 b)
+{
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 tc_dup(float v)
+{
+  return pack2(v, v);
+}
+constexpr u64 kTcAbsMask = 0x7FFFFFFF7FFFFFFFull;
+// x = hi + lo with hi on 11 significant bits (exactly a TF32 number), Veltkamp's splitting: 4 packed instructions
+// per pair instead of 6 integer / float ones
+__device__ __forceinline__ void tc_split2(u64 x, u64& hi, u64& lo)
+{
+  const u64 m1 = tc_dup(-1.0f);
+  const u64 t = tc_mul2(x, tc_dup(8193.0f)); // 2^13 + 1
+  const u64 d = tc_fma2(m1, x, t); // t - x
+  hi = tc_fma2(m1, d, t); // t - (t - x)
+  lo = tc_fma2(m1, hi, x); // x - hi, exact
+}
+// the reference's rational fast_tanh (activations.h:91-98) on a pair
+__device__ __forceinline__ u64 tc_fast_tanh2(u64 x)
+{
+  const u64 ax = x & kTcAbsMask;
+  const u64 x2 = tc_mul2(x, x);
+  const u64 c0 = tc_dup(2.45550750702956f);
+  const u64 t1 = tc_fma2(tc_dup(0.821226666969744f), ax, tc_dup(0.893229853513558f));
+  const u64 t0 = tc_fma2(c0, ax, c0);
+  const u64 num = tc_mul2(x, tc_fma2(t1, x2, t0));
+  const u64 s = tc_fma2(tc_dup(0.814642734961073f), tc_mul2(x, ax), x) & kTcAbsMask;
+  const u64 d0 = tc_dup(2.44506634652299f);
+  const u64 den = tc_fma2(tc_add2(x2, d0), s, d0);
+  float dl, dh;
+  unpack2(den, dl, dh);
+  return tc_mul2(num, pack2(rcp_approx(dl), rcp_approx(dh)));
+}
+
+// this thread's PH planes (NP = 2 PH pairs) of one column, split into hi / lo
 template <int PH>
-__device__ __forceinline__ void tc_store_planes(float4* __restrict__ hi_base, float4* __restrict__ lo_base, int stride,
-                                                int pl0, int col, const float (&v)[4 * PH])
+__device__ __forceinline__ void tc_store_pairs(float4* __restrict__ hi_base, float4* __restrict__ lo_base, int stride,
+                                               int pl0, int col, const u64 (&v)[2 * PH])
 {
 #pragma unroll
   for (int q = 0; q < PH; q++)
   {
-    float4 hi, lo;
-    tc_split4(make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), hi, lo);
-    hi_base[(pl0 + q) * stride + col] = hi;
-    lo_base[(pl0 + q) * stride + col] = lo;
+    ulonglong2 hi, lo;
+    tc_split2(v[2 * q], hi.x, lo.x);
+    tc_split2(v[2 * q + 1], hi.y, lo.y);
+    *reinterpret_cast<ulonglong2*>(hi_base + (pl0 + q) * stride + col) = hi;
+    *reinterpret_cast<ulonglong2*>(lo_base + (pl0 + q) * stride + col) = lo;
   }
 }
 
-// Halo columns [t0 - halo, t0) of layer L's input come from its ring: one (plane, column) item per thread.
-struct TcHaloItem
-{
-  bool valid;
-  int dst; // float4 index into the tile
-  float4 v;
-};
+// The rings of this kernel hold the layer inputs already split: hi planes [P][R], then lo planes [P][R]
+// (twice the floats of the FP32 kernel's rings, at float offset 2 * ring_off of the stream's state).  History then
+// moves ring -> shared memory with cp.async only: no registers, no arithmetic.
 template <int C>
-__device__ __forceinline__ void tc_halo_load(TcHaloItem& it, const LayerDesc& L, const float* __restrict__ state,
-                                             uint32_t tabs0)
+__device__ __forceinline__ const float4* tc_ring(const LayerDesc& L, const float* __restrict__ state)
+{
+  return reinterpret_cast<const float4*>(state + 2 * (size_t)L.ring_off);
+}
+
+// halo columns [t0 - halo, t0) of layer L's input: one (plane, column) item per thread, hi and lo
+template <int C>
+__device__ __forceinline__ void tc_halo_async(const LayerDesc& L, const TcSmem& sm, const float* __restrict__ state,
+                                              uint32_t tabs0)
 {
   constexpr int P = C / 4;
   const int halo = L.lookback < kHalo ? L.lookback : kHalo;
   const int col = threadIdx.x & (kHalo - 1), pl = threadIdx.x >> 6; // kHalo == 64
-  it.valid = (pl < P) && (col >= kHalo - halo);
-  it.dst = pl * kTcTW + col;
-  if (it.valid)
+  if (pl < P && col >= kHalo - halo)
   {
-    const float4* __restrict__ ring = reinterpret_cast<const float4*>(state + L.ring_off);
-    it.v = ld_ring(ring + pl * (L.ring_mask + 1) + ((tabs0 - (uint32_t)kHalo + (uint32_t)col) & (uint32_t)L.ring_mask));
-  }
-}
-__device__ __forceinline__ void tc_halo_store(const TcHaloItem& it, const TcSmem& sm)
-{
-  if (it.valid)
-  {
-    float4 hi, lo;
-    tc_split4(it.v, hi, lo);
-    sm.tile_hi[it.dst] = hi;
-    sm.tile_lo[it.dst] = lo;
+    const int R = L.ring_mask + 1;
+    const float4* src = tc_ring<C>(L, state) + pl * R + ((tabs0 - (uint32_t)kHalo + (uint32_t)col) & (uint32_t)L.ring_mask);
+    tc_cp_async16(sm.tile_hi + pl * kTcTW + col, src);
+    tc_cp_async16(sm.tile_lo + pl * kTcTW + col, src + P * R);
   }
 }
 
 // Taps whose window [t0 - off, t0 - off + 128) is not inside halo + tile (off > 64) are staged as their own
-// A operand, at most two per layer (wavenet_pack.cpp refuses more), in tap order.  The part of the window that
-// lies before t0 comes from the ring (fetched early, into registers); the part inside the current tile (only
-// when 64 < off < 128) is copied from the tile once it is complete.
+// A operand, at most two per layer (wavenet_pack.cpp refuses more), in tap order.  Rows before t0 come from the
+// ring (cp.async); rows inside the current tile (only when 64 < off < 128) are copied from the tile once it is
+// complete.
 __device__ __forceinline__ void tc_staged_offsets(const LayerDesc& L, int (&off)[2])
 {
   off[0] = off[1] = 0;
@@ -239,68 +288,45 @@ __device__ __forceinline__ void tc_staged_offsets(const LayerDesc& L, int (&off)
     }
   }
 }
-template <int PH>
-struct TcStage
-{
-  int off[2]; // 0 = slot unused
-  float4 v[2][PH];
-};
-template <int C>
-__device__ __forceinline__ void tc_stage_load(TcStage<C / 8>& s, const LayerDesc& L, const float* __restrict__ state,
-                                              uint32_t tabs0, int row, int pl0)
-{
-  constexpr int PH = C / 8;
-  tc_staged_offsets(L, s.off);
-  const float4* __restrict__ ring = reinterpret_cast<const float4*>(state + L.ring_off);
-  const int R = L.ring_mask + 1;
-#pragma unroll
-  for (int slot = 0; slot < 2; slot++)
-  {
-    const int rel = row - s.off[slot];
-    if (s.off[slot] != 0 && rel < 0)
-    {
-#pragma unroll
-      for (int q = 0; q < PH; q++)
-        s.v[slot][q] = ld_ring(ring + (pl0 + q) * R + ((tabs0 + (uint32_t)rel) & (uint32_t)L.ring_mask));
-    }
-  }
-}
 // returns true when some rows still have to be copied from the tile (tc_stage_copy, after a barrier)
 template <int C>
-__device__ __forceinline__ bool tc_stage_store(const TcStage<C / 8>& s, const TcSmem& sm, int row, int pl0)
+__device__ __forceinline__ bool tc_stage_async(const LayerDesc& L, const TcSmem& sm, const float* __restrict__ state,
+                                               uint32_t tabs0, int row, int pl0, int (&off)[2])
 {
   constexpr int PH = C / 8, P = C / 4;
+  tc_staged_offsets(L, off);
+  const int R = L.ring_mask + 1;
+  const float4* ring = tc_ring<C>(L, state);
   bool reads_tile = false;
 #pragma unroll
   for (int slot = 0; slot < 2; slot++)
   {
-    const int off = s.off[slot];
-    reads_tile |= (off != 0) && (off < kTcM);
-    if (off != 0 && row - off < 0)
+    const int o = off[slot];
+    reads_tile |= (o != 0) && (o < kTcM);
+    if (o != 0 && row - o < 0)
     {
       float4* st_hi = sm.ubuf + slot * (2 * P * kTcM);
       float4* st_lo = st_hi + P * kTcM;
 #pragma unroll
       for (int q = 0; q < PH; q++)
       {
-        float4 hi, lo;
-        tc_split4(s.v[slot][q], hi, lo);
-        st_hi[(pl0 + q) * kTcM + row] = hi;
-        st_lo[(pl0 + q) * kTcM + row] = lo;
+        const float4* src = ring + (pl0 + q) * R + ((tabs0 + (uint32_t)(row - o)) & (uint32_t)L.ring_mask);
+        tc_cp_async16(st_hi + (pl0 + q) * kTcM + row, src);
+        tc_cp_async16(st_lo + (pl0 + q) * kTcM + row, src + P * R);
       }
     }
   }
   return reads_tile;
 }
 template <int C>
-__device__ __forceinline__ void tc_stage_copy(const TcStage<C / 8>& s, const TcSmem& sm, int row, int pl0)
+__device__ __forceinline__ void tc_stage_copy(const int (&off)[2], const TcSmem& sm, int row, int pl0)
 {
   constexpr int PH = C / 8, P = C / 4;
 #pragma unroll
   for (int slot = 0; slot < 2; slot++)
   {
-    const int rel = row - s.off[slot];
-    if (s.off[slot] != 0 && rel >= 0)
+    const int rel = row - off[slot];
+    if (off[slot] != 0 && rel >= 0)
     {
       float4* st_hi = sm.ubuf + slot * (2 * P * kTcM);
       float4* st_lo = st_hi + P * kTcM;
@@ -336,45 +362,55 @@ __device__ __forceinline__ void tc_array_forward(const WaveNetKernelParams& p, c
   const float* __restrict__ gw = p.weights; // FFMA blob: rechannel / head weights (uniform, L1-resident)
 
   // ---- rechannel (Conv1x1 without bias, model.cpp:492), thread-local on this thread's output channels
-  float hres[CH];
+  constexpr int NP = CH / 2; // packed pairs per thread
+  u64 hres[NP]; // residual stream, fp32 pairs
+  u64 head2[NP];
 #pragma unroll
-  for (int o = 0; o < CH; o++)
-    hres[o] = 0.0f;
-  if constexpr (CIN == 1)
+  for (int q = 0; q < NP; q++)
+    head2[q] = pack2(head[2 * q], head[2 * q + 1]);
   {
+    float h[CH];
 #pragma unroll
     for (int o = 0; o < CH; o++)
-      hres[o] = __ldg(gw + A.rech_off + ch0 + o) * x;
-  }
-  else
-  {
-#pragma unroll
-    for (int pi = 0; pi < CIN / 4; pi++)
+      h[o] = 0.0f;
+    if constexpr (CIN == 1)
     {
-      const float4 v = sm.xch[pi * kTcM + row];
-      const float in4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int o = 0; o < CH; o++)
-          hres[o] = fmaf(__ldg(gw + A.rech_off + (4 * pi + i) * C + ch0 + o), in4[i], hres[o]);
+      for (int o = 0; o < CH; o++)
+        h[o] = __ldg(gw + A.rech_off + ch0 + o) * x;
     }
+    else
+    {
+#pragma unroll
+      for (int pi = 0; pi < CIN / 4; pi++)
+      {
+        const float4 v = sm.xch[pi * kTcM + row];
+        const float in4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int o = 0; o < CH; o++)
+            h[o] = fmaf(__ldg(gw + A.rech_off + (4 * pi + i) * C + ch0 + o), in4[i], h[o]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NP; q++)
+      hres[q] = pack2(h[2 * q], h[2 * q + 1]);
   }
   __syncthreads(); // xch / hx (aliases of ubuf) have been consumed by every thread; ubuf may be rewritten
-  tc_store_planes<PH>(sm.tile_hi, sm.tile_lo, kTcTW, pl0, kHalo + row, hres);
+  tc_store_pairs<PH>(sm.tile_hi, sm.tile_lo, kTcTW, pl0, kHalo + row, hres);
   {
     const LayerDesc& L0 = p.layers[A.layer0];
-    TcHaloItem it;
-    tc_halo_load<C>(it, L0, state, tabs0);
-    TcStage<PH> st;
-    tc_stage_load<C>(st, L0, state, tabs0, row, pl0);
-    tc_halo_store(it, sm);
-    if (tc_stage_store<C>(st, sm, row, pl0))
+    int off0[2];
+    tc_halo_async<C>(L0, sm, state, tabs0);
+    if (tc_stage_async<C>(L0, sm, state, tabs0, row, pl0, off0))
     {
       __syncthreads();
-      tc_stage_copy<C>(st, sm, row, pl0);
+      tc_stage_copy<C>(off0, sm, row, pl0);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
+  const u64 xx = tc_dup(x);
 
 #pragma unroll 1
   for (int li = 0; li < A.n_layers; li++)
@@ -386,9 +422,10 @@ __device__ __forceinline__ void tc_array_forward(const WaveNetKernelParams& p, c
     const int K = Ld.kernel, dil = Ld.dilation;
     const uint32_t wsel = par_z; // weight double buffer: toggles once per processed layer, like the Z barrier phase
     const float4* __restrict__ img = sm.wbuf + wsel * sm.wimg4;
-    const float4* __restrict__ vec4 = img + ((2 * K * KS + 2 * KS) * kTcTile) / 4 + pl0; // b | M | p | slopes
+    const ulonglong2* __restrict__ vec2 =
+      reinterpret_cast<const ulonglong2*>(img + ((2 * K * KS + 2 * KS) * kTcTile) / 4) + pl0; // b | M | p | slopes
 
-    asm volatile("cp.async.wait_group 0;" ::: "memory"); // this layer's B image has landed
+    asm volatile("cp.async.wait_group 0;" ::: "memory"); // this layer's B image, halo and staged taps have landed
     tc_fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -429,44 +466,61 @@ __device__ __forceinline__ void tc_array_forward(const WaveNetKernelParams& p, c
       }
       tc_commit(sm.mbar_z);
     }
-    // ---- while the tensor core works: stream in the next layer's weights, persist the tail of h_l, fetch the
-    //      next layer's halo
+    // ---- while the tensor core works: stream in the next layer's weights, persist the tail of h_l (split form:
+    //      this thread's own columns, read back from the tile)
     tc_prefetch_weights(p, sm, (gl + 1 == total_layers) ? 0 : gl + 1, wsel ^ 1u);
     if (row < Tv && row >= Tv - Ld.lookback)
     {
-      float4* __restrict__ ring = reinterpret_cast<float4*>(state + Ld.ring_off);
       const int R = Ld.ring_mask + 1;
+      float4* __restrict__ ring = const_cast<float4*>(tc_ring<C>(Ld, state));
+      const uint32_t slot = (tabs0 + (uint32_t)row) & (uint32_t)Ld.ring_mask;
 #pragma unroll
       for (int q = 0; q < PH; q++)
-        st_ring(ring + (pl0 + q) * R + ((tabs0 + (uint32_t)row) & (uint32_t)Ld.ring_mask),
-                make_float4(hres[4 * q], hres[4 * q + 1], hres[4 * q + 2], hres[4 * q + 3]));
+      {
+        st_ring(ring + (pl0 + q) * R + slot, sm.tile_hi[(pl0 + q) * kTcTW + kHalo + row]);
+        st_ring(ring + (P + pl0 + q) * R + slot, sm.tile_lo[(pl0 + q) * kTcTW + kHalo + row]);
+      }
     }
-    TcHaloItem halo_next;
-    halo_next.valid = false;
-    if (has_next)
-      tc_halo_load<C>(halo_next, Ln, state, tabs0);
     tc_mbar_wait(sm.mbar_z, par_z);
     par_z ^= 1u;
     tc_fence_after();
-    tc_halo_store(halo_next, sm); // the conv MMAs were the last readers of the old halo
+    // the conv MMAs were the last readers of the halo: fetch the next layer's
+    if (has_next)
+      tc_halo_async<C>(Ln, sm, state, tabs0);
 
     // ---- epilogue 1: z = Z + b + M c ; a = act(z) ; head += a ; a -> shared (hi / lo)
-    float a[CH];
-    tc_ld<CH>(tlane, a);
-#pragma unroll
-    for (int q = 0; q < PH; q++)
+    u64 a2[NP];
     {
-      const float4 b4 = vec4[q], m4 = vec4[4 + q];
-      a[4 * q + 0] += fmaf(m4.x, x, b4.x);
-      a[4 * q + 1] += fmaf(m4.y, x, b4.y);
-      a[4 * q + 2] += fmaf(m4.z, x, b4.z);
-      a[4 * q + 3] += fmaf(m4.w, x, b4.w);
-    }
-    apply_activation<CH>(a, Ld, reinterpret_cast<const float*>(vec4 + 12));
+      float a[CH];
+      tc_ld<CH>(tlane, a);
 #pragma unroll
-    for (int o = 0; o < CH; o++)
-      head[o] += a[o]; // model.cpp:530
-    tc_store_planes<PH>(sm.ubuf, sm.ubuf + P * kTcM, kTcM, pl0, row, a);
+      for (int q = 0; q < PH; q++)
+      {
+        const ulonglong2 b2 = vec2[q], m2 = vec2[4 + q];
+        a2[2 * q] = tc_add2(pack2(a[4 * q], a[4 * q + 1]), tc_fma2(m2.x, xx, b2.x));
+        a2[2 * q + 1] = tc_add2(pack2(a[4 * q + 2], a[4 * q + 3]), tc_fma2(m2.y, xx, b2.y));
+      }
+      if (Ld.act == KACT_FASTTANH)
+      {
+#pragma unroll
+        for (int q = 0; q < NP; q++)
+          a2[q] = tc_fast_tanh2(a2[q]);
+      }
+      else
+      {
+#pragma unroll
+        for (int q = 0; q < NP; q++)
+          unpack2(a2[q], a[2 * q], a[2 * q + 1]);
+        apply_activation<CH>(a, Ld, reinterpret_cast<const float*>(vec2 + 12));
+#pragma unroll
+        for (int q = 0; q < NP; q++)
+          a2[q] = pack2(a[2 * q], a[2 * q + 1]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NP; q++)
+      head2[q] = tc_add2(head2[q], a2[q]); // model.cpp:530
+    tc_store_pairs<PH>(sm.ubuf, sm.ubuf + P * kTcM, kTcM, pl0, row, a2);
     tc_fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -483,36 +537,42 @@ __device__ __forceinline__ void tc_array_forward(const WaveNetKernelParams& p, c
                 b_hi + (KS + s) * (kTcTile / 4), s > 0 ? 1u : 0u);
       tc_commit(sm.mbar_h);
     }
-    // ---- meanwhile: the next layer's far taps, ring part
-    TcStage<PH> stage_next;
-    if (has_next)
-      tc_stage_load<C>(stage_next, Ln, state, tabs0, row, pl0);
     tc_mbar_wait(sm.mbar_h, par_h);
     par_h ^= 1u;
     tc_fence_after();
 
     // ---- epilogue 2: h_{l+1} = h_l + p + D   (model.cpp:243,376), fp32 in registers
-    float d[CH];
-    tc_ld<CH>(tlane + 16, d);
-#pragma unroll
-    for (int q = 0; q < PH; q++)
     {
-      const float4 p4 = vec4[8 + q];
-      hres[4 * q + 0] += p4.x + d[4 * q + 0];
-      hres[4 * q + 1] += p4.y + d[4 * q + 1];
-      hres[4 * q + 2] += p4.z + d[4 * q + 2];
-      hres[4 * q + 3] += p4.w + d[4 * q + 3];
+      float d[CH];
+      tc_ld<CH>(tlane + 16, d);
+#pragma unroll
+      for (int q = 0; q < PH; q++)
+      {
+        const ulonglong2 p2 = vec2[8 + q];
+        hres[2 * q] = tc_add2(hres[2 * q], tc_add2(p2.x, pack2(d[4 * q], d[4 * q + 1])));
+        hres[2 * q + 1] = tc_add2(hres[2 * q + 1], tc_add2(p2.y, pack2(d[4 * q + 2], d[4 * q + 3])));
+      }
     }
     if (has_next)
     {
-      tc_store_planes<PH>(sm.tile_hi, sm.tile_lo, kTcTW, pl0, kHalo + row, hres);
-      if (tc_stage_store<C>(stage_next, sm, row, pl0))
+      tc_store_pairs<PH>(sm.tile_hi, sm.tile_lo, kTcTW, pl0, kHalo + row, hres);
+      // the 1x1 MMAs were the last readers of ubuf: the next layer's far taps may land there now
+      int offn[2];
+      if (tc_stage_async<C>(Ln, sm, state, tabs0, row, pl0, offn))
       {
         __syncthreads(); // the rows copied from the tile were written by other threads just now
-        tc_stage_copy<C>(stage_next, sm, row, pl0);
+        tc_stage_copy<C>(offn, sm, row, pl0);
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
+#pragma unroll
+  for (int q = 0; q < NP; q++)
+    unpack2(head2[q], head[2 * q], head[2 * q + 1]);
+  float hres_f[CH];
+#pragma unroll
+  for (int q = 0; q < NP; q++)
+    unpack2(hres[q], hres_f[2 * q], hres_f[2 * q + 1]);
 
   // ---- head rechannel (kernel size 1; model.cpp:548): partial sums over this thread's channels, the partner
   //      thread of the row supplies the other half through shared memory
@@ -554,7 +614,8 @@ __device__ __forceinline__ void tc_array_forward(const WaveNetKernelParams& p, c
     }
 #pragma unroll
     for (int q = 0; q < PH; q++)
-      sm.xch[(pl0 + q) * kTcM + row] = make_float4(hres[4 * q], hres[4 * q + 1], hres[4 * q + 2], hres[4 * q + 3]);
+      sm.xch[(pl0 + q) * kTcM + row] =
+        make_float4(hres_f[4 * q], hres_f[4 * q + 1], hres_f[4 * q + 2], hres_f[4 * q + 3]);
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < PHN; q++)
