@@ -210,6 +210,57 @@ __device__ __forceinline__ void add2_acc(u64& acc, const u64 v)
   asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(v));
 }
 
+// ---- packed fp32 pair arithmetic for the element-wise epilogue math (halves its issue slots) ----
+__device__ __forceinline__ u64 tc_fma2(u64 a, u64 b, u64 c)
+{
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 tc_mul2(u64 a, u64 b)
+{
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 tc_add2(u64 a, u64 b)
+{
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 tc_dup(float v)
+{
+  return pack2(v, v);
+}
+constexpr u64 kTcAbsMask = 0x7FFFFFFF7FFFFFFFull;
+// x = hi + lo with hi on 11 significant bits (exactly a TF32 number), Veltkamp's splitting: 4 packed instructions
+// per pair instead of 6 integer / float ones
+__device__ __forceinline__ void tc_split2(u64 x, u64& hi, u64& lo)
+{
+  const u64 m1 = tc_dup(-1.0f);
+  const u64 t = tc_mul2(x, tc_dup(8193.0f)); // 2^13 + 1
+  const u64 d = tc_fma2(m1, x, t); // t - x
+  hi = tc_fma2(m1, d, t); // t - (t - x)
+  lo = tc_fma2(m1, hi, x); // x - hi, exact
+}
+// the reference's rational fast_tanh (activations.h:91-98) on a pair
+__device__ __forceinline__ u64 tc_fast_tanh2(u64 x)
+{
+  const u64 ax = x & kTcAbsMask;
+  const u64 x2 = tc_mul2(x, x);
+  const u64 c0 = tc_dup(2.45550750702956f);
+  const u64 t1 = tc_fma2(tc_dup(0.821226666969744f), ax, tc_dup(0.893229853513558f));
+  const u64 t0 = tc_fma2(c0, ax, c0);
+  const u64 num = tc_mul2(x, tc_fma2(t1, x2, t0));
+  const u64 s = tc_fma2(tc_dup(0.814642734961073f), tc_mul2(x, ax), x) & kTcAbsMask;
+  const u64 d0 = tc_dup(2.44506634652299f);
+  const u64 den = tc_fma2(tc_add2(x2, d0), s, d0);
+  float dl, dh;
+  unpack2(den, dl, dh);
+  return tc_mul2(num, pack2(rcp_approx(dl), rcp_approx(dh)));
+}
+
 // acc[o] += w_row[o] * x for C outputs, two per FFMA2 (x broadcast to both halves).
 template <int C>
 __device__ __forceinline__ void axpy_row(u64 (&acc)[C / 2], const float* __restrict__ w_row, const float x)
@@ -422,6 +473,18 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
 #pragma unroll
     for (int j = 0; j < S; j++)
     {
+      if (Ld.act == KACT_FASTTANH)
+      {
+        // the benchmark regime: the rational fast_tanh on packed pairs (7 instead of 11 issue slots per element)
+#pragma unroll
+        for (int q = 0; q < C / 2; q++)
+        {
+          acc[j][q] = tc_fast_tanh2(acc[j][q]);
+          add2_acc(head[j][q], acc[j][q]); // model.cpp:530
+          unpack2(acc[j][q], a[j][2 * q], a[j][2 * q + 1]);
+        }
+        continue;
+      }
 #pragma unroll
       for (int q = 0; q < C / 2; q++)
         unpack2(acc[j][q], a[j][2 * q], a[j][2 * q + 1]);
