@@ -186,6 +186,11 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_kernel(const LstmKernelPara
       p.state[(size_t)stream * p.state_stride + i] = sstate[i * kLstmThreads + tid];
 }
 
+} // namespace
+#include "lstm_group.cuh"
+namespace
+{
+
 // =================================================================================================
 // Linear (FIR) kernel, direct form (NAM/linear.cpp:168-199): y[t] = bias + sum_j w[j] x[t-j]
 // One CTA per (stream, tile of frames); the tile plus RF-1 history samples are staged in shared
@@ -677,6 +682,37 @@ void launch_lstm(nam_b200_model* m, const float* d_in, float* d_out, int batch, 
   kp.hidden = ls.hidden;
   kp.fast_tanh = m->fast_tanh_runtime;
   const int H = ls.hidden;
+  if (H <= kLstmGroupMaxHidden && ls.num_layers <= kLstmGroupMaxLayers)
+  {
+    // a group of G lanes per stream (lstm_group.cuh)
+    const int G = H <= 4 ? 4 : (H <= 8 ? 8 : (H <= 16 ? 16 : 32));
+    const int spc = kLstmGroupThreads / G;
+    size_t w_floats = 0;
+    for (int l = 0; l < ls.num_layers; l++)
+    {
+      const int W = ((l == 0) ? ls.input_size : H) + H;
+      w_floats += (size_t)4 * H * (W | 1) + 4 * H;
+    }
+    const size_t smem_g = (w_floats + H + 1 + (size_t)2 * spc * (kLstmGroupChunk + 1)) * sizeof(float);
+    if (smem_g <= 227 * 1024)
+    {
+      const int grid_g = (batch + spc - 1) / spc;
+      auto launch = [&](auto kern) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        kern<<<grid_g, kLstmGroupThreads, smem_g, st>>>(kp);
+      };
+      switch (G)
+      {
+        case 4: launch(lstm_group_kernel<4>); break;
+        case 8: launch(lstm_group_kernel<8>); break;
+        case 16: launch(lstm_group_kernel<16>); break;
+        default: launch(lstm_group_kernel<32>); break;
+      }
+      CUDA_CHECK(cudaGetLastError());
+      m->launches++;
+      return;
+    }
+  }
   const size_t smem = (((m->n_weight_floats + 3) & ~(size_t)3) + (size_t)ls.num_layers * 2 * H * kLstmThreads
                        + (size_t)4 * H * kLstmThreads + (size_t)2 * kLstmThreads * (kLstmChunk + 1))
                       * sizeof(float);

@@ -207,9 +207,11 @@ def test_lstm_batch_and_runtime_fast_switch():
         assert np.max(np.abs(got - ref)) <= TOL
 
 
-def test_lstm_two_layers_random():
+@pytest.mark.parametrize("H,nl", [(12, 2), (3, 1), (8, 3), (16, 1), (24, 2), (40, 1), (64, 2), (70, 1)])
+def test_lstm_two_layers_random(H, nl):
+    """Hidden sizes across the lane-group widths of lstm_group.cuh (4 / 8 / 16 / 32 lanes per stream, two units per
+    lane above 32) and, at 70, the thread-per-stream fallback; 1-3 layers; a batch that does not fill the last CTA."""
     rng = np.random.default_rng(4)
-    H, nl = 12, 2
     n = sum(4 * H * ((1 if l == 0 else H) + H) + 4 * H + 2 * H for l in range(nl)) + H + 1
     nam = {"version": "0.5.4", "architecture": "LSTM", "config": {"input_size": 1, "hidden_size": H, "num_layers": nl},
            "weights": [float(v) for v in rng.uniform(-0.4, 0.4, n)], "sample_rate": 48000}
