@@ -401,9 +401,9 @@ def run_b200(args) -> None:
     if world == 1 and not args.no_secondary and args.model == MODEL:
         secondary = {}
 
-        def quick(name, model_name, b, frames, steps=8):
+        def quick(name, model_name, b, frames, steps=8, **kw):
             try:
-                m2 = nb.get_dsp(fx.load_model(model_name), batch=b, device=local_rank, fast_tanh=fast)
+                m2 = nb.get_dsp(fx.load_model(model_name), batch=b, device=local_rank, fast_tanh=fast, **kw)
                 m2.Reset(48000.0, frames)
                 xi = torch.from_numpy(fx.synthetic_batch(b, frames, seed=7)).cuda()
                 yo = torch.empty_like(xi)
@@ -425,7 +425,11 @@ def run_b200(args) -> None:
             except Exception as exc:  # a secondary workload must never cost the headline line
                 secondary[name] = {"error": str(exc)[:200]}
 
-        quick("wavenet_a1_standard_batch1", MODEL, 1, 4096)
+        quick("wavenet_a1_standard_batch1", MODEL, 1, 4096, steps=32)
+        quick("wavenet_a1_standard_batch1_wavefront_tiles", MODEL, 1, 4096, steps=32, tile_mode=1)
+        quick("wavenet_a1_standard_batch1_one_96000_frame_call", MODEL, 1, 96000, steps=16)
+        quick("wavenet_a1_standard_batch1_one_96000_frame_call_tile512", MODEL, 1, 96000, steps=16, kernel_geometry=2)
+        quick("wavenet_a1_standard_batch16", MODEL, 16, 4096, steps=16)
         quick("wavenet_a1_standard_batch256", MODEL, 256, 4096)
         quick("wavenet_a1_standard_batch4096_64frame_calls", MODEL, 4096, 64, steps=32)
         quick("wavenet_a1_standard_batch4096_128frame_calls", MODEL, 4096, 128, steps=32)

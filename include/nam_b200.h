@@ -61,7 +61,11 @@ typedef struct nam_b200_options
                               2 = FP32 FFMA2 kernel, 256-thread CTAs (tile 512); 3 = tensor-core kernel (tcgen05,
                               3xTF32 split, tile 128); 4 = the general kernel (all WaveNet options, one CTA per stream,
                               thread per frame) that otherwise serves only models outside the fused families */
-  int32_t reserved[7];
+  int32_t tile_mode; /* few streams x long calls (batch x tiles <= resident CTAs): 0 = library default: lock-step
+                        tile-parallel mode (every (stream, tile) its own CTA, all tiles advancing layer by layer; a
+                        history buffer of up to ~150 MB is allocated by reset()); 1 = wavefront tile-parallel mode (no
+                        buffer, tile c one layer behind tile c-1); 2 = never: one CTA walks a stream's tiles in turn */
+  int32_t reserved[6];
 } nam_b200_options;
 
 typedef struct nam_b200_info

@@ -21,7 +21,8 @@ class Options(C.Structure):
         ("prewarm_on_reset", C.c_int32),
         ("ctas_per_sm", C.c_int32),
         ("kernel_geometry", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("tile_mode", C.c_int32),
+        ("reserved", C.c_int32 * 6),
     ]
 
 

@@ -336,6 +336,10 @@ struct nam_b200_model
   int variant = 0;
   int wn_ctas_per_sm = 0; // resident CTAs per SM of the fused kernel (occupancy query, cached)
   int* d_tile_flags = nullptr; // tile-parallel mode hand-over counters, one per resident CTA
+  size_t tile_flags_capacity = 0;
+  float* d_hist = nullptr; // lock-step tile-parallel mode: per-call history buffer (WaveNetKernelParams::hist)
+  size_t hist_floats = 0;
+  int wn_ctas_ls[2] = {0, 0}; // resident CTAs per SM of the lock-step kernels (geometries 0 / 1)
   int wn_ctas_short[2] = {0, 0}; // same for the short-call (multi-stream tile) geometries 2 / 3
   int wn_geometry = 1; // 0 / 1: index into kWnGeom (FFMA kernel); 2: tensor-core kernel (wavenet_tc.cuh)
   float* d_tc_blob = nullptr; // per-layer B-operand images of the tensor-core kernel
@@ -380,6 +384,8 @@ struct nam_b200_model
       cudaFree(d_glayers);
     if (d_tile_flags)
       cudaFree(d_tile_flags);
+    if (d_hist)
+      cudaFree(d_hist);
     if (d_state)
       cudaFree(d_state);
     if (d_state_tmp)
@@ -453,6 +459,54 @@ int occupancy_wavenet_variant(size_t smem)
   return n > 0 ? n : 1;
 }
 
+// lock-step tile-parallel kernels (LS = true): geometries 0 / 1 only
+template <int C0, int C1, int NT, int MINB, int LQ>
+void launch_wavenet_ls_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem, cudaStream_t st)
+{
+  auto kern = wavenet_fused_kernel<C0, C1, kWnS, NT, MINB, LQ, true>;
+  static bool configured[64] = {false};
+  if (!configured[m->device & 63])
+  {
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[m->device & 63] = true;
+  }
+  kern<<<grid, NT, smem, st>>>(kp);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+template <int C0, int C1, int NT, int MINB, int LQ>
+int occupancy_wavenet_ls_variant(size_t smem)
+{
+  auto kern = wavenet_fused_kernel<C0, C1, kWnS, NT, MINB, LQ, true>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, NT, smem) != cudaSuccess)
+    return 1;
+  return n > 0 ? n : 1;
+}
+
+#define WN_LS_CASE(C0, C1, FN, ...)                                                                                  \
+  case (C0) * 100 + (C1): return geom == 0 ? FN<C0, C1, 128, 3, 8>(__VA_ARGS__) : FN<C0, C1, 256, 2, 9>(__VA_ARGS__);
+
+#define WN_LS_DISPATCH(FN, ...)                                                                                      \
+  switch (c0 * 100 + c1)                                                                                             \
+  {                                                                                                                  \
+    WN_LS_CASE(4, 0, FN, __VA_ARGS__)                                                                                \
+    WN_LS_CASE(8, 0, FN, __VA_ARGS__)                                                                                \
+    WN_LS_CASE(16, 0, FN, __VA_ARGS__)                                                                               \
+    WN_LS_CASE(4, 4, FN, __VA_ARGS__)                                                                                \
+    WN_LS_CASE(4, 8, FN, __VA_ARGS__)                                                                                \
+    WN_LS_CASE(4, 16, FN, __VA_ARGS__)                                                                               \
+    WN_LS_CASE(8, 4, FN, __VA_ARGS__)                                                                                \
+    WN_LS_CASE(8, 8, FN, __VA_ARGS__)                                                                                \
+    WN_LS_CASE(8, 16, FN, __VA_ARGS__)                                                                               \
+    WN_LS_CASE(16, 4, FN, __VA_ARGS__)                                                                               \
+    WN_LS_CASE(16, 8, FN, __VA_ARGS__)                                                                               \
+    WN_LS_CASE(16, 16, FN, __VA_ARGS__)                                                                              \
+    default: throw std::runtime_error("no fused WaveNet kernel for channel pair " + std::to_string(c0) + "/"         \
+                                      + std::to_string(c1));                                                         \
+  }
+
 #define WN_CASE(C0, C1, FN, ...)                                                                                     \
   case (C0) * 100 + (C1):                                                                                            \
     return geom == 0 ? FN<C0, C1, 128, 3, 8>(__VA_ARGS__)                                                            \
@@ -486,6 +540,107 @@ void launch_wavenet_dispatch(int c0, int c1, int geom, nam_b200_model* m, const 
 int occupancy_wavenet_dispatch(int c0, int c1, int geom, size_t smem)
 {
   WN_DISPATCH(occupancy_wavenet_variant, smem)
+}
+
+void launch_wavenet_ls_dispatch(int c0, int c1, int geom, nam_b200_model* m, const WaveNetKernelParams& kp, int grid,
+                                size_t smem, cudaStream_t st)
+{
+  WN_LS_DISPATCH(launch_wavenet_ls_variant, m, kp, grid, smem, st)
+}
+int occupancy_wavenet_ls_dispatch(int c0, int c1, int geom, size_t smem)
+{
+  WN_LS_DISPATCH(occupancy_wavenet_ls_variant, smem)
+}
+
+size_t wavenet_smem_bytes(const WaveNetPlan& plan, int geom);
+
+// ---- lock-step tile-parallel mode: geometry choice and history buffer -----------------------------------------------
+// planes (4 channels each) of hist per stream: every layer's input, plus the head accumulator of a convolutional head
+int wavenet_hist_planes(const WaveNetPlan& plan, int* plane0 = nullptr)
+{
+  int planes = 0;
+  for (int a = 0; a < plan.n_arrays; a++)
+  {
+    if (plane0)
+      plane0[a] = planes;
+    planes += (plan.arrays[a].n_layers + (plan.arrays[a].head_kernel > 1 ? 1 : 0)) * (plan.cp[a] / 4);
+  }
+  return planes;
+}
+
+// resident CTAs of the lock-step kernel of geometry g (0 / 1) on the whole device; 0 if it cannot run
+long wavenet_ls_capacity(nam_b200_model* m, int g)
+{
+  const WaveNetPlan& plan = m->plan;
+  const size_t smem = wavenet_smem_bytes(plan, g);
+  if (smem > 227 * 1024)
+    return 0;
+  if (m->wn_ctas_ls[g] <= 0)
+    m->wn_ctas_ls[g] = occupancy_wavenet_ls_dispatch(plan.cp[0], plan.n_arrays > 1 ? plan.cp[1] : 0, g, smem);
+  return (long)m->wn_ctas_ls[g] * m->sm_count;
+}
+
+// The geometry the lock-step mode would use for (batch, n_frames): the smallest tile whose CTAs are all co-resident
+// (more, shorter layer-steps in flight), -1 if none.  kernel_geometry 1 / 2 pins the geometry.
+int wavenet_ls_geometry(nam_b200_model* m, int batch, int n_frames, int* tiles_out)
+{
+  if (m->opts.tile_mode != 0 || m->wn_geometry > 1 || m->use_generic)
+    return -1;
+  for (int g = 0; g < 2; g++)
+  {
+    if (m->opts.kernel_geometry != 0 && g != m->wn_geometry)
+      continue;
+    const int tf = kWnS * kWnGeom[g].nt;
+    const int tiles = (n_frames + tf - 1) / tf;
+    const long cap = wavenet_ls_capacity(m, g);
+    if (tiles >= 2 && (long)batch * tiles <= cap)
+    {
+      *tiles_out = tiles;
+      return g;
+    }
+  }
+  return -1;
+}
+
+// reset(): size the history buffer and the flags for every (batch <= max_batch, n_frames <= max_frames) the
+// lock-step mode can serve, so that process() never allocates
+void ensure_hist(nam_b200_model* m)
+{
+  if (m->spec.arch != Arch::WaveNet || m->use_generic || m->wn_geometry > 1 || m->opts.tile_mode != 0)
+    return;
+  const int planes = wavenet_hist_planes(m->plan);
+  size_t need = 0, need_flags = 0;
+  for (int g = 0; g < 2; g++)
+  {
+    if (m->opts.kernel_geometry != 0 && g != m->wn_geometry)
+      continue;
+    const int tf = kWnS * kWnGeom[g].nt;
+    const long tiles_max = (m->max_frames + tf - 1) / tf;
+    const long cap = wavenet_ls_capacity(m, g);
+    if (tiles_max < 2 || cap < 2)
+      continue;
+    const long ctas = std::min<long>((long)m->opts.max_batch * tiles_max, cap);
+    need = std::max(need, (size_t)ctas * tf * planes * 4);
+    need_flags = std::max(need_flags, (size_t)ctas);
+  }
+  if (need > m->hist_floats)
+  {
+    if (m->d_hist)
+      cudaFree(m->d_hist);
+    m->d_hist = nullptr;
+    m->hist_floats = 0;
+    CUDA_CHECK(cudaMalloc(&m->d_hist, need * sizeof(float)));
+    m->hist_floats = need;
+  }
+  if (need_flags > m->tile_flags_capacity)
+  {
+    if (m->d_tile_flags)
+      cudaFree(m->d_tile_flags);
+    m->d_tile_flags = nullptr;
+    m->tile_flags_capacity = 0;
+    CUDA_CHECK(cudaMalloc(&m->d_tile_flags, need_flags * sizeof(int)));
+    m->tile_flags_capacity = need_flags;
+  }
 }
 
 size_t wavenet_smem_bytes(const WaveNetPlan& plan, int geom)
@@ -637,16 +792,51 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
   if (m->wn_ctas_per_sm <= 0)
     m->wn_ctas_per_sm = m->opts.ctas_per_sm > 0 ? m->opts.ctas_per_sm : occupancy_wavenet_dispatch(c0, c1, geom, smem);
   const int per_sm = m->wn_ctas_per_sm;
-  // Few streams, long calls: one CTA per (stream, tile), tiles of a stream handing their ring columns over layer
-  // by layer (a wavefront over tiles x layers instead of a serial walk).  All CTAs must be co-resident.
+  // Few streams, long calls, lock-step: one CTA per (stream, tile), all tiles advancing layer by layer together
+  // (WaveNetKernelParams::hist).  All CTAs must be co-resident.
+  {
+    int tiles = 0;
+    const int g = wavenet_ls_geometry(m, batch, n_frames, &tiles);
+    if (g >= 0)
+    {
+      const int tf = kWnS * kWnGeom[g].nt;
+      int plane0[kMaxArrays] = {0, 0, 0, 0};
+      const int planes = wavenet_hist_planes(plan, plane0);
+      const size_t per_stream = (size_t)planes * tiles * tf * 4;
+      if ((size_t)batch * per_stream <= m->hist_floats && (size_t)batch * tiles <= m->tile_flags_capacity)
+      {
+        CUDA_CHECK(cudaMemsetAsync(m->d_tile_flags, 0, (size_t)batch * tiles * sizeof(int), st));
+        kp.tile_flags = m->d_tile_flags;
+        kp.tiles_per_stream = tiles;
+        kp.hist = m->d_hist;
+        kp.hist_stride = (long)per_stream;
+        kp.hist_cols = tiles * tf;
+        for (int a = 0; a < kMaxArrays; a++)
+          kp.hist_plane0[a] = plane0[a];
+        launch_wavenet_ls_dispatch(c0, c1, g, m, kp, batch * tiles, wavenet_smem_bytes(plan, g), st);
+        m->launches++;
+        return;
+      }
+    }
+  }
+  // The same as a wavefront (tile_mode 1): a tile hands its ring columns to its successor layer by layer, so tile c
+  // runs one layer behind tile c-1 -- (tiles + layers) layer-steps per call, but no history buffer.
+  if (m->opts.tile_mode == 1)
   {
     const int tile_frames = kWnS * kWnGeom[geom].nt;
     const int tiles = (n_frames + tile_frames - 1) / tile_frames;
     const long capacity = (long)per_sm * m->sm_count;
     if (tiles >= 2 && (long)batch * tiles <= capacity && 2L * batch <= capacity)
     {
-      if (!m->d_tile_flags)
+      if ((size_t)capacity > m->tile_flags_capacity)
+      {
+        if (m->d_tile_flags)
+          cudaFree(m->d_tile_flags);
+        m->d_tile_flags = nullptr;
+        m->tile_flags_capacity = 0;
         CUDA_CHECK(cudaMalloc(&m->d_tile_flags, (size_t)capacity * sizeof(int)));
+        m->tile_flags_capacity = (size_t)capacity;
+      }
       CUDA_CHECK(cudaMemsetAsync(m->d_tile_flags, 0, (size_t)batch * tiles * sizeof(int), st));
       kp.tile_flags = m->d_tile_flags;
       kp.tiles_per_stream = tiles;
@@ -1352,6 +1542,7 @@ int nam_b200_reset(nam_b200_model* m, double sample_rate, int max_frames)
     m->max_frames = max_frames;
     ensure_staging(m, (size_t)m->opts.max_batch * max_frames);
     ensure_pinned(m, (size_t)2 * max_frames);
+    ensure_hist(m);
     init_state(m);
     m->is_reset = true;
     CUDA_CHECK(cudaEventRecord(m->ev0, m->stream));

@@ -71,6 +71,16 @@ struct WaveNetKernelParams
   // (tile, layer) instead of a serial walk.  tile_flags == nullptr: the classic mode.
   int* tile_flags;
   int tiles_per_stream;
+  // Lock-step variant of the tile-parallel mode (wavenet_fused_kernel<..., LS = true>): every tile writes ALL columns of
+  // every layer's input into a per-call history buffer hist[stream][plane][hist_cols][4 floats] the moment it has
+  // produced them and publishes the step right away, so tile c can start layer l as soon as tiles c-1 .. c-m have
+  // finished layer l-1 (m = tiles the look-back spans): all tiles advance layer by layer together and a call costs
+  // ~(layers) layer-steps instead of (tiles + layers).  The rings are only read during the call (history from before
+  // the call) and rewritten from hist at the very end, once every tile of the stream has finished.
+  float* hist; // [batch][hist_stride]
+  long hist_stride; // floats per stream = total planes * hist_cols * 4
+  int hist_cols; // tiles_per_stream * frames per tile
+  int hist_plane0[kMaxArrays]; // first plane of array a: its layers' inputs, P planes each, then its head-conv input
   // tensor-core variant (wavenet_tc.cuh): per-layer shared-memory images of the B operands
   const float* tc_blob;
   int tc_off[kMaxLayers]; // float offset of layer i's image in tc_blob

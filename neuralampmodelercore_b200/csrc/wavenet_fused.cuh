@@ -157,6 +157,7 @@ struct TileSync
 {
   const int* prev; // flag of the same stream's previous tile (nullptr: nothing to wait for)
   int* mine; // this tile's flag (nullptr: classic mode)
+  int tile_i; // index of this tile inside its stream (lock-step mode: tiles tile_i-1, tile_i-2, ... are polled)
 };
 __device__ __forceinline__ void tile_wait(const TileSync& ts, int step)
 {
@@ -182,6 +183,29 @@ __device__ __forceinline__ void tile_publish(const TileSync& ts, int step)
     if (threadIdx.x == 0)
       asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ts.mine), "r"(step + 1) : "memory");
   }
+}
+
+// ---- lock-step hand-over (WaveNetKernelParams::hist) ------------------------------------------
+// "My columns of step `step` are in hist" (flag = step + 1), then wait until the `m` previous tiles of the stream
+// have published the same step.  The first barrier also orders this CTA's own shared-tile writes before the reads
+// that follow; lanes 0..m-1 poll one predecessor each.
+constexpr int kLsFinalStep = 1 << 20;
+__device__ __forceinline__ void ls_publish_wait(const TileSync& ts, const int step, const int m)
+{
+  __threadfence(); // this thread's hist stores are visible device-wide
+  __syncthreads();
+  if (threadIdx.x == 0)
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ts.mine), "r"(step + 1) : "memory");
+  for (int k = threadIdx.x; k < m; k += blockDim.x)
+  {
+    const int* f = ts.mine - 1 - k;
+    int v;
+    do
+    {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    } while (v <= step);
+  }
+  __syncthreads();
 }
 
 // ---- packed fp32 pairs ------------------------------------------------------------------------
@@ -286,11 +310,14 @@ __device__ __forceinline__ void axpy_row(u64 (&acc)[C / 2], const float* __restr
 //   state[j], Tv[j]: ring base and number of valid frames of the stream that owns this thread's j-th frame
 //          (Tv[j] == 0 for a slot beyond the batch); state0 / stream0 / n_streams locate the other sub-tiles' rings
 //          for the halo fill.
-template <int CIN, int C, int HOUT, int S, int NT, int LQ>
+//   LS   : lock-step tile-parallel mode (Q == 1 only): hist_a = this stream's history buffer at the array's first
+//          plane, t0 = call-relative first frame of the tile (see WaveNetKernelParams::hist)
+template <int CIN, int C, int HOUT, int S, int NT, int LQ, bool LS>
 __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, const ArrayDesc& A,
                                               const float* __restrict__ sw, float4* __restrict__ tile,
                                               float* const (&state)[S], const int stream0, const uint32_t tabs0,
-                                              const TileSync& ts, const int step0, const int (&Tv)[S],
+                                              const TileSync& ts, const int step0, float4* const hist_a, const int t0,
+                                              const int (&Tv)[S],
                                               const float (&hin)[S][CIN], const float (&cond)[S],
                                               u64 (&head)[S][C / 2], float (&hout)[S][C], float (&headout)[S][HOUT])
 {
@@ -301,7 +328,9 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
   constexpr int TW = Q * SW; // columns per plane in the shared tile
   constexpr int P = C / 4; // planes
   static_assert(Q >= 1 && Q * FQ == T && (Q == 1 || FQ <= NT), "sub-tile geometry");
+  static_assert(!LS || Q == 1, "lock-step mode: one stream per tile");
   const int tid = threadIdx.x;
+  const int NC = p.hist_cols; // LS: columns per plane of hist
   // this thread's j-th frame: sub-tile, frame inside it, tile column
   int fj[S], colj[S];
 #pragma unroll
@@ -336,6 +365,9 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
       unpack2(h[2 * pl], v.x, v.y);
       unpack2(h[2 * pl + 1], v.z, v.w);
       tile[pl * TW + colj[j]] = v;
+      if constexpr (LS)
+        if (fj[j] < Tv[j])
+          st_ring(hist_a + (size_t)pl * NC + t0 + fj[j], v); // layer 0's input columns
     }
   }
 
@@ -359,10 +391,26 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
       ring[j] = reinterpret_cast<float4*>(state[Q == 1 ? 0 : j] + Ld.ring_off);
     const int halo = (lookback <= kHalo) ? lookback : 0; // (a 64-column halo for the longer look-backs costs more than it saves: measured)
 
-    tile_wait(ts, step0 + li); // tile-parallel mode: the previous tile's columns of this layer are in the ring
+    // LS: this layer's input columns [call start, tile start) come from hist (written by the previous tiles during this
+    // call), older ones from the ring
+    const float4* const hist_l = LS ? hist_a + (size_t)li * P * NC : nullptr;
+    if constexpr (LS)
+      ls_publish_wait(ts, step0 + li, min(ts.tile_i, (lookback + FQ - 1) >> LQ));
+    else
+      tile_wait(ts, step0 + li); // tile-parallel mode: the previous tile's columns of this layer are in the ring
 
     // ---- phase 0: small-dilation layers pull their history [t0-L, t0) into the halo
-    if constexpr (Q == 1)
+    if constexpr (LS)
+    {
+      for (int idx = tid; idx < halo * P; idx += NT)
+      {
+        const int pl = idx / halo, col = idx - pl * halo;
+        const int a = t0 - halo + col;
+        tile[pl * TW + kHalo - halo + col] = ld_ring(
+          a >= 0 ? hist_l + (size_t)pl * NC + a : ring[0] + pl * R + ((tabs0 - (uint32_t)halo + (uint32_t)col) & ring_mask));
+      }
+    }
+    else if constexpr (Q == 1)
     {
       for (int idx = tid; idx < halo * P; idx += NT)
       {
@@ -382,7 +430,8 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
           ld_ring(rq + pl * R + ((tabs0 - (uint32_t)halo + (uint32_t)col) & ring_mask));
       }
     }
-    __syncthreads(); // B0: tile columns (previous layer's phase 2) + halo are visible
+    if (!LS || halo > 0) // (LS: the hand-over's barrier already made the tile columns visible)
+      __syncthreads(); // B0: tile columns (previous layer's phase 2) + halo are visible
 
     // ---- phase 1: z = b + M c + sum_k W_k h[t-(K-1-k)d] ; a = act(z) ; head += a
     u64 acc[S][C / 2];
@@ -434,6 +483,8 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
       const float4* sp[S];
       uint32_t gi[S];
       bool glob[S];
+      const float4* gp[S]; // LS: the column in hist (this call) or in the ring (before it), and its plane stride
+      int gs[S];
 #pragma unroll
       for (int j = 0; j < S; j++)
       {
@@ -441,6 +492,12 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
         glob[j] = rel < -halo;
         sp[j] = tile + colj[j] - off;
         gi[j] = (tabs0 + (uint32_t)rel) & ring_mask;
+        if constexpr (LS)
+        {
+          const bool in_call = t0 + rel >= 0;
+          gp[j] = in_call ? hist_l + (t0 + rel) : ring[j] + gi[j];
+          gs[j] = in_call ? NC : R;
+        }
       }
 #pragma unroll kPlUnroll
       for (int pl = 0; pl < P; pl++)
@@ -449,7 +506,12 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
 #pragma unroll
         for (int j = 0; j < S; j++)
         {
-          if (glob[j])
+          if constexpr (LS)
+          {
+            xq[j] = glob[j] ? ld_ring(gp[j]) : *sp[j];
+            gp[j] += gs[j];
+          }
+          else if (glob[j])
             xq[j] = ld_ring(ring[j] + gi[j]);
           else
             xq[j] = *sp[j];
@@ -501,7 +563,7 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
 #pragma unroll
     for (int j = 0; j < S; j++)
     {
-      const bool keep = (fj[j] < Tv[j]) && (fj[j] >= Tv[j] - lookback);
+      const bool keep = !LS && (fj[j] < Tv[j]) && (fj[j] >= Tv[j] - lookback); // (LS: the rings are rewritten at the end)
 #pragma unroll
       for (int pl = 0; pl < P; pl++)
       {
@@ -533,6 +595,9 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
           unpack2(hn[j][2 * pl], v.x, v.y);
           unpack2(hn[j][2 * pl + 1], v.z, v.w);
           tile[pl * TW + colj[j]] = v;
+          if constexpr (LS)
+            if (fj[j] < Tv[j])
+              st_ring(hist_a + ((size_t)(li + 1) * P + pl) * NC + t0 + fj[j], v); // the next layer's input columns
         }
       }
       else
@@ -542,7 +607,8 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
           unpack2(hn[j][q], hout[j][2 * q], hout[j][2 * q + 1]);
       }
     }
-    tile_publish(ts, step0 + li);
+    if constexpr (!LS)
+      tile_publish(ts, step0 + li);
   }
 
   const float* __restrict__ wh = sw + A.head_off;
@@ -554,7 +620,9 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
     const int HK = A.head_kernel, hdil = A.head_dilation, HL = (HK - 1) * hdil;
     const uint32_t hmask = (uint32_t)A.head_ring_mask;
     const int HR = A.head_ring_mask + 1;
-    tile_wait(ts, step0 + A.n_layers);
+    float4* const hist_h = LS ? hist_a + (size_t)A.n_layers * P * NC : nullptr; // LS: the head accumulator's columns
+    if constexpr (!LS)
+      tile_wait(ts, step0 + A.n_layers);
     float4* hring[S];
 #pragma unroll
     for (int j = 0; j < S; j++)
@@ -569,20 +637,37 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
         unpack2(head[j][2 * pl], v.x, v.y);
         unpack2(head[j][2 * pl + 1], v.z, v.w);
         tile[pl * TW + colj[j]] = v;
+        if constexpr (LS)
+          if (fj[j] < Tv[j])
+            st_ring(hist_h + (size_t)pl * NC + t0 + fj[j], v);
       }
-    for (int idx = tid; idx < Q * P * HL; idx += NT)
+    if constexpr (LS)
     {
-      const int col = idx % HL, t2 = idx / HL;
-      const int pl = t2 % P, q = t2 / P;
-      const float4* __restrict__ rq =
-        (Q == 1) ? hring[0] : reinterpret_cast<const float4*>(sub_state(q) + A.head_ring_off);
-      tile[pl * TW + q * SW + kHalo - HL + col] = ld_ring(rq + pl * HR + ((tabs0 - (uint32_t)HL + (uint32_t)col) & hmask));
+      ls_publish_wait(ts, step0 + A.n_layers, min(ts.tile_i, (HL + FQ - 1) >> LQ));
+      for (int idx = tid; idx < P * HL; idx += NT)
+      {
+        const int pl = idx / HL, col = idx - pl * HL;
+        const int a = t0 - HL + col;
+        tile[pl * TW + kHalo - HL + col] =
+          ld_ring(a >= 0 ? hist_h + (size_t)pl * NC + a : hring[0] + pl * HR + ((tabs0 - (uint32_t)HL + (uint32_t)col) & hmask));
+      }
+    }
+    else
+    {
+      for (int idx = tid; idx < Q * P * HL; idx += NT)
+      {
+        const int col = idx % HL, t2 = idx / HL;
+        const int pl = t2 % P, q = t2 / P;
+        const float4* __restrict__ rq =
+          (Q == 1) ? hring[0] : reinterpret_cast<const float4*>(sub_state(q) + A.head_ring_off);
+        tile[pl * TW + q * SW + kHalo - HL + col] = ld_ring(rq + pl * HR + ((tabs0 - (uint32_t)HL + (uint32_t)col) & hmask));
+      }
     }
     __syncthreads(); // accumulator columns + halo visible; all ring reads done before the ring is rewritten
 #pragma unroll
     for (int j = 0; j < S; j++)
     {
-      if ((fj[j] < Tv[j]) && (fj[j] >= Tv[j] - HL))
+      if (!LS && (fj[j] < Tv[j]) && (fj[j] >= Tv[j] - HL))
       {
 #pragma unroll
         for (int pl = 0; pl < P; pl++)
@@ -616,7 +701,8 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
       for (int ho = 0; ho < HOUT; ho++)
         headout[j][ho] = out[ho];
     }
-    tile_publish(ts, step0 + A.n_layers);
+    if constexpr (!LS)
+      tile_publish(ts, step0 + A.n_layers);
     __syncthreads(); // the next array / tile rewrites the tile columns
     return;
   }
@@ -657,10 +743,51 @@ __device__ __forceinline__ void array_forward(const WaveNetKernelParams& p, cons
   }
 }
 
+// Lock-step mode epilogue: the stream's rings take the last `lookback` columns of the call from hist (every tile
+// copies the columns it owns).  Runs after every tile of the stream has finished reading the rings.
+template <int C, int S, int NT, int LQ>
+__device__ __forceinline__ void ls_write_back(const WaveNetKernelParams& p, const ArrayDesc& A, float* state,
+                                              const float4* hist_a, const int t0, const uint32_t tabs0, const int tv)
+{
+  constexpr int P = C / 4;
+  const int NC = p.hist_cols;
+#pragma unroll 1
+  for (int li = 0; li <= A.n_layers; li++)
+  {
+    int lookback, mask, off;
+    if (li < A.n_layers)
+    {
+      const LayerDesc& Ld = p.layers[A.layer0 + li];
+      lookback = Ld.lookback, mask = Ld.ring_mask, off = Ld.ring_off;
+    }
+    else
+    {
+      if (A.head_kernel <= 1)
+        break;
+      lookback = (A.head_kernel - 1) * A.head_dilation, mask = A.head_ring_mask, off = A.head_ring_off;
+    }
+    float4* ring = reinterpret_cast<float4*>(state + off);
+    const float4* h = hist_a + (size_t)li * P * NC;
+#pragma unroll
+    for (int j = 0; j < S; j++)
+    {
+      const int f = (j * NT + (int)threadIdx.x) & ((1 << LQ) - 1);
+      if (f < tv && t0 + f >= p.n_frames - lookback)
+      {
+#pragma unroll
+        for (int pl = 0; pl < P; pl++)
+          st_ring(ring + pl * (mask + 1) + ((tabs0 + (uint32_t)f) & (uint32_t)mask), ld_ring(h + (size_t)pl * NC + t0 + f));
+      }
+    }
+  }
+}
+
 // One persistent CTA per slot of Q = (S * NT) >> LQ streams.  C1 == 0: single layer array.
-template <int C0, int C1, int S, int NT, int MINB, int LQ>
+// LS: lock-step tile-parallel mode (one CTA per (stream, tile), see WaveNetKernelParams::hist); needs tile_flags.
+template <int C0, int C1, int S, int NT, int MINB, int LQ, bool LS = false>
 __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_constant__ WaveNetKernelParams p)
 {
+  static_assert(!LS || (S * NT) == (1 << LQ), "lock-step mode: one stream per tile");
   constexpr int T = S * NT;
   constexpr int FQ = 1 << LQ;
   constexpr int Q = T / FQ;
@@ -681,8 +808,8 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
   // this CTA owns ONE (stream, tile) and hands its ring columns to the next tile's CTA layer by layer.
   int s_begin = blockIdx.x * Q, s_end = p.batch, s_step = gridDim.x * Q;
   int t_begin = 0, t_end = p.n_frames;
-  TileSync ts{nullptr, nullptr};
-  if (Q == 1 && p.tile_flags != nullptr)
+  TileSync ts{nullptr, nullptr, 0};
+  if (Q == 1 && (LS || p.tile_flags != nullptr))
   {
     const int tile_i = blockIdx.x % p.tiles_per_stream;
     s_begin = blockIdx.x / p.tiles_per_stream;
@@ -691,6 +818,7 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
     t_end = min(p.n_frames, t_begin + FQ);
     ts.mine = p.tile_flags + (size_t)s_begin * p.tiles_per_stream + tile_i;
     ts.prev = tile_i > 0 ? ts.mine - 1 : nullptr;
+    ts.tile_i = tile_i;
   }
   const int step1 = p.arrays[0].n_layers + 1; // first hand-over step of the second layer array
 
@@ -719,6 +847,10 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
     {
       const int tv = min(FQ, p.n_frames - t0);
       const uint32_t tabs0 = p.t_base + (uint32_t)t0;
+      // LS: this stream's history buffer at the first plane of each array
+      float4* const hist_s = LS ? reinterpret_cast<float4*>(p.hist + (size_t)stream0 * p.hist_stride) : nullptr;
+      float4* const hist0 = LS ? hist_s + (size_t)p.hist_plane0[0] * p.hist_cols : nullptr;
+      float4* const hist1 = LS ? hist_s + (size_t)p.hist_plane0[1] * p.hist_cols : nullptr;
       int Tv[S];
       float x[S][1], cond[S];
 #pragma unroll
@@ -738,8 +870,8 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
           for (int q = 0; q < C0 / 2; q++)
             head0[j][q] = 0ull; // model.cpp:469
         float hout0[S][C0], ho0[S][1];
-        array_forward<1, C0, 1, S, NT, LQ>(p, p.arrays[0], sw, tile, state, stream0, tabs0, ts, 0, Tv, x, cond, head0, hout0,
-                                           ho0);
+        array_forward<1, C0, 1, S, NT, LQ, LS>(p, p.arrays[0], sw, tile, state, stream0, tabs0, ts, 0, hist0, t0, Tv, x, cond,
+                                               head0, hout0, ho0);
 #pragma unroll
         for (int j = 0; j < S; j++)
           y[j] = ho0[j][0];
@@ -754,8 +886,8 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
 #pragma unroll
             for (int q = 0; q < C0 / 2; q++)
               head0[j][q] = 0ull;
-          array_forward<1, C0, C1, S, NT, LQ>(p, p.arrays[0], sw, tile, state, stream0, tabs0, ts, 0, Tv, x, cond, head0,
-                                              hout0, ho0);
+          array_forward<1, C0, C1, S, NT, LQ, LS>(p, p.arrays[0], sw, tile, state, stream0, tabs0, ts, 0, hist0, t0, Tv, x, cond,
+                                                  head0, hout0, ho0);
         }
         // second array: layer input = previous array's layer output, head accumulator starts from
         // the previous array's head output (model.cpp:846-848, :473-486)
@@ -766,8 +898,8 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
           for (int q = 0; q < C1 / 2; q++)
             head1[j][q] = pack2(ho0[j][2 * q], ho0[j][2 * q + 1]);
         float hout1[S][C1], ho1[S][1];
-        array_forward<C0, C1, 1, S, NT, LQ>(p, p.arrays[1], sw, tile, state, stream0, tabs0, ts, step1, Tv, hout0, cond,
-                                            head1, hout1, ho1);
+        array_forward<C0, C1, 1, S, NT, LQ, LS>(p, p.arrays[1], sw, tile, state, stream0, tabs0, ts, step1, hist1, t0, Tv, hout0,
+                                                cond, head1, hout1, ho1);
 #pragma unroll
         for (int j = 0; j < S; j++)
           y[j] = ho1[j][0];
@@ -776,6 +908,24 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
       for (int j = 0; j < S; j++)
         if (fj[j] < Tv[j])
           yout[j][t0 + fj[j]] = p.head_scale * y[j]; // model.cpp:888-897
+      if constexpr (LS)
+      {
+        // every tile of the stream is done with the rings -> rewrite them from hist for the next call
+        ls_publish_wait(ts, kLsFinalStep, 0);
+        for (int k = tid; k < p.tiles_per_stream; k += NT)
+        {
+          const int* f = ts.mine - ts.tile_i + k;
+          int v;
+          do
+          {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+          } while (v <= kLsFinalStep);
+        }
+        __syncthreads();
+        ls_write_back<C0, S, NT, LQ>(p, p.arrays[0], state[0], hist0, t0, tabs0, Tv[0]);
+        if constexpr (C1 != 0)
+          ls_write_back<C1, S, NT, LQ>(p, p.arrays[1], state[0], hist1, t0, tabs0, Tv[0]);
+      }
     }
     __syncthreads(); // the next streams reuse the tile
   }

@@ -257,7 +257,7 @@ class DSP:
 
 
 def _options(lib, batch: int, device: int, prewarm: Optional[bool], fast_tanh: Optional[bool], ctas_per_sm: int,
-             kernel_geometry: int = 0):
+             kernel_geometry: int = 0, tile_mode: int = 0):
     o = _capi.Options()
     lib.nam_b200_default_options(C.byref(o))
     o.device = int(device)
@@ -266,21 +266,24 @@ def _options(lib, batch: int, device: int, prewarm: Optional[bool], fast_tanh: O
     o.prewarm_on_reset = 1 if prewarm is None else int(bool(prewarm))
     o.ctas_per_sm = int(ctas_per_sm)
     o.kernel_geometry = int(kernel_geometry)
+    o.tile_mode = int(tile_mode)
     return o
 
 
 def get_dsp(config, batch: int = 1, device: int = -1, prewarm: Optional[bool] = None,
-            fast_tanh: Optional[bool] = None, ctas_per_sm: int = 0, kernel_geometry: int = 0) -> DSP:
+            fast_tanh: Optional[bool] = None, ctas_per_sm: int = 0, kernel_geometry: int = 0,
+            tile_mode: int = 0) -> DSP:
     """nam::get_dsp: `config` is a path to a .nam file, a dict (parsed .nam) or a JSON string.
 
     batch      number of independent streams the handle carries (the reference: one DSP object each)
     prewarm    DspLoadOptions.prewarm (NAM/get_dsp.h:70-78): None = reference default (Reset prewarms)
     fast_tanh  None = use the process-wide switch (enable_fast_tanh()), like the reference
+    kernel_geometry / tile_mode / ctas_per_sm   tuning knobs, see nam_b200_options (include/nam_b200.h)
     """
     import json
 
     lib = _capi.load()
-    o = _options(lib, batch, device, prewarm, fast_tanh, ctas_per_sm, kernel_geometry)
+    o = _options(lib, batch, device, prewarm, fast_tanh, ctas_per_sm, kernel_geometry, tile_mode)
     h = C.c_void_p()
     if isinstance(config, (str, os.PathLike)) and not (isinstance(config, str) and config.lstrip().startswith("{")):
         rc = lib.nam_b200_create_from_file(str(Path(config)).encode(), C.byref(o), C.byref(h))
