@@ -63,8 +63,11 @@ typedef struct nam_b200_options
                               thread per frame) that otherwise serves only models outside the fused families */
   int32_t tile_mode; /* few streams x long calls (batch x tiles <= resident CTAs): 0 = library default: lock-step
                         tile-parallel mode (every (stream, tile) its own CTA, all tiles advancing layer by layer; a
-                        history buffer of up to ~150 MB is allocated by reset()); 1 = wavefront tile-parallel mode (no
-                        buffer, tile c one layer behind tile c-1); 2 = never: one CTA walks a stream's tiles in turn */
+                        history buffer of up to ~150 MB is allocated by reset(); tiles of 256 frames with one frame per
+                        thread unless kernel_geometry 1 / 2 pins 128 x 2 / 256 x 2 threads x frames); 1 = wavefront
+                        tile-parallel mode (no buffer, tile c one layer behind tile c-1); 2 = never: one CTA walks a
+                        stream's tiles in turn.  Tile-parallel launches need their CTAs co-resident: do not run
+                        other kernels on the same GPU concurrently with such a call */
   int32_t reserved[6];
 } nam_b200_options;
 
@@ -104,8 +107,11 @@ int nam_b200_reset(nam_b200_model* m, double sample_rate, int max_frames);
 /* DSP::prewarm() on its own (after a reset with prewarm_on_reset == 0). */
 int nam_b200_prewarm(nam_b200_model* m);
 
-/* Batched throughput entry: `batch` (<= max_batch) mono streams, stream b reads
+/* Batched throughput entry: `batch` (<= max_batch) streams, stream b reads
  * in[b*in_stride .. +n_frames) and writes out[b*out_stride .. +n_frames); n_frames <= max_frames.
+ * Multi-channel models (in_channels / out_channels of nam_b200_info != 1; WaveNet: NAM/wavenet/model.cpp:809-820,
+ * 888-909, LSTM: NAM/lstm.cpp:103-125): a stream's row holds its channel planes back to back, channel c of stream b
+ * at in[b*in_stride + c*n_frames .. +n_frames) (out likewise), strides >= channels * n_frames.
  * Host pointers; copies ride the handle's stream; returns after the result is in `out`. */
 int nam_b200_process_f32(nam_b200_model* m, const float* in, float* out, int batch, int n_frames, int64_t in_stride,
                          int64_t out_stride);
@@ -115,7 +121,8 @@ int nam_b200_process_f32(nam_b200_model* m, const float* in, float* out, int bat
 int nam_b200_process_f32_device(nam_b200_model* m, const float* in_device, float* out_device, int batch, int n_frames,
                                 int64_t in_stride, int64_t out_stride, void* cuda_stream);
 
-/* nam::DSP::process for stream 0 of the handle: planar input[channel][frame]. */
+/* nam::DSP::process for stream 0 of the handle: planar input[channel][frame], in_channels input arrays and
+ * out_channels output arrays like the reference's NAM_SAMPLE** (NAM/dsp.h:97). */
 int nam_b200_process_f64_planar(nam_b200_model* m, const double* const* input, double* const* output, int n_frames);
 int nam_b200_process_f32_planar(nam_b200_model* m, const float* const* input, float* const* output, int n_frames);
 

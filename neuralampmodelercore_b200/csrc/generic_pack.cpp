@@ -187,10 +187,9 @@ GenericPlan plan_generic(const ModelSpec& ms)
   if (ms.arch != Arch::WaveNet)
     return no("not a WaveNet");
   const WaveNetSpec& wn = ms.wavenet;
-  if (wn.in_channels != 1 || ms.out_channels != 1)
-    return no("CUDA path is mono in / mono out (in_channels " + std::to_string(wn.in_channels) + ", out_channels "
-              + std::to_string(ms.out_channels) + ")");
   Packer pk{plan, {}};
+  if (!pk.width(wn.in_channels, "input channels") || !pk.width(ms.out_channels, "output channels"))
+    return no(pk.err);
   if (!pk.net(wn, ms.out_channels, plan.net))
     return no(pk.err);
   if (wn.condition_dsp)
@@ -200,14 +199,24 @@ GenericPlan plan_generic(const ModelSpec& ms)
       return no("condition_dsp is not a WaveNet");
     if (cm.wavenet.condition_dsp)
       return no("nested condition_dsp");
-    if (cm.wavenet.in_channels != 1)
-      return no("condition_dsp with " + std::to_string(cm.wavenet.in_channels) + " input channels");
+    if (cm.wavenet.in_channels != wn.in_channels) // model.cpp:603-611
+      return no("input channels of WaveNet (" + std::to_string(wn.in_channels)
+                + ") don't match input channels of condition DSP (" + std::to_string(cm.wavenet.in_channels) + ")");
     if (!pk.net(cm.wavenet, cm.out_channels, plan.cond))
       return no("condition_dsp: " + pk.err);
     if (!pk.width(cm.out_channels, "condition_dsp output width"))
       return no(pk.err);
     plan.has_cond = true;
   }
+  // the input vector is the first array's layer input and, without a condition_dsp, every array's condition
+  // (model.cpp:809-820,840; the reference leaves a mismatch to an Eigen assertion)
+  if (wn.arrays[0].input_size != wn.in_channels)
+    return no("input_size of the first layer array (" + std::to_string(wn.arrays[0].input_size) + ") != in_channels ("
+              + std::to_string(wn.in_channels) + ")");
+  const int cond_dim = plan.has_cond ? wn.condition_dsp->out_channels : wn.in_channels;
+  for (const ArraySpec& A : wn.arrays)
+    if (A.condition_size != cond_dim)
+      return no("condition_size " + std::to_string(A.condition_size) + " != condition width " + std::to_string(cond_dim));
   if (!pk.err.empty())
     return no(pk.err);
   plan.weights.resize((plan.weights.size() + 3) & ~(size_t)3, 0.0f);

@@ -73,6 +73,9 @@ struct LstmKernelParams
   int batch, n_frames;
   int num_layers, input_size, hidden;
   int fast_tanh;
+  // multi-channel models (lstm.cpp:103-125): stream b's channel c is the plane in[b * in_stride + c * n_frames ..];
+  // input_size == in_channels.  Mono models take the staged (coalesced) path, in_ch == out_ch == 1.
+  int in_ch, out_ch;
 };
 
 constexpr int kLstmThreads = 64; // streams per CTA
@@ -125,6 +128,9 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_kernel(const LstmKernelPara
     __syncthreads();
     if (active)
     {
+      const bool multi = p.in_ch > 1 || p.out_ch > 1;
+      const float* __restrict__ gin = p.in + (size_t)stream * p.in_stride + t0;
+      float* __restrict__ gout = p.out + (size_t)stream * p.out_stride + t0;
       for (int f = 0; f < tc; f++)
       {
         float x_scalar = sio[tid * (kLstmChunk + 1) + f];
@@ -142,8 +148,11 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_kernel(const LstmKernelPara
           {
             const float* wr = w + r * W;
             float acc = 0.0f;
-            if (l == 0)
-              acc = fmaf(wr[0], x_scalar, acc); // input_size == 1 on this path
+            if (l == 0 && !multi)
+              acc = fmaf(wr[0], x_scalar, acc); // input_size == 1
+            else if (l == 0)
+              for (int j = 0; j < I; j++)
+                acc = fmaf(wr[j], __ldg(gin + (size_t)j * p.n_frames + f), acc);
             else
               for (int j = 0; j < I; j++)
                 acc = fmaf(wr[j], xprev[j * kLstmThreads + tid], acc);
@@ -166,6 +175,18 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_kernel(const LstmKernelPara
         }
         // head (lstm.cpp:164-167)
         const float* hl = sstate + ((p.num_layers - 1) * 2) * H * kLstmThreads;
+        if (multi)
+        {
+          // head: (out_channels x H) row-major, then the bias vector (lstm.cpp:79-97)
+          for (int oc = 0; oc < p.out_ch; oc++)
+          {
+            float y = 0.0f;
+            for (int j = 0; j < H; j++)
+              y = fmaf(w[oc * H + j], hl[j * kLstmThreads + tid], y);
+            gout[(size_t)oc * p.n_frames + f] = y + w[p.out_ch * H + oc];
+          }
+          continue;
+        }
         float y = 0.0f;
         for (int j = 0; j < H; j++)
           y = fmaf(w[j], hl[j * kLstmThreads + tid], y);
@@ -176,7 +197,7 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_kernel(const LstmKernelPara
     for (int idx = tid; idx < kLstmThreads * kLstmChunk; idx += kLstmThreads)
     {
       const int s = idx / kLstmChunk, f = idx - s * kLstmChunk;
-      if (stream0 + s < p.batch && f < tc)
+      if (stream0 + s < p.batch && f < tc && p.out_ch == 1 && p.in_ch == 1)
         p.out[(size_t)(stream0 + s) * p.out_stride + t0 + f] = sout[s * (kLstmChunk + 1) + f];
     }
     __syncthreads();
@@ -339,7 +360,7 @@ struct nam_b200_model
   size_t tile_flags_capacity = 0;
   float* d_hist = nullptr; // lock-step tile-parallel mode: per-call history buffer (WaveNetKernelParams::hist)
   size_t hist_floats = 0;
-  int wn_ctas_ls[2] = {0, 0}; // resident CTAs per SM of the lock-step kernels (geometries 0 / 1)
+  int wn_ctas_ls[3] = {0, 0, 0}; // resident CTAs per SM of the lock-step kernels (kLsGeom)
   int wn_ctas_short[2] = {0, 0}; // same for the short-call (multi-stream tile) geometries 2 / 3
   int wn_geometry = 1; // 0 / 1: index into kWnGeom (FFMA kernel); 2: tensor-core kernel (wavenet_tc.cuh)
   float* d_tc_blob = nullptr; // per-layer B-operand images of the tensor-core kernel
@@ -459,25 +480,40 @@ int occupancy_wavenet_variant(size_t smem)
   return n > 0 ? n : 1;
 }
 
-// lock-step tile-parallel kernels (LS = true): geometries 0 / 1 only
-template <int C0, int C1, int NT, int MINB, int LQ>
+// lock-step tile-parallel kernels (LS = true), one stream per tile.  A lone CTA's layer step is latency-bound
+// (dependent issue, one or two warps per scheduler), so the first choice gives every thread ONE frame: half the
+// instructions per thread and layer step, twice the warps per tile.
+//   LS geometry 0: 256 threads x 1 frame, tile 256, >= 3 CTAs/SM   (default)
+//   LS geometry 1: 128 threads x 2 frames, tile 256, >= 3 CTAs/SM  (kernel_geometry 1)
+//   LS geometry 2: 256 threads x 2 frames, tile 512, >= 2 CTAs/SM  (kernel_geometry 2; also when tile 256 does not fit)
+struct LsGeometry
+{
+  int nt, s, min_ctas, lq;
+  int tile_frames() const { return 1 << lq; }
+};
+constexpr LsGeometry kLsGeom[3] = {{256, 1, 3, 8}, {128, 2, 3, 8}, {256, 2, 2, 9}};
+
+template <int C0, int C1, int S, int NT, int MINB, int LQ>
 void launch_wavenet_ls_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem, cudaStream_t st)
 {
-  auto kern = wavenet_fused_kernel<C0, C1, kWnS, NT, MINB, LQ, true>;
+  auto kern = wavenet_fused_kernel<C0, C1, S, NT, MINB, LQ, true>;
   static bool configured[64] = {false};
   if (!configured[m->device & 63])
   {
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured[m->device & 63] = true;
   }
-  kern<<<grid, NT, smem, st>>>(kp);
-  CUDA_CHECK(cudaGetLastError());
+  // The tiles spin on each other's flags, so they must all be resident at once: a cooperative launch is
+  // gang-scheduled (it starts only when the whole grid fits), which keeps two such launches from different handles
+  // from starving each other.
+  void* args[] = {const_cast<void*>(static_cast<const void*>(&kp))};
+  CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3((unsigned)grid), dim3(NT), args, smem, st));
 }
 
-template <int C0, int C1, int NT, int MINB, int LQ>
+template <int C0, int C1, int S, int NT, int MINB, int LQ>
 int occupancy_wavenet_ls_variant(size_t smem)
 {
-  auto kern = wavenet_fused_kernel<C0, C1, kWnS, NT, MINB, LQ, true>;
+  auto kern = wavenet_fused_kernel<C0, C1, S, NT, MINB, LQ, true>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   int n = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, NT, smem) != cudaSuccess)
@@ -486,7 +522,9 @@ int occupancy_wavenet_ls_variant(size_t smem)
 }
 
 #define WN_LS_CASE(C0, C1, FN, ...)                                                                                  \
-  case (C0) * 100 + (C1): return geom == 0 ? FN<C0, C1, 128, 3, 8>(__VA_ARGS__) : FN<C0, C1, 256, 2, 9>(__VA_ARGS__);
+  case (C0) * 100 + (C1):                                                                                            \
+    return geom == 0 ? FN<C0, C1, 1, 256, 3, 8>(__VA_ARGS__)                                                         \
+                     : (geom == 1 ? FN<C0, C1, 2, 128, 3, 8>(__VA_ARGS__) : FN<C0, C1, 2, 256, 2, 9>(__VA_ARGS__));
 
 #define WN_LS_DISPATCH(FN, ...)                                                                                      \
   switch (c0 * 100 + c1)                                                                                             \
@@ -552,7 +590,11 @@ int occupancy_wavenet_ls_dispatch(int c0, int c1, int geom, size_t smem)
   WN_LS_DISPATCH(occupancy_wavenet_ls_variant, smem)
 }
 
-size_t wavenet_smem_bytes(const WaveNetPlan& plan, int geom);
+size_t wavenet_ls_smem_bytes(const WaveNetPlan& plan, int g)
+{
+  const int cmax = std::max(plan.cp[0], plan.cp[1]);
+  return (plan.blob.size() + 3) / 4 * 16 + (size_t)(cmax / 4) * (kHalo + kLsGeom[g].tile_frames()) * 16;
+}
 
 // ---- lock-step tile-parallel mode: geometry choice and history buffer -----------------------------------------------
 // planes (4 channels each) of hist per stream: every layer's input, plus the head accumulator of a convolutional head
@@ -568,11 +610,11 @@ int wavenet_hist_planes(const WaveNetPlan& plan, int* plane0 = nullptr)
   return planes;
 }
 
-// resident CTAs of the lock-step kernel of geometry g (0 / 1) on the whole device; 0 if it cannot run
+// resident CTAs of the lock-step kernel of LS geometry g on the whole device; 0 if it cannot run
 long wavenet_ls_capacity(nam_b200_model* m, int g)
 {
   const WaveNetPlan& plan = m->plan;
-  const size_t smem = wavenet_smem_bytes(plan, g);
+  const size_t smem = wavenet_ls_smem_bytes(plan, g);
   if (smem > 227 * 1024)
     return 0;
   if (m->wn_ctas_ls[g] <= 0)
@@ -580,17 +622,26 @@ long wavenet_ls_capacity(nam_b200_model* m, int g)
   return (long)m->wn_ctas_ls[g] * m->sm_count;
 }
 
-// The geometry the lock-step mode would use for (batch, n_frames): the smallest tile whose CTAs are all co-resident
-// (more, shorter layer-steps in flight), -1 if none.  kernel_geometry 1 / 2 pins the geometry.
+// is LS geometry g a candidate under the handle's options?  kernel_geometry 1 / 2 pin LS geometry 1 / 2; the default
+// tries 0 (tile 256) and then 2 (tile 512: half as many CTAs to keep co-resident)
+bool wavenet_ls_candidate(const nam_b200_model* m, int g)
+{
+  if (m->opts.kernel_geometry == 0)
+    return g != 1;
+  return g == m->opts.kernel_geometry;
+}
+
+// The LS geometry the lock-step mode would use for (batch, n_frames): the first candidate whose CTAs are all
+// co-resident, -1 if none.
 int wavenet_ls_geometry(nam_b200_model* m, int batch, int n_frames, int* tiles_out)
 {
   if (m->opts.tile_mode != 0 || m->wn_geometry > 1 || m->use_generic)
     return -1;
-  for (int g = 0; g < 2; g++)
+  for (int g = 0; g < 3; g++)
   {
-    if (m->opts.kernel_geometry != 0 && g != m->wn_geometry)
+    if (!wavenet_ls_candidate(m, g))
       continue;
-    const int tf = kWnS * kWnGeom[g].nt;
+    const int tf = kLsGeom[g].tile_frames();
     const int tiles = (n_frames + tf - 1) / tf;
     const long cap = wavenet_ls_capacity(m, g);
     if (tiles >= 2 && (long)batch * tiles <= cap)
@@ -610,11 +661,11 @@ void ensure_hist(nam_b200_model* m)
     return;
   const int planes = wavenet_hist_planes(m->plan);
   size_t need = 0, need_flags = 0;
-  for (int g = 0; g < 2; g++)
+  for (int g = 0; g < 3; g++)
   {
-    if (m->opts.kernel_geometry != 0 && g != m->wn_geometry)
+    if (!wavenet_ls_candidate(m, g))
       continue;
-    const int tf = kWnS * kWnGeom[g].nt;
+    const int tf = kLsGeom[g].tile_frames();
     const long tiles_max = (m->max_frames + tf - 1) / tf;
     const long cap = wavenet_ls_capacity(m, g);
     if (tiles_max < 2 || cap < 2)
@@ -799,7 +850,7 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
     const int g = wavenet_ls_geometry(m, batch, n_frames, &tiles);
     if (g >= 0)
     {
-      const int tf = kWnS * kWnGeom[g].nt;
+      const int tf = kLsGeom[g].tile_frames();
       int plane0[kMaxArrays] = {0, 0, 0, 0};
       const int planes = wavenet_hist_planes(plan, plane0);
       const size_t per_stream = (size_t)planes * tiles * tf * 4;
@@ -813,7 +864,7 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
         kp.hist_cols = tiles * tf;
         for (int a = 0; a < kMaxArrays; a++)
           kp.hist_plane0[a] = plane0[a];
-        launch_wavenet_ls_dispatch(c0, c1, g, m, kp, batch * tiles, wavenet_smem_bytes(plan, g), st);
+        launch_wavenet_ls_dispatch(c0, c1, g, m, kp, batch * tiles, wavenet_ls_smem_bytes(plan, g), st);
         m->launches++;
         return;
       }
@@ -871,8 +922,10 @@ void launch_lstm(nam_b200_model* m, const float* d_in, float* d_out, int batch, 
   kp.input_size = ls.input_size;
   kp.hidden = ls.hidden;
   kp.fast_tanh = m->fast_tanh_runtime;
+  kp.in_ch = m->spec.in_channels;
+  kp.out_ch = m->spec.out_channels;
   const int H = ls.hidden;
-  if (H <= kLstmGroupMaxHidden && ls.num_layers <= kLstmGroupMaxLayers)
+  if (H <= kLstmGroupMaxHidden && ls.num_layers <= kLstmGroupMaxLayers && kp.in_ch == 1 && kp.out_ch == 1)
   {
     // a group of G lanes per stream (lstm_group.cuh)
     const int G = H <= 4 ? 4 : (H <= 8 ? 8 : (H <= 16 ? 16 : 32));
@@ -1054,12 +1107,13 @@ void prewarm(nam_b200_model* m)
   if (ps <= 0)
     return;
   const int bs = std::max(m->max_frames, 1);
-  ensure_staging(m, (size_t)std::max<size_t>((size_t)bs, (size_t)m->opts.max_batch * bs));
-  CUDA_CHECK(cudaMemsetAsync(m->d_in, 0, (size_t)bs * sizeof(float), m->stream));
+  const size_t ci = (size_t)m->spec.in_channels, co = (size_t)m->spec.out_channels;
+  ensure_staging(m, (size_t)m->opts.max_batch * bs * std::max(ci, co));
+  CUDA_CHECK(cudaMemsetAsync(m->d_in, 0, (size_t)bs * ci * sizeof(float), m->stream));
   int done = 0;
   while (done < ps)
   {
-    run_device(m, m->d_in, m->d_out, 1, bs, bs, bs, m->stream);
+    run_device(m, m->d_in, m->d_out, 1, bs, (long)(bs * ci), (long)(bs * co), m->stream);
     done += bs;
   }
   broadcast_state(m);
@@ -1133,8 +1187,10 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
     CUDA_CHECK(cudaEventCreate(&m->ev0));
     CUDA_CHECK(cudaEventCreate(&m->ev1));
 
-    if (m->spec.in_channels != 1 || m->spec.out_channels != 1)
-      return fail(NAM_B200_ERR_UNSUPPORTED, "CUDA path is mono in / mono out (model has "
+    // multi-channel models: WaveNet through the general kernel, LSTM through the thread-per-stream kernel
+    const bool mono = m->spec.in_channels == 1 && m->spec.out_channels == 1;
+    if (!mono && m->spec.arch == Arch::Linear)
+      return fail(NAM_B200_ERR_UNSUPPORTED, "Linear on the CUDA path is mono in / mono out (model has "
                                               + std::to_string(m->spec.in_channels) + " in, "
                                               + std::to_string(m->spec.out_channels) + " out channels)");
     std::vector<float> blob;
@@ -1143,6 +1199,11 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
       case Arch::WaveNet:
       {
         m->plan = plan_wavenet(m->spec);
+        if (!mono && m->plan.eligible)
+        {
+          m->plan.eligible = false;
+          m->plan.why_not = "multi-channel in / out";
+        }
         if (!m->plan.eligible || m->opts.kernel_geometry == 4)
         {
           // outside the fused families (or asked for explicitly): the general kernel
@@ -1187,8 +1248,12 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
       case Arch::LSTM:
       {
         const LstmSpec& ls = m->spec.lstm;
-        if (ls.input_size != 1)
-          return fail(NAM_B200_ERR_UNSUPPORTED, "LSTM input_size != 1");
+        if (ls.input_size != m->spec.in_channels) // lstm.cpp:74,111: in_channels samples land in an input_size vector
+          return fail(NAM_B200_ERR_UNSUPPORTED, "LSTM input_size (" + std::to_string(ls.input_size) + ") != in_channels ("
+                                                  + std::to_string(m->spec.in_channels) + ")");
+        if ((int)ls.head_b.size() != m->spec.out_channels || m->spec.out_channels > 64)
+          return fail(NAM_B200_ERR_UNSUPPORTED, "LSTM head with " + std::to_string(ls.head_b.size()) + " rows for "
+                                                  + std::to_string(m->spec.out_channels) + " output channels");
         if (ls.num_layers < 1)
           return fail(NAM_B200_ERR_UNSUPPORTED, "LSTM with zero layers");
         double macs = 0.0;
@@ -1200,7 +1265,7 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
         }
         blob.insert(blob.end(), ls.head_w.begin(), ls.head_w.end());
         blob.insert(blob.end(), ls.head_b.begin(), ls.head_b.end());
-        macs += ls.hidden;
+        macs += (double)ls.hidden * m->spec.out_channels;
         m->state_stride = ((long)ls.num_layers * 2 * ls.hidden + 3) & ~3L;
         m->flops_per_frame = 2.0 * macs;
         m->variant = 2000 + ls.hidden;
@@ -1386,11 +1451,17 @@ static int inspect_spec(const ModelSpec& spec, char* out, int64_t capacity)
     std::snprintf(out, (size_t)capacity, "%s", text.c_str());
     return NAM_B200_OK;
   }
-  if (spec.in_channels != 1 || spec.out_channels != 1)
-    reason = "CUDA path is mono in / mono out";
+  const bool mono = spec.in_channels == 1 && spec.out_channels == 1;
+  if (!mono && spec.arch == Arch::Linear)
+    reason = "Linear on the CUDA path is mono in / mono out";
   else if (spec.arch == Arch::WaveNet)
   {
-    const WaveNetPlan plan = plan_wavenet(spec);
+    WaveNetPlan plan = plan_wavenet(spec);
+    if (!mono && plan.eligible)
+    {
+      plan.eligible = false;
+      plan.why_not = "multi-channel in / out";
+    }
     if (plan.eligible)
     {
       kernel = "fused";
@@ -1415,12 +1486,12 @@ static int inspect_spec(const ModelSpec& spec, char* out, int64_t capacity)
   }
   else if (spec.arch == Arch::LSTM)
   {
-    if (spec.lstm.input_size != 1 || spec.lstm.num_layers < 1)
-      reason = "LSTM input_size != 1 or no layers";
+    if (spec.lstm.input_size != spec.in_channels || spec.lstm.num_layers < 1)
+      reason = "LSTM input_size != in_channels or no layers";
     else
     {
       kernel = "lstm";
-      double macs = spec.lstm.hidden;
+      double macs = (double)spec.lstm.hidden * spec.out_channels;
       for (const auto& c : spec.lstm.cells)
         macs += 4.0 * c.hidden * (c.input_size + c.hidden);
       flops = 2.0 * macs;
@@ -1540,8 +1611,9 @@ int nam_b200_reset(nam_b200_model* m, double sample_rate, int max_frames)
     if (max_frames < 1)
       return fail(NAM_B200_ERR_INVALID_ARGUMENT, "max_frames must be >= 1");
     m->max_frames = max_frames;
-    ensure_staging(m, (size_t)m->opts.max_batch * max_frames);
-    ensure_pinned(m, (size_t)2 * max_frames);
+    const size_t ch = (size_t)std::max(m->spec.in_channels, m->spec.out_channels);
+    ensure_staging(m, (size_t)m->opts.max_batch * max_frames * ch);
+    ensure_pinned(m, (size_t)2 * max_frames * ch);
     ensure_hist(m);
     init_state(m);
     m->is_reset = true;
@@ -1595,8 +1667,9 @@ int nam_b200_process_f32(nam_b200_model* m, const float* in, float* out, int bat
       return rc;
     if (n_frames == 0)
       return NAM_B200_OK;
-    if (in_stride < n_frames || out_stride < n_frames)
-      return fail(NAM_B200_ERR_INVALID_ARGUMENT, "stride smaller than n_frames");
+    const size_t ci = (size_t)m->spec.in_channels, co = (size_t)m->spec.out_channels;
+    if ((size_t)in_stride < ci * n_frames || (size_t)out_stride < co * n_frames)
+      return fail(NAM_B200_ERR_INVALID_ARGUMENT, "stride smaller than channels x n_frames");
     const size_t row = (size_t)n_frames * sizeof(float);
     // Large WaveNet batches: pipeline the call in chunks of whole kernel waves so that the copies of chunk c+1 /
     // c-1 overlap the kernel of chunk c (the kernel is compute-bound; the copies would otherwise add ~18 %).
@@ -1639,12 +1712,13 @@ int nam_b200_process_f32(nam_b200_model* m, const float* in, float* out, int bat
       m->timing_valid = true;
       return NAM_B200_OK;
     }
-    CUDA_CHECK(cudaMemcpy2DAsync(m->d_in, row, in, (size_t)in_stride * sizeof(float), row, (size_t)batch,
+    // (multi-channel models: a stream's row is its channel planes back to back)
+    CUDA_CHECK(cudaMemcpy2DAsync(m->d_in, ci * row, in, (size_t)in_stride * sizeof(float), ci * row, (size_t)batch,
                                  cudaMemcpyHostToDevice, m->stream));
     CUDA_CHECK(cudaEventRecord(m->ev0, m->stream));
-    run_device(m, m->d_in, m->d_out, batch, n_frames, n_frames, n_frames, m->stream);
+    run_device(m, m->d_in, m->d_out, batch, n_frames, (long)(ci * n_frames), (long)(co * n_frames), m->stream);
     CUDA_CHECK(cudaEventRecord(m->ev1, m->stream));
-    CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)out_stride * sizeof(float), m->d_out, row, row, (size_t)batch,
+    CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)out_stride * sizeof(float), m->d_out, co * row, co * row, (size_t)batch,
                                  cudaMemcpyDeviceToHost, m->stream));
     CUDA_CHECK(cudaStreamSynchronize(m->stream));
     m->timing_valid = true;
@@ -1656,7 +1730,23 @@ int nam_b200_process_f32_planar(nam_b200_model* m, const float* const* input, fl
 {
   if (!input || !output)
     return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null channel array");
-  return nam_b200_process_f32(m, input[0], output[0], 1, n_frames, n_frames, n_frames);
+  nam_b200_model* a = active_model(m);
+  if (!a || (a->spec.in_channels == 1 && a->spec.out_channels == 1))
+    return nam_b200_process_f32(m, input[0], output[0], 1, n_frames, n_frames, n_frames);
+  // multi-channel: gather the caller's channel arrays into one row of planes
+  const int rc = check_process_args(a, input[0], output[0], 1, n_frames);
+  if (rc != NAM_B200_OK)
+    return rc;
+  const size_t ci = (size_t)a->spec.in_channels, co = (size_t)a->spec.out_channels, n = (size_t)n_frames;
+  std::vector<float> hin(ci * n), hout(co * n);
+  for (size_t c = 0; c < ci; c++)
+    std::memcpy(hin.data() + c * n, input[c], n * sizeof(float));
+  const int rc2 = nam_b200_process_f32(m, hin.data(), hout.data(), 1, n_frames, (int64_t)(ci * n), (int64_t)(co * n));
+  if (rc2 != NAM_B200_OK)
+    return rc2;
+  for (size_t c = 0; c < co; c++)
+    std::memcpy(output[c], hout.data() + c * n, n * sizeof(float));
+  return NAM_B200_OK;
 }
 
 int nam_b200_process_f64_planar(nam_b200_model* m, const double* const* input, double* const* output, int n_frames)
@@ -1670,19 +1760,22 @@ int nam_b200_process_f64_planar(nam_b200_model* m, const double* const* input, d
       return rc;
     if (n_frames == 0)
       return NAM_B200_OK;
+    const size_t ci = (size_t)m->spec.in_channels, co = (size_t)m->spec.out_channels, n = (size_t)n_frames;
     float* hin = m->h_pin;
-    float* hout = m->h_pin + m->max_frames;
-    for (int i = 0; i < n_frames; i++)
-      hin[i] = (float)input[0][i]; // the double -> float cast of model.cpp:817 / lstm.cpp:111
-    CUDA_CHECK(cudaMemcpyAsync(m->d_in, hin, (size_t)n_frames * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    float* hout = m->h_pin + (size_t)m->max_frames * std::max(ci, co);
+    for (size_t c = 0; c < ci; c++)
+      for (size_t i = 0; i < n; i++)
+        hin[c * n + i] = (float)input[c][i]; // the double -> float cast of model.cpp:817 / lstm.cpp:111
+    CUDA_CHECK(cudaMemcpyAsync(m->d_in, hin, ci * n * sizeof(float), cudaMemcpyHostToDevice, m->stream));
     CUDA_CHECK(cudaEventRecord(m->ev0, m->stream));
-    run_device(m, m->d_in, m->d_out, 1, n_frames, n_frames, n_frames, m->stream);
+    run_device(m, m->d_in, m->d_out, 1, n_frames, (long)(ci * n), (long)(co * n), m->stream);
     CUDA_CHECK(cudaEventRecord(m->ev1, m->stream));
-    CUDA_CHECK(cudaMemcpyAsync(hout, m->d_out, (size_t)n_frames * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_CHECK(cudaMemcpyAsync(hout, m->d_out, co * n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
     CUDA_CHECK(cudaStreamSynchronize(m->stream));
     m->timing_valid = true;
-    for (int i = 0; i < n_frames; i++)
-      output[0][i] = (double)hout[i];
+    for (size_t c = 0; c < co; c++)
+      for (size_t i = 0; i < n; i++)
+        output[c][i] = (double)hout[c * n + i];
     return NAM_B200_OK;
   });
 }

@@ -239,11 +239,14 @@ __device__ __forceinline__ void g_net(const GenThread& c, const GNet& N, const G
       out[i] = N.head_scale * hout[i];
 }
 
-// mono in / mono out streams (the C ABI's batched entry); persistent CTAs, one stream at a time
+// The C ABI's batched entry; persistent CTAs, one stream at a time.  Multi-channel models (model.cpp:809-820,
+// :888-909): stream s's channel c is the plane in[s * in_stride + c * n_frames ..] (out likewise); the input vector
+// is both the first array's layer input and -- unless a condition_dsp produces it -- the condition.
 __global__ void __launch_bounds__(kGenTile) wavenet_generic_kernel(const __grid_constant__ GenericKernelParams p)
 {
   GenThread c;
   c.w = p.weights;
+  const int ci = p.net.in_channels, co = p.net.out_channels;
   for (int s = blockIdx.x; s < p.batch; s += gridDim.x)
   {
     c.st = p.state + (size_t)s * p.state_stride;
@@ -254,14 +257,18 @@ __global__ void __launch_bounds__(kGenTile) wavenet_generic_kernel(const __grid_
       const int f = t0 + (int)threadIdx.x;
       c.valid = f < p.n_frames;
       c.t = p.t_base + (uint32_t)f;
-      float in[1] = {c.valid ? __ldg(xin + f) : 0.0f}, out[kGenMaxVec], cond[kGenMaxVec];
+      float in[kGenMaxVec], out[kGenMaxVec], cond[kGenMaxVec];
+      for (int ch = 0; ch < ci; ch++)
+        in[ch] = c.valid ? __ldg(xin + (size_t)ch * p.n_frames + f) : 0.0f;
       if (p.has_cond)
         g_net(c, p.cond, p.layers, in, in, cond); // _process_condition (model.cpp:777-807)
       else
-        cond[0] = in[0];
+        for (int ch = 0; ch < ci; ch++)
+          cond[ch] = in[ch];
       g_net(c, p.net, p.layers, in, cond, out);
       if (c.valid)
-        yout[f] = out[0];
+        for (int ch = 0; ch < co; ch++)
+          yout[(size_t)ch * p.n_frames + f] = out[ch];
     }
   }
 }

@@ -228,9 +228,14 @@ class DSP:
             _raise(rc, self._lib)
 
     def process_batch(self, x: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
-        """x: (batch, n) float32 host array, one row per independent stream -> (batch, n) float32."""
+        """x: (batch, n) float32 host array, one row per independent stream -> (batch, n) float32.
+        Multi-channel models: x (batch, in_channels, n) -> (batch, out_channels, n)."""
+        if x.ndim == 3:
+            return self._process_batch_multichannel(x, out)
         if x.ndim != 2 or x.dtype != np.float32:
             raise TypeError("process_batch takes a 2-D float32 array [batch, frames]")
+        if self.in_channels != 1 or self.out_channels != 1:
+            raise TypeError("multi-channel model: process_batch takes [batch, in_channels, frames]")
         if not x.flags["C_CONTIGUOUS"]:
             x = np.ascontiguousarray(x)
         b, n = x.shape
@@ -240,6 +245,22 @@ class DSP:
         xs = x.strides[0] // 4 if b > 1 else n
         os_ = out.strides[0] // 4 if b > 1 else n
         rc = self._lib.nam_b200_process_f32(self._h, x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), b, n, xs, os_)
+        if rc != 0:
+            _raise(rc, self._lib)
+        return out
+
+    def _process_batch_multichannel(self, x: np.ndarray, out: Optional[np.ndarray]) -> np.ndarray:
+        if x.dtype != np.float32 or x.shape[1] != self.in_channels:
+            raise TypeError(f"process_batch takes a float32 array [batch, {self.in_channels}, frames]")
+        x = np.ascontiguousarray(x)
+        b, ci, n = x.shape
+        co = self.out_channels
+        if out is None:
+            out = np.empty((b, co, n), np.float32)
+        elif out.shape != (b, co, n) or out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"out must be a contiguous float32 array [batch, {co}, frames]")
+        rc = self._lib.nam_b200_process_f32(self._h, x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), b, n,
+                                            ci * n, co * n)
         if rc != 0:
             _raise(rc, self._lib)
         return out

@@ -49,6 +49,7 @@ def _load(variant: str) -> C.CDLL:
         lib.namref_reset.argtypes = [C.c_void_p, C.c_double, C.c_int]
         lib.namref_process_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.namref_run_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int]
+        lib.namref_process_planar_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.namref_set_slimmable_size.argtypes = [C.c_void_p, C.c_double]
         for name in ("prewarm_samples", "in_channels", "out_channels"):
             getattr(lib, f"namref_{name}").argtypes = [C.c_void_p]
@@ -110,6 +111,23 @@ class ReferenceModel:
     def set_slimmable_size(self, value: float) -> None:
         if self._lib.namref_set_slimmable_size(self._h, float(value)) != 0:
             raise ReferenceError_(self._lib.namref_last_error().decode(errors="replace"))
+
+    @property
+    def in_channels(self) -> int:
+        return int(self._lib.namref_in_channels(self._h))
+
+    @property
+    def out_channels(self) -> int:
+        return int(self._lib.namref_out_channels(self._h))
+
+    def process_planar(self, x: np.ndarray) -> np.ndarray:
+        """One DSP::process call on x (in_channels, n) -> (out_channels, n); n <= the last reset's maxBufferSize."""
+        x = np.ascontiguousarray(x, np.float32)
+        assert x.ndim == 2 and x.shape[0] == self.in_channels
+        y = np.zeros((self.out_channels, x.shape[1]), np.float32)
+        if self._lib.namref_process_planar_f32(self._h, x.ctypes.data, y.ctypes.data, x.shape[1]) != 0:
+            raise ReferenceError_(self._lib.namref_last_error().decode(errors="replace"))
+        return y
 
     def run(self, x: np.ndarray, block: int) -> np.ndarray:
         """Mono signal through DSP::process in `block`-frame calls (block <= the last reset's maxBufferSize)."""

@@ -117,6 +117,38 @@ int namref_process_f32(void* p, const float* in, float* out, int n)
   }
 }
 
+// multi-channel: in = [in_channels][n] planes, out = [out_channels][n] planes, through the same DSP::process
+int namref_process_planar_f32(void* p, const float* in, float* out, int n)
+{
+  Handle* h = static_cast<Handle*>(p);
+  try
+  {
+    const int ci = h->dsp->NumInputChannels(), co = h->dsp->NumOutputChannels();
+    std::vector<std::vector<NAM_SAMPLE>> xi((size_t)ci), xo((size_t)co);
+    std::vector<NAM_SAMPLE*> ip((size_t)ci), op((size_t)co);
+    for (int c = 0; c < ci; c++)
+    {
+      xi[(size_t)c].assign(in + (size_t)c * n, in + (size_t)(c + 1) * n);
+      ip[(size_t)c] = xi[(size_t)c].data();
+    }
+    for (int c = 0; c < co; c++)
+    {
+      xo[(size_t)c].assign((size_t)n, 0);
+      op[(size_t)c] = xo[(size_t)c].data();
+    }
+    h->dsp->process(ip.data(), op.data(), n);
+    for (int c = 0; c < co; c++)
+      for (int i = 0; i < n; i++)
+        out[(size_t)c * n + i] = (float)xo[(size_t)c][(size_t)i];
+    return 0;
+  }
+  catch (const std::exception& e)
+  {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 // whole signal in blocks (the tools' protocol: tools/render.cpp:147-176, tools/benchmodel.cpp:128-133)
 int namref_run_f32(void* p, const float* in, float* out, long n_total, int block)
 {

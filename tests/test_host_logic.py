@@ -72,8 +72,12 @@ def test_kernel_selection_and_algorithmic_work():
     multi["config"]["in_channels"] = 2
     multi["config"]["layers"][0]["input_size"] = 2
     multi["weights"] = multi["weights"] + [0.0] * 3  # rechannel 2 -> 3 instead of 1 -> 3
+    info = nb.inspect(multi)  # two input channels but condition_size 1: the reference would trip an Eigen assertion
+    assert info["kernel"] == "unsupported" and "condition_size" in info["reason"]
+    multi["config"]["layers"][0]["condition_size"] = multi["config"]["layers"][1]["condition_size"] = 2
+    multi["weights"] = multi["weights"] + [0.0] * (3 * 2 + 2 * 1)  # one more mixin column per layer (channels 3, 3 | 2)
     info = nb.inspect(multi)
-    assert info["kernel"] == "unsupported" and "mono" in info["reason"]
+    assert info["kernel"] == "generic" and info["in_channels"] == 2 and "mono" in info["reason"]
 
 
 def test_loader_errors_match_reference_behaviour():

@@ -277,11 +277,11 @@ def test_full_size_linearity_free_properties():
 def test_error_behaviour():
     with pytest.raises(nb.NamFileValidationError):
         nb.get_dsp("/nonexistent/model.nam")
-    multi = fx.load_model("wavenet")  # two input channels: valid .nam, no CUDA kernel serves it (mono only)
+    multi = fx.load_model("wavenet")  # two input channels but condition_size 1 (an Eigen assertion in the reference)
     multi["config"]["in_channels"] = 2
     multi["config"]["layers"][0]["input_size"] = 2
     multi["weights"] = multi["weights"] + [0.0] * 3
-    with pytest.raises(nb.UnsupportedModelError, match="mono"):
+    with pytest.raises(nb.UnsupportedModelError, match="condition_size"):
         nb.get_dsp(multi)
     d = nb.get_dsp(fx.load_model("wavenet"), batch=2)
     with pytest.raises(RuntimeError):

@@ -113,3 +113,45 @@ def test_slimmable_container_semantics():
     r.reset(48000.0, 64)
     assert np.max(np.abs(r.run(x, 64) - orc(lite, x))) <= TOL
     r.close()
+
+
+def _multichannel_models():
+    from oracle import nam_config
+
+    def rnd(nam, seed, last=None):
+        n = nam_config.expected_weight_count(nam)
+        w = np.random.default_rng(seed).uniform(-0.35, 0.35, size=n).astype(np.float32)
+        if last is not None:
+            w[-1] = last
+        nam["weights"] = [float(v) for v in w]
+        return nam
+
+    a0 = {"input_size": 2, "condition_size": 2, "head_size": 4, "channels": 5, "kernel_size": 3, "dilations": [1, 2, 4, 9],
+          "activation": "Tanh", "gated": False, "head_bias": False}
+    a1 = {"input_size": 5, "condition_size": 2, "head_size": 3, "channels": 4, "kernel_size": 3, "dilations": [1, 6],
+          "activation": "Tanh", "gated": True, "head_bias": True}
+    yield "wavenet 2 in / 3 out", rnd(fx.make_wavenet_nam([a0, a1], [], head_scale=0.5, in_channels=2), 4, last=0.5)
+    for ci, co, H, nl in ((2, 3, 5, 1), (3, 1, 8, 2)):
+        nam = {"version": "0.5.4", "architecture": "LSTM", "sample_rate": 48000.0,
+               "config": {"in_channels": ci, "out_channels": co, "input_size": ci, "hidden_size": H, "num_layers": nl},
+               "weights": []}
+        yield f"lstm {ci} in / {co} out", rnd(nam, ci * 10 + co)
+
+
+def test_multichannel_models():
+    """in_channels / out_channels != 1 (NAM/wavenet/model.cpp:809-820,888-909; NAM/lstm.cpp:103-125): the oracle's
+    reading of the channel handling against the reference build, DSP::process with channel arrays."""
+    for label, nam in _multichannel_models():
+        r = ref.ReferenceModel.from_dict(nam)
+        o = oracle.OracleModel.from_dict(nam)
+        assert (r.in_channels, r.out_channels) == (o.in_channels, o.out_channels), label
+        r.reset(48000.0, 64)
+        o.reset(48000.0, 64)
+        x = fx.synthetic_batch(r.in_channels, 640, seed=17)
+        for p in range(0, 640, 64):
+            yr = r.process_planar(x[:, p:p + 64])
+            yo = np.atleast_2d(o.process(np.ascontiguousarray(x[:, p:p + 64])))
+            err = float(np.max(np.abs(yr - yo)))
+            assert err <= TOL, f"{label} block at {p}: {err:.3e}"
+        r.close()
+        o.close()
