@@ -74,7 +74,7 @@ typedef struct nam_b200_options
 typedef struct nam_b200_info
 {
   int32_t struct_size;
-  int32_t architecture; /* 1 WaveNet, 2 LSTM, 3 Linear */
+  int32_t architecture; /* 1 WaveNet, 2 LSTM, 3 Linear, 5 ConvNet (4: a SlimmableContainer reports its active sub-model) */
   int32_t in_channels, out_channels;
   int32_t prewarm_samples; /* DSP::GetPrewarmSamples() */
   int32_t max_batch, max_frames; /* max_frames = maxBufferSize of the last reset (0 before) */

@@ -20,13 +20,14 @@ constexpr int kGenMaxHeadConvs = 8;
 constexpr int kGenFilmSites = 8;
 constexpr int kGenTile = 128; // frames per tile == threads per CTA of the general kernel
 
-// y = W x (+ b): W (out x in) row-major at weights[w_off]; b at weights[b_off] or b_off < 0
+// y = W x (+ b): W stored transposed and padded, [in][out_pad] with out_pad = out rounded up to 4 (zeros), 16-byte
+// aligned at weights[w_off]; b (out_pad floats, zero padded) at weights[b_off] or b_off < 0
 struct GMat
 {
   int in, out, w_off, b_off;
 };
 
-// causal dilated convolution; weights [k][out][in], tap 0 = oldest.  The ring keeps the convolution's INPUT
+// causal dilated convolution; weights [k][in][out_pad] (as GMat, per tap), tap 0 = oldest.  The ring keeps the convolution's INPUT
 // vectors of the last ring_mask + 1 >= look-back + kGenTile frames of a stream (a whole tile is written before
 // any tap is read): element (slot, i) at float ring_off + slot * in + i of the stream's state
 struct GConv
@@ -74,6 +75,32 @@ struct GNet
   GConv head_convs[kGenMaxHeadConvs]; // post-stack head (model.cpp:19-103)
 };
 
+// ConvNet (NAM/convnet.cpp): blocks of kernel-2 dilated convolution -> per-channel affine (folded BatchNorm, absent
+// when bn_off < 0) -> activation, then a linear head
+constexpr int kGenMaxBlocks = 48;
+struct GConvNet
+{
+  int in_channels, out_channels, channels, n_blocks;
+  GAct act;
+  GMat head;
+  GConv convs[kGenMaxBlocks];
+  int bn_off[kGenMaxBlocks]; // weights[bn_off ..]: scale[channels] then loc[channels]; -1: no batchnorm
+};
+
+struct ConvNetKernelParams
+{
+  const float* weights;
+  GConvNet net;
+  float* state; // [stream][state_stride]
+  long state_stride;
+  const float* in; // stream s, channel c: in[s * in_stride + c * n_frames ..]
+  float* out;
+  long in_stride, out_stride;
+  int batch, n_frames;
+  uint32_t t_base;
+  int n_weight_floats;
+};
+
 struct GenericKernelParams
 {
   const float* weights;
@@ -88,6 +115,7 @@ struct GenericKernelParams
   long in_stride, out_stride;
   int batch, n_frames;
   uint32_t t_base;
+  int n_weight_floats; // multiple of 4; the kernel keeps the blob in shared memory when it was given the room
 };
 
 } // namespace namb200

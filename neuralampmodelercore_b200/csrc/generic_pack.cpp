@@ -19,6 +19,27 @@ struct Packer
     plan.weights.insert(plan.weights.end(), v.begin(), v.end());
     return off;
   }
+  // 16-byte aligned, padded with zeros to a multiple of 4 floats (the kernel reads float4s)
+  int put4(const std::vector<float>& v)
+  {
+    plan.weights.resize((plan.weights.size() + 3) & ~(size_t)3, 0.0f);
+    const int off = (int)plan.weights.size();
+    plan.weights.insert(plan.weights.end(), v.begin(), v.end());
+    plan.weights.resize((plan.weights.size() + 3) & ~(size_t)3, 0.0f);
+    return off;
+  }
+  // `taps` (out x in) row-major matrices -> [tap][in][out_pad], out_pad = out rounded up to 4: one float4 holds the
+  // weights of four outputs for one input, the layout the kernel's 4-output accumulation wants
+  int put_transposed(const std::vector<float>& w, int taps, int in, int out)
+  {
+    const int op = (out + 3) & ~3;
+    std::vector<float> t((size_t)taps * in * op, 0.0f);
+    for (int k = 0; k < taps; k++)
+      for (int o = 0; o < out; o++)
+        for (int i = 0; i < in; i++)
+          t[((size_t)k * in + i) * op + o] = w[((size_t)k * out + o) * in + i];
+    return put4(t);
+  }
   bool width(int n, const char* what)
   {
     if (n < 1 || n > kGenMaxVec)
@@ -34,12 +55,16 @@ struct Packer
     GMat g{};
     g.in = m.in;
     g.out = m.out;
-    g.w_off = put(m.w);
-    g.b_off = m.bias ? put(m.b) : -1;
     width(m.in, "matrix input width");
     width(m.out, "matrix output width");
-    if ((long)m.w.size() != (long)m.in * m.out && err.empty())
-      err = "internal: 1x1 weight count";
+    if ((long)m.w.size() != (long)m.in * m.out)
+    {
+      if (err.empty())
+        err = "internal: 1x1 weight count";
+      return g;
+    }
+    g.w_off = put_transposed(m.w, 1, m.in, m.out);
+    g.b_off = m.bias ? put4(m.b) : -1;
     plan.macs_per_frame += (double)m.in * m.out / std::max(m.groups, 1);
     return g;
   }
@@ -50,12 +75,16 @@ struct Packer
     g.out = v.out;
     g.kernel = v.kernel;
     g.dilation = v.dilation;
-    g.w_off = put(v.w);
-    g.b_off = v.bias ? put(v.b) : -1;
     width(v.in, "convolution input width");
     width(v.out, "convolution output width");
-    if ((long)v.w.size() != (long)v.kernel * v.in * v.out && err.empty())
-      err = "internal: conv weight count";
+    if ((long)v.w.size() != (long)v.kernel * v.in * v.out)
+    {
+      if (err.empty())
+        err = "internal: conv weight count";
+      return g;
+    }
+    g.w_off = put_transposed(v.w, v.kernel, v.in, v.out);
+    g.b_off = v.bias ? put4(v.b) : -1;
     g.ring_mask = 0;
     g.ring_off = (int)plan.state_floats;
     if (v.kernel > 1)
@@ -217,6 +246,52 @@ GenericPlan plan_generic(const ModelSpec& ms)
   for (const ArraySpec& A : wn.arrays)
     if (A.condition_size != cond_dim)
       return no("condition_size " + std::to_string(A.condition_size) + " != condition width " + std::to_string(cond_dim));
+  if (!pk.err.empty())
+    return no(pk.err);
+  plan.weights.resize((plan.weights.size() + 3) & ~(size_t)3, 0.0f);
+  plan.state_floats = (plan.state_floats + 3) & ~3L;
+  plan.eligible = true;
+  return plan;
+}
+
+GenericPlan plan_convnet(const ModelSpec& ms)
+{
+  GenericPlan plan;
+  auto no = [&plan](const std::string& why) {
+    plan.eligible = false;
+    plan.why_not = why;
+    return plan;
+  };
+  if (ms.arch != Arch::ConvNet)
+    return no("not a ConvNet");
+  const ConvNetSpec& cn = ms.convnet;
+  if ((int)cn.blocks.size() > kGenMaxBlocks)
+    return no(std::to_string(cn.blocks.size()) + " ConvNet blocks (kernel handles up to " + std::to_string(kGenMaxBlocks) + ")");
+  Packer pk{plan, {}};
+  GConvNet& N = plan.convnet;
+  N = GConvNet{};
+  N.in_channels = ms.in_channels;
+  N.out_channels = ms.out_channels;
+  N.channels = cn.channels;
+  N.n_blocks = (int)cn.blocks.size();
+  pk.width(ms.in_channels, "input channels");
+  pk.width(ms.out_channels, "output channels");
+  pk.width(cn.channels, "channels");
+  N.act = pk.act(cn.act);
+  for (size_t i = 0; i < cn.blocks.size() && pk.err.empty(); i++)
+  {
+    const ConvNetSpec::Block& b = cn.blocks[i];
+    N.convs[i] = pk.conv(b.conv);
+    N.bn_off[i] = -1;
+    if (cn.batchnorm)
+    {
+      std::vector<float> sl(b.scale);
+      sl.insert(sl.end(), b.loc.begin(), b.loc.end());
+      N.bn_off[i] = pk.put4(sl);
+      plan.macs_per_frame += cn.channels;
+    }
+  }
+  N.head = pk.mat(cn.head);
   if (!pk.err.empty())
     return no(pk.err);
   plan.weights.resize((plan.weights.size() + 3) & ~(size_t)3, 0.0f);

@@ -777,7 +777,21 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
     gp.batch = batch;
     gp.n_frames = n_frames;
     gp.t_base = m->t_base;
-    wavenet_generic_kernel<<<std::min(batch, 16 * m->sm_count), kGenTile, 0, st>>>(gp);
+    gp.n_weight_floats = (int)((m->n_weight_floats + 3) & ~(size_t)3);
+    const size_t wbytes = (size_t)gp.n_weight_floats * sizeof(float);
+    const int grid_g = std::min(batch, 16 * m->sm_count);
+    if (wbytes <= 200 * 1024)
+    {
+      static bool configured[64] = {false};
+      if (!configured[m->device & 63])
+      {
+        CUDA_CHECK(cudaFuncSetAttribute(wavenet_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured[m->device & 63] = true;
+      }
+      wavenet_generic_kernel<true><<<grid_g, kGenTile, wbytes, st>>>(gp);
+    }
+    else
+      wavenet_generic_kernel<false><<<grid_g, kGenTile, 0, st>>>(gp);
     CUDA_CHECK(cudaGetLastError());
     m->launches++;
     return;
@@ -1023,6 +1037,40 @@ int wavenet_chunk_streams(nam_b200_model* m)
   return 4 * per_sm * m->sm_count;
 }
 
+void launch_convnet(nam_b200_model* m, const float* d_in, float* d_out, int batch, int n_frames, long in_stride,
+                    long out_stride, cudaStream_t st)
+{
+  ConvNetKernelParams kp{};
+  kp.weights = m->d_weights;
+  kp.net = m->gplan.convnet;
+  kp.state = m->d_state;
+  kp.state_stride = m->state_stride;
+  kp.in = d_in;
+  kp.out = d_out;
+  kp.in_stride = in_stride;
+  kp.out_stride = out_stride;
+  kp.batch = batch;
+  kp.n_frames = n_frames;
+  kp.t_base = m->t_base;
+  kp.n_weight_floats = (int)((m->n_weight_floats + 3) & ~(size_t)3);
+  const size_t wbytes = (size_t)kp.n_weight_floats * sizeof(float);
+  const int grid = std::min(batch, 16 * m->sm_count);
+  if (wbytes <= 200 * 1024)
+  {
+    static bool configured[64] = {false};
+    if (!configured[m->device & 63])
+    {
+      CUDA_CHECK(cudaFuncSetAttribute(convnet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured[m->device & 63] = true;
+    }
+    convnet_kernel<true><<<grid, kGenTile, wbytes, st>>>(kp);
+  }
+  else
+    convnet_kernel<false><<<grid, kGenTile, 0, st>>>(kp);
+  CUDA_CHECK(cudaGetLastError());
+  m->launches++;
+}
+
 // Run the hot path on device buffers and advance the stream clock.
 void run_device(nam_b200_model* m, const float* d_in, float* d_out, int batch, int n_frames, long in_stride,
                 long out_stride, cudaStream_t st)
@@ -1032,6 +1080,8 @@ void run_device(nam_b200_model* m, const float* d_in, float* d_out, int batch, i
     case Arch::WaveNet: launch_wavenet(m, d_in, d_out, batch, n_frames, in_stride, out_stride, st); break;
     case Arch::LSTM: launch_lstm(m, d_in, d_out, batch, n_frames, in_stride, out_stride, st); break;
     case Arch::Linear: launch_linear(m, d_in, d_out, batch, n_frames, in_stride, out_stride, st); break;
+    case Arch::ConvNet: launch_convnet(m, d_in, d_out, batch, n_frames, in_stride, out_stride, st); break;
+    default: throw std::runtime_error("no kernel for this architecture");
   }
   m->t_base += (uint32_t)n_frames;
 }
@@ -1279,6 +1329,18 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
         m->variant = 3000;
         break;
       }
+      case Arch::ConvNet:
+      {
+        m->gplan = plan_convnet(m->spec);
+        if (!m->gplan.eligible)
+          return fail(NAM_B200_ERR_UNSUPPORTED, "ConvNet not supported on the CUDA path: " + m->gplan.why_not);
+        blob = m->gplan.weights;
+        m->state_stride = std::max(m->gplan.state_floats, 4L);
+        m->flops_per_frame = 2.0 * m->gplan.macs_per_frame;
+        m->variant = 9500;
+        break;
+      }
+      default: return fail(NAM_B200_ERR_UNSUPPORTED, "no CUDA kernel for architecture " + m->spec.architecture);
     }
     m->n_weight_floats = blob.size();
     const size_t alloc_floats = (blob.size() + 3) & ~(size_t)3;
@@ -1498,6 +1560,19 @@ static int inspect_spec(const ModelSpec& spec, char* out, int64_t capacity)
       state_floats = (long)spec.lstm.num_layers * 2 * spec.lstm.hidden;
       variant = 2000 + spec.lstm.hidden;
     }
+  }
+  else if (spec.arch == Arch::ConvNet)
+  {
+    const GenericPlan gp = plan_convnet(spec);
+    if (gp.eligible)
+    {
+      kernel = "convnet";
+      flops = 2.0 * gp.macs_per_frame;
+      state_floats = gp.state_floats;
+      variant = 9500;
+    }
+    else
+      reason = gp.why_not;
   }
   else
   {

@@ -1,5 +1,7 @@
 #include "nam_model_spec.h"
 
+#include <cmath>
+
 #include <array>
 #include <cctype>
 #include <fstream>
@@ -581,6 +583,59 @@ void build_linear(ModelSpec& ms, const json::Value& config, const std::vector<fl
   ms.prewarm_samples = 0;
 }
 
+// NAM/convnet.cpp:321-335 (config), :172-201 (constructor), :48-60 (block), :14-37 (BatchNorm), :132-153 (head)
+void build_convnet(ModelSpec& ms, const json::Value& config, const std::vector<float>& weights, const LoadOptions& opts)
+{
+  ConvNetSpec& cn = ms.convnet;
+  cn.channels = config.at("channels").as_int("channels");
+  cn.batchnorm = config.at("batchnorm").as_bool("batchnorm");
+  cn.groups = config.value_int("groups", 1);
+  cn.act = parse_activation(config.at("activation"), opts);
+  ms.in_channels = config.value_int("in_channels", 1);
+  ms.out_channels = config.value_int("out_channels", 1);
+  if (cn.channels <= 0 || ms.in_channels <= 0 || ms.out_channels <= 0)
+    throw std::runtime_error("ConvNet: bad configuration");
+  std::vector<int> dilations;
+  for (const auto& d : config.at("dilations").items("dilations"))
+    dilations.push_back(d.as_int("dilations[]"));
+  if (dilations.empty())
+    throw std::runtime_error("ConvNet: 'dilations' must not be empty");
+  WeightStream ws(weights);
+  const int C = cn.channels;
+  long pw = 1; // convnet.cpp:198-200
+  for (size_t i = 0; i < dilations.size(); i++)
+  {
+    ConvNetSpec::Block b;
+    read_conv1d(b.conv, i == 0 ? ms.in_channels : C, C, 2, !cn.batchnorm, dilations[i], cn.groups, &ws);
+    if (cn.batchnorm)
+    {
+      std::vector<float> mean(C), var(C), w(C), bias(C);
+      for (auto& v : mean)
+        v = ws.next();
+      for (auto& v : var)
+        v = ws.next();
+      for (auto& v : w)
+        v = ws.next();
+      for (auto& v : bias)
+        v = ws.next();
+      const float eps = ws.next();
+      b.scale.resize(C);
+      b.loc.resize(C);
+      for (int j = 0; j < C; j++)
+      {
+        b.scale[j] = w[j] / std::sqrt(eps + var[j]);
+        b.loc[j] = bias[j] - b.scale[j] * mean[j];
+      }
+    }
+    pw += dilations[i];
+    cn.blocks.push_back(std::move(b));
+  }
+  read_conv1x1(cn.head, C, ms.out_channels, true, 1, &ws);
+  if (ws.position() != ws.size())
+    throw std::runtime_error("Didn't touch all the weights when initializing ConvNet");
+  ms.prewarm_samples = (int)pw;
+}
+
 ModelSpec build_spec(const json::Value& root, const LoadOptions& opts)
 {
   if (!root.is_object())
@@ -634,6 +689,11 @@ ModelSpec build_spec(const json::Value& root, const LoadOptions& opts)
   {
     ms.arch = Arch::Linear;
     build_linear(ms, config, weights);
+  }
+  else if (ms.architecture == "ConvNet")
+  {
+    ms.arch = Arch::ConvNet;
+    build_convnet(ms, config, weights, opts);
   }
   else if (ms.architecture == "SlimmableContainer")
   {

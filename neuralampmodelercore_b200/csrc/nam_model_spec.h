@@ -8,6 +8,7 @@
 //   NAM/conv1d.cpp:11-56, NAM/dsp.cpp:363-398      Conv1D / Conv1x1 weight layouts
 //   NAM/lstm.cpp:9-29,70-101,171-181 LSTM
 //   NAM/linear.cpp:61-81,306-316     Linear
+//   NAM/convnet.cpp:14-60,132-201,321-335  ConvNet
 // No CUDA here: everything in this file runs once at load time on the host.
 #pragma once
 
@@ -34,7 +35,8 @@ enum class Arch
   WaveNet = 1,
   LSTM = 2,
   Linear = 3,
-  Container = 4 // "SlimmableContainer": N complete sub-models, one active at a time (NAM/container.cpp)
+  Container = 4, // "SlimmableContainer": N complete sub-models, one active at a time (NAM/container.cpp)
+  ConvNet = 5 // NAM/convnet.cpp: kernel-2 dilated Conv1D -> BatchNorm -> activation blocks, linear head
 };
 
 // Order of nam::activations::ActivationType (NAM/activations.h:26-39)
@@ -181,6 +183,22 @@ struct LinearSpec
   float bias_value = 0.0f;
 };
 
+/// NAM/convnet.cpp: a chain of blocks (kernel-2 dilated Conv1D, BatchNorm folded to y = x * scale + loc, activation)
+/// and a linear head.
+struct ConvNetSpec
+{
+  int channels = 0, groups = 1;
+  bool batchnorm = false;
+  struct Block
+  {
+    Conv1DW conv; // (first: in_channels) -> channels, kernel 2, bias iff no batchnorm (convnet.cpp:55-56)
+    std::vector<float> scale, loc; // BatchNorm::BatchNorm (convnet.cpp:14-37), empty without batchnorm
+  };
+  std::vector<Block> blocks;
+  ActSpec act;
+  Conv1x1W head; // channels -> out_channels, bias (convnet.cpp:132-153)
+};
+
 struct ModelSpec
 {
   Arch arch = Arch::WaveNet;
@@ -194,6 +212,7 @@ struct ModelSpec
   WaveNetSpec wavenet;
   LstmSpec lstm;
   LinearSpec linear;
+  ConvNetSpec convnet;
   // Arch::Container: (max_value, the sub-model's complete .nam document re-serialised); ascending max_value,
   // the last one >= 1.0 (ContainerModel ctor, container.cpp:19-47)
   struct Submodel

@@ -9,7 +9,7 @@
 // dilated taps cross threads, through the convolution's input ring in HBM/L2 (write the tile's columns, barrier,
 // read the taps, barrier).  The models that need this path are small (example_models/wavenet_a2_max.nam:
 // 818 + 1,052 weights) and exist for their features; the throughput families have the fused kernels.  Weights are
-// read through the read-only path at warp-uniform addresses.
+// staged in shared memory (transposed, four outputs per float4) and read at warp-uniform addresses.
 #pragma once
 
 #include "generic_desc.h"
@@ -35,7 +35,7 @@ __device__ __forceinline__ float g_act1(const GenThread& c, const GAct& A, float
     case KACT_HARDTANH: return fminf(fmaxf(x, -1.0f), 1.0f);
     case KACT_RELU: return x > 0.0f ? x : 0.0f;
     case KACT_LEAKYRELU: return x > 0.0f ? x : A.p0 * x;
-    case KACT_PRELU: return x > 0.0f ? x : __ldg(c.w + A.slopes_off + (A.n_slopes == 1 ? 0 : ch)) * x;
+    case KACT_PRELU: return x > 0.0f ? x : c.w[A.slopes_off + (A.n_slopes == 1 ? 0 : ch)] * x;
     case KACT_SIGMOID: return act_sigmoid(x);
     case KACT_SILU: return x * act_sigmoid(x);
     case KACT_HARDSWISH:
@@ -50,22 +50,43 @@ __device__ __forceinline__ float g_act1(const GenThread& c, const GAct& A, float
   }
 }
 
-// y = W x (+ b)
+// acc4[o4] += W_tap x for the outputs o4*4 .. o4*4+3 (weights [in][out_pad], one float4 per input: the four FMA
+// chains of a group are independent, one weight load feeds four of them)
+__device__ __forceinline__ void g_accumulate(const float* __restrict__ wt, const int in, const int op, const float* x,
+                                             float* y)
+{
+  for (int o = 0; o < op; o += 4)
+  {
+    float a0 = y[o], a1 = y[o + 1], a2 = y[o + 2], a3 = y[o + 3];
+    const float4* __restrict__ w4 = reinterpret_cast<const float4*>(wt + o);
+    for (int i = 0; i < in; i++)
+    {
+      const float4 w = w4[(size_t)i * (op >> 2)];
+      const float xi = x[i];
+      a0 = fmaf(w.x, xi, a0);
+      a1 = fmaf(w.y, xi, a1);
+      a2 = fmaf(w.z, xi, a2);
+      a3 = fmaf(w.w, xi, a3);
+    }
+    y[o] = a0, y[o + 1] = a1, y[o + 2] = a2, y[o + 3] = a3;
+  }
+}
+
+// y = W x (+ b).  y is written up to out rounded up to 4 (the padding rows are zero): every caller's buffer has room.
 __device__ __forceinline__ void g_matvec(const GenThread& c, const GMat& M, const float* x, float* y)
 {
-  for (int o = 0; o < M.out; o++)
-  {
-    const float* __restrict__ wr = c.w + M.w_off + o * M.in;
-    float acc = 0.0f;
-    for (int i = 0; i < M.in; i++)
-      acc = fmaf(__ldg(wr + i), x[i], acc);
-    y[o] = (M.b_off >= 0) ? acc + __ldg(c.w + M.b_off + o) : acc;
-  }
+  const int op = (M.out + 3) & ~3;
+  for (int o = 0; o < op; o++)
+    y[o] = 0.0f;
+  g_accumulate(c.w + M.w_off, M.in, op, x, y);
+  if (M.b_off >= 0)
+    for (int o = 0; o < M.out; o++)
+      y[o] += c.w[M.b_off + o];
 }
 
 // causal dilated convolution over the tile: every thread persists its x[t] in the ring, then reads x[t - off]
 // (earlier threads' columns of this tile, or earlier calls'; zeros before the reset).  Called by all threads of the
-// CTA in step (the control flow depends on the descriptors only).
+// CTA in step (the control flow depends on the descriptors only).  Sums run taps oldest -> newest, inputs ascending.
 __device__ __forceinline__ void g_conv(const GenThread& c, const GConv& V, const float* x, float* y)
 {
   const int K = V.kernel;
@@ -79,7 +100,8 @@ __device__ __forceinline__ void g_conv(const GenThread& c, const GConv& V, const
     }
     __syncthreads();
   }
-  for (int o = 0; o < V.out; o++)
+  const int op = (V.out + 3) & ~3;
+  for (int o = 0; o < op; o++)
     y[o] = 0.0f;
   float tap[kGenMaxVec];
   for (int k = 0; k < K; k++)
@@ -93,18 +115,11 @@ __device__ __forceinline__ void g_conv(const GenThread& c, const GConv& V, const
         tap[i] = __ldcg(rs + i);
       src = tap;
     }
-    const float* __restrict__ wk = c.w + V.w_off + (long)k * V.out * V.in;
-    for (int o = 0; o < V.out; o++)
-    {
-      float acc = y[o];
-      for (int i = 0; i < V.in; i++)
-        acc = fmaf(__ldg(wk + o * V.in + i), src[i], acc);
-      y[o] = acc;
-    }
+    g_accumulate(c.w + V.w_off + (long)k * V.in * op, V.in, op, src, y);
   }
   if (V.b_off >= 0)
     for (int o = 0; o < V.out; o++)
-      y[o] += __ldg(c.w + V.b_off + o);
+      y[o] += c.w[V.b_off + o];
   if (K > 1)
     __syncthreads(); // every tap of this tile is read before the next tile's columns land in the ring
 }
@@ -242,10 +257,22 @@ __device__ __forceinline__ void g_net(const GenThread& c, const GNet& N, const G
 // The C ABI's batched entry; persistent CTAs, one stream at a time.  Multi-channel models (model.cpp:809-820,
 // :888-909): stream s's channel c is the plane in[s * in_stride + c * n_frames ..] (out likewise); the input vector
 // is both the first array's layer input and -- unless a condition_dsp produces it -- the condition.
+// WS: the weight blob is staged in shared memory once per CTA (it fits for every model the kernel accepts in
+// practice: example_models/wavenet_a2_max.nam is 7.5 KB); otherwise it is read through the read-only path.
+template <bool WS>
 __global__ void __launch_bounds__(kGenTile) wavenet_generic_kernel(const __grid_constant__ GenericKernelParams p)
 {
+  extern __shared__ float4 gen_smem4[];
   GenThread c;
   c.w = p.weights;
+  if constexpr (WS)
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.weights);
+    for (int i = threadIdx.x; i < p.n_weight_floats / 4; i += kGenTile)
+      gen_smem4[i] = __ldg(src + i);
+    __syncthreads();
+    c.w = reinterpret_cast<const float*>(gen_smem4);
+  }
   const int ci = p.net.in_channels, co = p.net.out_channels;
   for (int s = blockIdx.x; s < p.batch; s += gridDim.x)
   {
@@ -269,6 +296,56 @@ __global__ void __launch_bounds__(kGenTile) wavenet_generic_kernel(const __grid_
       if (c.valid)
         for (int ch = 0; ch < co; ch++)
           yout[(size_t)ch * p.n_frames + f] = out[ch];
+    }
+  }
+}
+
+// ConvNet (NAM/convnet.cpp:204-272): the same frame-per-thread tiling; a block is Conv1D(kernel 2, dilation d) ->
+// BatchNorm as two separate roundings, multiply then add (convnet.cpp:39-46) -> activation (:66-88); head W x + b.
+template <bool WS>
+__global__ void __launch_bounds__(kGenTile) convnet_kernel(const __grid_constant__ ConvNetKernelParams p)
+{
+  extern __shared__ float4 gen_smem4[];
+  GenThread c;
+  c.w = p.weights;
+  if constexpr (WS)
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.weights);
+    for (int i = threadIdx.x; i < p.n_weight_floats / 4; i += kGenTile)
+      gen_smem4[i] = __ldg(src + i);
+    __syncthreads();
+    c.w = reinterpret_cast<const float*>(gen_smem4);
+  }
+  const GConvNet& N = p.net;
+  for (int s = blockIdx.x; s < p.batch; s += gridDim.x)
+  {
+    c.st = p.state + (size_t)s * p.state_stride;
+    const float* __restrict__ xin = p.in + (size_t)s * p.in_stride;
+    float* __restrict__ yout = p.out + (size_t)s * p.out_stride;
+    for (int t0 = 0; t0 < p.n_frames; t0 += kGenTile)
+    {
+      const int f = t0 + (int)threadIdx.x;
+      c.valid = f < p.n_frames;
+      c.t = p.t_base + (uint32_t)f;
+      float x[kGenMaxVec], z[kGenMaxVec];
+      for (int ch = 0; ch < N.in_channels; ch++)
+        x[ch] = c.valid ? __ldg(xin + (size_t)ch * p.n_frames + f) : 0.0f;
+      for (int b = 0; b < N.n_blocks; b++)
+      {
+        g_conv(c, N.convs[b], x, z);
+        if (N.bn_off[b] >= 0)
+        {
+          const float* __restrict__ sc = c.w + N.bn_off[b];
+          for (int j = 0; j < N.channels; j++)
+            z[j] = __fadd_rn(__fmul_rn(z[j], sc[j]), sc[N.channels + j]);
+        }
+        for (int j = 0; j < N.channels; j++)
+          x[j] = g_act1(c, N.act, z[j], j);
+      }
+      g_matvec(c, N.head, x, z);
+      if (c.valid)
+        for (int ch = 0; ch < N.out_channels; ch++)
+          yout[(size_t)ch * p.n_frames + f] = z[ch];
     }
   }
 }

@@ -12,6 +12,7 @@ Reference behaviour restated here (paths relative to the reference repository):
   * activation config ........................ NAM/activations.cpp:55-130
   * LSTM config .............................. NAM/lstm.cpp:171-181
   * Linear config ............................ NAM/linear.cpp:306-316
+  * ConvNet config ........................... NAM/convnet.cpp:321-335
 
 cfg (int32) schema, consumed sequentially by nam_oracle.c:
   WaveNet : 1, in_channels, n_arrays, with_head,
@@ -23,6 +24,7 @@ cfg (int32) schema, consumed sequentially by nam_oracle.c:
             if with_head: head_channels, head_out_channels, n_kernel_sizes, kernel_sizes..., ACT
   LSTM    : 2, in_channels, out_channels, num_layers, input_size, hidden_size
   Linear  : 3, in_channels, out_channels, receptive_field, bias
+  ConvNet : 4, in_channels, out_channels, channels, n_dilations, dilations..., batchnorm, groups, ACT
   ACT     : type_code, n_params   (the params themselves go to fparams, in order)
 fparams (float32): [head_scale (WaveNet only)] then activation parameters in cfg order.
 """
@@ -36,7 +38,7 @@ from typing import Any, Optional
 
 import numpy as np
 
-ARCH_WAVENET, ARCH_LSTM, ARCH_LINEAR = 1, 2, 3
+ARCH_WAVENET, ARCH_LSTM, ARCH_LINEAR, ARCH_CONVNET = 1, 2, 3, 4
 
 ACT_CODES = {
     "Tanh": 0,
@@ -300,6 +302,11 @@ def flatten(nam: dict) -> FlatModel:
             int(config["receptive_field"]),
             int(bool(config["bias"])),
         ]
+    elif arch == "ConvNet":
+        dil = [int(d) for d in config["dilations"]]
+        cfg += [ARCH_CONVNET, int(config.get("in_channels", 1)), int(config.get("out_channels", 1)),
+                int(config["channels"]), len(dil)] + dil + [int(bool(config["batchnorm"])), int(config.get("groups", 1))]
+        _act(config["activation"], cfg, fp)
     else:
         raise NamConfigError(f"No config parser registered for architecture: {arch}")
     return FlatModel(
@@ -345,6 +352,14 @@ def expected_weight_count(nam: dict) -> int:
         return total + out * H + out
     if arch == "Linear":
         return int(c["receptive_field"]) + int(bool(c["bias"]))
+    if arch == "ConvNet":  # convnet.cpp:48-60 (conv, kernel 2, bias iff no batchnorm), :14-37 (4 x dim + eps), :132-153 head
+        ch, g, bn = int(c["channels"]), int(c.get("groups", 1)), bool(c["batchnorm"])
+        cin, total = int(c.get("in_channels", 1)), 0
+        for _d in c["dilations"]:
+            total += (cin * ch * 2) // g + (4 * ch + 1 if bn else ch)
+            cin = ch
+        out = int(c.get("out_channels", 1))
+        return total + out * ch + out
     if arch != "WaveNet":
         raise NamConfigError(arch)
     fm = flatten({**nam, "weights": []})

@@ -1066,6 +1066,13 @@ struct nam_oracle
   float* lin_w; /* reversed impulse response (NAM/linear.cpp:71-74) */
   float lin_b;
   float* lin_hist; /* in_ch x (rf + max_buf) row per channel */
+  /* convnet (NAM/convnet.cpp) */
+  int cn_blocks, cn_channels, cn_batchnorm;
+  conv1d_t* cn_convs;
+  float *cn_scale, *cn_loc; /* [block][channels] */
+  act_t cn_act;
+  float *cn_head_w, *cn_head_b;
+  float* cn_buf[2]; /* (channels | in_ch) x max_buf, frame-major */
 };
 
 static int parse_array_params(array_params_t* p, cursor_t* c)
@@ -1328,6 +1335,71 @@ static int build_linear(nam_oracle* o, cursor_t* c)
   return 0;
 }
 
+/* ConvNet (NAM/convnet.cpp:172-201 constructor, :48-60 block weights, :14-37 BatchNorm, :132-153 head).
+ * cfg: in_channels, out_channels, channels, n_blocks, dilations..., batchnorm, groups, ACT */
+static int build_convnet(nam_oracle* o, cursor_t* c)
+{
+  o->in_ch = take_i(c);
+  o->out_ch = take_i(c);
+  o->cn_channels = take_i(c);
+  o->cn_blocks = take_i(c);
+  if (c->failed || o->cn_blocks <= 0 || o->cn_blocks > 4096 || o->cn_channels <= 0)
+  {
+    set_err("bad ConvNet config");
+    return -1;
+  }
+  int* dil = (int*)xcalloc((size_t)o->cn_blocks, sizeof(int));
+  for (int i = 0; i < o->cn_blocks; i++)
+    dil[i] = take_i(c);
+  o->cn_batchnorm = take_i(c);
+  const int groups = take_i(c);
+  act_parse(&o->cn_act, c);
+  const int C = o->cn_channels;
+  o->cn_convs = (conv1d_t*)xcalloc((size_t)o->cn_blocks, sizeof(conv1d_t));
+  o->cn_scale = (float*)xcalloc((size_t)o->cn_blocks * C, sizeof(float));
+  o->cn_loc = (float*)xcalloc((size_t)o->cn_blocks * C, sizeof(float));
+  o->prewarm_samples = 1; /* convnet.cpp:198-200 */
+  for (int i = 0; i < o->cn_blocks; i++)
+  {
+    /* "HACK 2 kernel" (convnet.cpp:55-56): kernel size 2, bias only without batchnorm */
+    if (conv1d_init(&o->cn_convs[i], i == 0 ? o->in_ch : C, C, 2, !o->cn_batchnorm, dil[i], groups) != 0)
+    {
+      free(dil);
+      return -1;
+    }
+    conv1d_set_weights(&o->cn_convs[i], c);
+    if (o->cn_batchnorm)
+    {
+      /* running_mean, running_var, weight, bias, eps -> scale = w / sqrt(eps + var), loc = b - scale * mean */
+      float* tmp = (float*)xcalloc((size_t)4 * C, sizeof(float));
+      for (int j = 0; j < 4 * C; j++)
+        tmp[j] = take_w(c);
+      const float eps = take_w(c);
+      for (int j = 0; j < C; j++)
+      {
+        const float sc = tmp[2 * C + j] / sqrtf(eps + tmp[C + j]);
+        o->cn_scale[(size_t)i * C + j] = sc;
+        o->cn_loc[(size_t)i * C + j] = tmp[3 * C + j] - sc * tmp[j];
+      }
+      free(tmp);
+    }
+    o->prewarm_samples += dil[i];
+  }
+  free(dil);
+  o->cn_head_w = (float*)xcalloc((size_t)o->out_ch * C, sizeof(float));
+  o->cn_head_b = (float*)xcalloc((size_t)o->out_ch, sizeof(float));
+  for (int j = 0; j < o->out_ch * C; j++)
+    o->cn_head_w[j] = take_w(c);
+  for (int j = 0; j < o->out_ch; j++)
+    o->cn_head_b[j] = take_w(c);
+  if (c->failed || c->i_w != c->n_w)
+  {
+    set_err("Didn't touch all the weights when initializing ConvNet"); /* convnet.cpp:194-195 */
+    return -1;
+  }
+  return 0;
+}
+
 nam_oracle* nam_oracle_create(const int32_t* cfg, int n_cfg, const float* fparams, int n_fparams,
                               const float* weights, int n_weights, double expected_sample_rate, int fast_tanh,
                               nam_oracle* condition_dsp)
@@ -1352,6 +1424,8 @@ nam_oracle* nam_oracle_create(const int32_t* cfg, int n_cfg, const float* fparam
     rc = build_lstm(o, &c);
   else if (o->arch == NAM_ORACLE_ARCH_LINEAR)
     rc = build_linear(o, &c);
+  else if (o->arch == NAM_ORACLE_ARCH_CONVNET)
+    rc = build_convnet(o, &c);
   else
     set_err("No config parser registered for architecture code %d", o->arch);
   if (rc == 0 && (o->in_ch <= 0 || o->out_ch <= 0))
@@ -1412,6 +1486,19 @@ void nam_oracle_destroy(nam_oracle* o)
   free(o->head_b);
   free(o->lin_w);
   free(o->lin_hist);
+  if (o->cn_convs)
+  {
+    for (int i = 0; i < o->cn_blocks; i++)
+      conv1d_free(&o->cn_convs[i]);
+    free(o->cn_convs);
+    act_free(&o->cn_act);
+  }
+  free(o->cn_scale);
+  free(o->cn_loc);
+  free(o->cn_head_w);
+  free(o->cn_head_b);
+  free(o->cn_buf[0]);
+  free(o->cn_buf[1]);
   free(o);
 }
 
@@ -1469,6 +1556,18 @@ static void set_max_buffer(nam_oracle* o, int mb)
     free(o->lin_hist);
     o->lin_hist = (float*)xcalloc((size_t)o->in_ch * (size_t)(o->rf + mb), sizeof(float));
   }
+  else if (o->arch == NAM_ORACLE_ARCH_CONVNET)
+  {
+    /* ConvNet::SetMaxBufferSize (convnet.cpp:283-292): every block's Conv1D restarts from a zero history */
+    const int wmax = o->cn_channels > o->in_ch ? o->cn_channels : o->in_ch;
+    for (int i = 0; i < o->cn_blocks; i++)
+      conv1d_set_max_buffer(&o->cn_convs[i], mb);
+    for (int k = 0; k < 2; k++)
+    {
+      free(o->cn_buf[k]);
+      o->cn_buf[k] = (float*)xcalloc((size_t)wmax * mb, sizeof(float));
+    }
+  }
 }
 
 static void lstm_cell_step(lstm_cell_t* L, const float* x, int fast)
@@ -1502,8 +1601,15 @@ static void lstm_cell_step(lstm_cell_t* L, const float* x, int fast)
 }
 
 /* Core processing on float planar buffers. */
+static void convnet_process(nam_oracle* o, const float* const* in, float* const* out, int n);
+
 static void process_core(nam_oracle* o, const float* const* in, float* const* out, int n)
 {
+  if (o->arch == NAM_ORACLE_ARCH_CONVNET)
+  {
+    convnet_process(o, in, out, n);
+    return;
+  }
   if (o->arch == NAM_ORACLE_ARCH_WAVENET)
   {
     /* _set_condition_array (model.cpp:809-820) */
@@ -1638,6 +1744,44 @@ static void process_core(nam_oracle* o, const float* const* in, float* const* ou
       memmove(h, h + n, sizeof(float) * (size_t)rf);
     }
   }
+}
+
+/* ConvNet::process (convnet.cpp:204-272): blocks of Conv1D(kernel 2) -> BatchNorm affine (:39-46: multiply, then
+ * add) -> activation (:66-88), then the head W x + b (:155-170) */
+static void convnet_process(nam_oracle* o, const float* const* in, float* const* out, int n)
+{
+  const int C = o->cn_channels;
+  float *cur = o->cn_buf[0], *nxt = o->cn_buf[1];
+  for (int f = 0; f < n; f++)
+    for (int ch = 0; ch < o->in_ch; ch++)
+      cur[(size_t)f * o->in_ch + ch] = in[ch][f];
+  for (int i = 0; i < o->cn_blocks; i++)
+  {
+    conv1d_process(&o->cn_convs[i], cur, nxt, n);
+    if (o->cn_batchnorm)
+    {
+      const float *sc = o->cn_scale + (size_t)i * C, *lc = o->cn_loc + (size_t)i * C;
+      for (int f = 0; f < n; f++)
+        for (int j = 0; j < C; j++)
+        {
+          float v = nxt[(size_t)f * C + j] * sc[j];
+          v = v + lc[j];
+          nxt[(size_t)f * C + j] = v;
+        }
+    }
+    act_apply(&o->cn_act, nxt, (long)C * n, o->fast_tanh);
+    float* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  for (int f = 0; f < n; f++)
+    for (int ch = 0; ch < o->out_ch; ch++)
+    {
+      float acc = 0.0f;
+      for (int j = 0; j < C; j++)
+        acc += o->cn_head_w[(size_t)ch * C + j] * cur[(size_t)f * C + j];
+      out[ch][f] = acc + o->cn_head_b[ch];
+    }
 }
 
 void nam_oracle_process_f32(nam_oracle* o, const float* const* in, float* const* out, int n)
@@ -1837,9 +1981,9 @@ static void* batch_worker(void* arg)
 int nam_oracle_run_batch_mono_f32(const nam_oracle* proto, const float* in, float* out, int batch, long n_total,
                                   int block, int threads)
 {
-  if (proto->in_ch != 1 || proto->out_ch != 1)
+  if (proto->in_ch != 1 || proto->out_ch != 1 || proto->arch == NAM_ORACLE_ARCH_CONVNET)
   {
-    set_err("run_batch_mono: model is not mono");
+    set_err("run_batch_mono: model is not mono (or a ConvNet: no clone support, use one instance per stream)");
     return -1;
   }
   if (block > proto->max_buf)
@@ -1897,9 +2041,9 @@ static void* pbatch_worker(void* arg)
 
 struct nam_oracle_batch* nam_oracle_batch_create(const nam_oracle* proto, int batch)
 {
-  if (proto->in_ch != 1 || proto->out_ch != 1 || batch < 1)
+  if (proto->in_ch != 1 || proto->out_ch != 1 || batch < 1 || proto->arch == NAM_ORACLE_ARCH_CONVNET)
   {
-    set_err("batch_create: model must be mono and batch >= 1");
+    set_err("batch_create: model must be mono (not a ConvNet) and batch >= 1");
     return NULL;
   }
   struct nam_oracle_batch* B = (struct nam_oracle_batch*)xcalloc(1, sizeof(*B));

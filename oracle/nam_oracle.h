@@ -27,7 +27,7 @@ extern "C" {
 
 typedef struct nam_oracle nam_oracle;
 
-enum { NAM_ORACLE_ARCH_WAVENET = 1, NAM_ORACLE_ARCH_LSTM = 2, NAM_ORACLE_ARCH_LINEAR = 3 };
+enum { NAM_ORACLE_ARCH_WAVENET = 1, NAM_ORACLE_ARCH_LSTM = 2, NAM_ORACLE_ARCH_LINEAR = 3, NAM_ORACLE_ARCH_CONVNET = 4 };
 
 /* activation type codes: order of nam::activations::ActivationType (NAM/activations.h:26-39) */
 enum {

@@ -155,3 +155,55 @@ def test_multichannel_models():
             assert err <= TOL, f"{label} block at {p}: {err:.3e}"
         r.close()
         o.close()
+
+
+def _convnet(channels, dilations, batchnorm, activation, seed, in_channels=1, out_channels=1, groups=1):
+    from oracle import nam_config
+
+    nam = {"version": "0.5.4", "architecture": "ConvNet", "sample_rate": 48000.0,
+           "config": {"channels": channels, "dilations": list(dilations), "batchnorm": batchnorm, "activation": activation,
+                      "groups": groups, "in_channels": in_channels, "out_channels": out_channels},
+           "weights": []}
+    n = nam_config.expected_weight_count(nam)
+    rng = np.random.default_rng(seed)
+    w = rng.uniform(-0.4, 0.4, size=n).astype(np.float32)
+    if batchnorm:  # running_var and eps must be positive (convnet.cpp:34): walk the stream like the constructor does
+        pos, cin = 0, in_channels
+        for _d in dilations:
+            pos += (cin * channels * 2) // groups
+            w[pos + channels:pos + 2 * channels] = rng.uniform(0.5, 1.5, size=channels)
+            w[pos + 4 * channels] = 1e-5
+            pos += 4 * channels + 1
+            cin = channels
+    nam["weights"] = [float(v) for v in w]
+    return nam
+
+
+CONVNETS = [
+    dict(channels=8, dilations=[1, 2, 4, 8, 16, 32], batchnorm=True, activation="Tanh", seed=1),
+    dict(channels=5, dilations=[1, 3, 9], batchnorm=False, activation="ReLU", seed=2),
+    dict(channels=6, dilations=[2, 4, 64, 128], batchnorm=True, activation={"type": "LeakyReLU", "negative_slope": 0.05},
+         seed=3, in_channels=2, out_channels=3, groups=1),
+    dict(channels=4, dilations=[1, 2], batchnorm=False, activation="Sigmoid", seed=4, groups=2, in_channels=2),
+]
+
+
+@pytest.mark.parametrize("kw", CONVNETS, ids=[f"convnet{i}" for i in range(len(CONVNETS))])
+@pytest.mark.parametrize("fast", [False, True], ids=["exact_tanh", "fast_tanh"])
+def test_convnet(kw, fast):
+    """NAM/convnet.cpp (kernel-2 dilated Conv1D -> BatchNorm -> activation blocks, linear head): the reference's own
+    tests only assert isfinite (tools/test/test_convnet.cpp), so the oracle's reading is held to the reference build."""
+    nam = _convnet(**kw)
+    r = ref.ReferenceModel.from_dict(nam, fast_tanh=fast)
+    o = oracle.OracleModel.from_dict(nam, fast_tanh=fast)
+    assert (r.in_channels, r.out_channels, r.prewarm_samples) == (o.in_channels, o.out_channels, o.prewarm_samples)
+    r.reset(48000.0, 96)
+    o.reset(48000.0, 96)
+    x = fx.synthetic_batch(r.in_channels, 960, seed=23)
+    for p in range(0, 960, 96):
+        yr = r.process_planar(x[:, p:p + 96])
+        yo = np.atleast_2d(o.process(np.ascontiguousarray(x[:, p:p + 96])))
+        err = float(np.max(np.abs(yr - yo)))
+        assert err <= TOL, f"block at {p}: {err:.3e}"
+    r.close()
+    o.close()
