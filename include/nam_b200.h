@@ -156,6 +156,14 @@ double nam_b200_last_kernel_ms(nam_b200_model* m);
 int nam_b200_inspect_json(const char* nam_json_text, int fast_tanh, char* out, int64_t capacity);
 int nam_b200_inspect_file(const char* nam_path, int fast_tanh, char* out, int64_t capacity);
 
+/* Host-only: the sub-models of a slimmable document -- a "SlimmableContainer" file (NAM/container.cpp) or a WaveNet
+ * whose layer arrays carry {"slimmable": {"method": "slice_channels_uniform"}} (NAM/wavenet/model.cpp:1290-1315,
+ * NAM/wavenet/slimmable.cpp: one sliced plain WaveNet per interval between the ratio breakpoints).  index < 0: returns
+ * the number of sub-models (0 = not slimmable).  Otherwise writes the sub-model's complete .nam document (truncated to
+ * capacity - 1 bytes) and its max_value (nam_b200_set_slimmable_size picks the first sub-model with value <
+ * max_value), and returns the document's full length. */
+int64_t nam_b200_submodel_json(const char* nam_json_text, int index, double* max_value, char* out, int64_t capacity);
+
 /* Thread-local message of the last failing call on this thread. */
 const char* nam_b200_last_error(void);
 

@@ -15,6 +15,7 @@ from .dsp import (  # noqa: F401
     get_dsp,
     inspect,
     measure_fp32_tflops,
+    submodels,
     using_fast_tanh,
 )
 
@@ -24,6 +25,7 @@ __all__ = [
     "DSP",
     "get_dsp",
     "inspect",
+    "submodels",
     "enable_fast_tanh",
     "disable_fast_tanh",
     "using_fast_tanh",

@@ -74,6 +74,7 @@ EXPORTED_SYMBOLS = [
     "nam_b200_measure_fp32_tflops",
     "nam_b200_inspect_json",
     "nam_b200_inspect_file",
+    "nam_b200_submodel_json",
 ]
 
 
@@ -124,6 +125,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.nam_b200_inspect_json.restype = C.c_int
     lib.nam_b200_inspect_file.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int64]
     lib.nam_b200_inspect_file.restype = C.c_int
+    lib.nam_b200_submodel_json.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_double), C.c_char_p, C.c_int64]
+    lib.nam_b200_submodel_json.restype = C.c_int64
     lib.nam_b200_measure_fp32_tflops.argtypes = [C.c_int, C.c_int]
     lib.nam_b200_measure_fp32_tflops.restype = C.c_double
     for name in (

@@ -1637,6 +1637,37 @@ int nam_b200_inspect_file(const char* nam_path, int fast_tanh, char* out, int64_
   }
 }
 
+int64_t nam_b200_submodel_json(const char* nam_json_text, int index, double* max_value, char* out, int64_t capacity)
+{
+  if (!nam_json_text)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null argument");
+  try
+  {
+    LoadOptions lo;
+    const ModelSpec spec = model_spec_from_text(nam_json_text, lo);
+    if (spec.arch != Arch::Container)
+      return index < 0 ? 0 : fail(NAM_B200_ERR_UNSUPPORTED, "model is not slimmable");
+    if (index < 0)
+      return (int64_t)spec.submodels.size();
+    if ((size_t)index >= spec.submodels.size())
+      return fail(NAM_B200_ERR_INVALID_ARGUMENT, "sub-model index out of range");
+    const ModelSpec::Submodel& sm = spec.submodels[(size_t)index];
+    if (max_value)
+      *max_value = sm.max_value;
+    if (out && capacity > 0)
+    {
+      const size_t n = std::min((size_t)capacity - 1, sm.model_json.size());
+      std::memcpy(out, sm.model_json.data(), n);
+      out[n] = 0;
+    }
+    return (int64_t)sm.model_json.size();
+  }
+  catch (const std::exception& ex)
+  {
+    return fail(NAM_B200_ERR_MODEL, ex.what());
+  }
+}
+
 int nam_b200_get_info(const nam_b200_model* m, nam_b200_info* info)
 {
   m = active_model(m);

@@ -1,6 +1,8 @@
 #include "nam_model_spec.h"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdio>
 
 #include <array>
 #include <cctype>
@@ -636,6 +638,322 @@ void build_convnet(ModelSpec& ms, const json::Value& config, const std::vector<f
   ms.prewarm_samples = (int)pw;
 }
 
+
+// ---- "slimmable" WaveNet (model.cpp:1290-1315 dispatch; NAM/wavenet/slimmable.cpp) ----------------------------
+// A WaveNet whose layer arrays carry {"slimmable": {"method": "slice_channels_uniform", ...}} is, in the reference,
+// a SlimmableWavenet: SetSlimmableSize(ratio) picks a channel count per array from its allowed_channels, keeps the
+// FIRST rows / columns of every weight tensor and builds a fresh, smaller WaveNet.  Here it becomes a container of
+// plain WaveNet documents, one per interval between the ratio breakpoints, so the SlimmableContainer machinery
+// (create_common, nam_b200_set_slimmable_size) serves it unchanged.
+bool config_is_slimmable_wavenet(const json::Value& config)
+{
+  if (!config.is_object() || !config.contains("layers") || !config.at("layers").is_array())
+    return false;
+  for (const auto& lc : config.at("layers").items("layers"))
+  {
+    if (!lc.is_object() || !lc.contains("slimmable") || !lc.at("slimmable").is_object())
+      continue;
+    const json::Value& m = lc.at("slimmable").get("method");
+    const std::string method = m.is_string() ? m.as_string() : std::string();
+    if (method != "slice_channels_uniform")
+    {
+      if (!method.empty())
+        throw std::runtime_error("SlimmableWavenet: unsupported slimmable method '" + method + "'");
+      continue;
+    }
+    return true;
+  }
+  return false;
+}
+
+// reads the full weight stream tensor by tensor and keeps the leading rows / columns (slimmable.cpp:20-69)
+class WeightSlicer
+{
+public:
+  WeightSlicer(const std::vector<float>& full, std::vector<float>& slim)
+  : _full(full)
+  , _slim(slim)
+  {
+  }
+  // (out x in x taps) weights, tap innermost, then an optional bias of `out`
+  void tensor(int out, int in, int taps, int keep_out, int keep_in, bool bias)
+  {
+    for (int o = 0; o < out; o++)
+      for (int i = 0; i < in; i++)
+        for (int k = 0; k < taps; k++)
+        {
+          const float w = next();
+          if (o < keep_out && i < keep_in)
+            _slim.push_back(w);
+        }
+    if (bias)
+      for (int o = 0; o < out; o++)
+      {
+        const float b = next();
+        if (o < keep_out)
+          _slim.push_back(b);
+      }
+  }
+  void copy(int n)
+  {
+    for (int i = 0; i < n; i++)
+      _slim.push_back(next());
+  }
+  bool done() const { return _pos == _full.size(); }
+
+private:
+  float next()
+  {
+    if (_pos >= _full.size())
+      throw std::runtime_error("SlimmableWavenet: weight stream too short");
+    return _full[_pos++];
+  }
+  const std::vector<float>& _full;
+  std::vector<float>& _slim;
+  size_t _pos = 0;
+};
+
+int slim_bottleneck(const ArraySpec& A, int new_channels)
+{
+  if (!A.l1x1_active)
+    return new_channels; // bottleneck must equal channels when layer1x1 is inactive (slimmable.cpp:81-86)
+  return std::max(1, A.bottleneck * new_channels / A.channels);
+}
+
+// extract_slimmed_weights (slimmable.cpp:133-262), in the weight-stream order of the WaveNet constructor
+std::vector<float> slice_wavenet_weights(const WaveNetSpec& wn, const std::vector<float>& full, const std::vector<int>& target)
+{
+  std::vector<float> slim;
+  WeightSlicer ws(full, slim);
+  const int n_arrays = (int)wn.arrays.size();
+  for (int a = 0; a < n_arrays; a++)
+  {
+    const ArraySpec& A = wn.arrays[(size_t)a];
+    if (A.head_kernel != 1)
+      throw std::runtime_error("SlimmableWavenet: head rechannel kernel_size must be 1 (slimming with head kernel_size > 1 "
+                               "is not implemented)");
+    if (A.groups_input != 1)
+      throw std::runtime_error("SlimmableWavenet: groups_input > 1 not supported");
+    if (A.groups_input_mixin != 1)
+      throw std::runtime_error("SlimmableWavenet: groups_input_mixin > 1 not supported");
+    if (A.l1x1_active && A.l1x1_groups != 1)
+      throw std::runtime_error("SlimmableWavenet: layer1x1 groups > 1 not supported");
+    if (A.h1x1_active && A.h1x1_groups != 1)
+      throw std::runtime_error("SlimmableWavenet: head1x1 groups > 1 not supported");
+    const int C = A.channels, B = A.bottleneck, c = target[(size_t)a], b = slim_bottleneck(A, c), cond = A.condition_size;
+    const int in_keep = (a == 0) ? A.input_size : target[(size_t)a - 1];
+    const int head_keep = (a + 1 < n_arrays) ? target[(size_t)a + 1] : A.head_size;
+    const int HO = A.h1x1_active ? A.h1x1_out : B, ho = A.h1x1_active ? A.h1x1_out : b;
+    ws.tensor(C, A.input_size, 1, c, in_keep, false); // rechannel
+    for (const LayerSpec& L : A.layers)
+    {
+      const int mult = (L.gating != Gating::None) ? 2 : 1;
+      const int BG = mult * B, bg = mult * b;
+      ws.tensor(BG, C, L.conv.kernel, bg, c, true); // conv
+      ws.tensor(BG, cond, 1, bg, cond, false); // input mixin
+      if (A.l1x1_active)
+        ws.tensor(C, B, 1, c, b, true);
+      if (A.h1x1_active)
+        ws.tensor(A.h1x1_out, B, 1, A.h1x1_out, b, true);
+      // the eight FiLM sites in weight-stream order; the kept rows are the LEADING rows of the (scale | shift) stack,
+      // exactly as the reference slices them (slimmable.cpp:186-254)
+      const int full_dim[F_COUNT] = {C, BG, cond, BG, BG, B, C, A.h1x1_out};
+      const int keep_dim[F_COUNT] = {c, bg, cond, bg, bg, b, c, A.h1x1_out};
+      for (int f = 0; f < F_COUNT; f++)
+      {
+        const FilmSpec& F = L.film[f];
+        if (!F.active || (f == F_L1X1_POST && !A.l1x1_active) || (f == F_H1X1_POST && !A.h1x1_active))
+          continue;
+        const int m2 = F.shift ? 2 : 1;
+        ws.tensor(m2 * full_dim[f], cond, 1, m2 * keep_dim[f], cond, true);
+      }
+    }
+    ws.tensor(A.head_size, HO, 1, head_keep, ho, A.head_bias); // head rechannel
+  }
+  ws.copy(1); // head_scale
+  if (!ws.done())
+    throw std::runtime_error("SlimmableWavenet: weight stream longer than the configuration implies");
+  return slim;
+}
+
+std::string json_number(double v)
+{
+  char buf[40];
+  std::snprintf(buf, sizeof(buf), "%.17g", v);
+  return buf;
+}
+
+// one layer-array config with its channel counts replaced and "slimmable" cleared (modify_params_for_channels,
+// slimmable.cpp:268-295)
+std::string slim_layer_json(const json::Value& lc, int channels, int bottleneck, int input_size, int head_size)
+{
+  std::string out = "{";
+  bool first = true, saw_bottleneck = false;
+  auto emit = [&](const std::string& key, const std::string& value) {
+    out += (first ? "\"" : ", \"") + key + "\": " + value;
+    first = false;
+  };
+  for (const auto& kv : lc.members())
+  {
+    if (kv.first == "channels")
+      emit(kv.first, std::to_string(channels));
+    else if (kv.first == "bottleneck")
+    {
+      emit(kv.first, std::to_string(bottleneck));
+      saw_bottleneck = true;
+    }
+    else if (kv.first == "input_size")
+      emit(kv.first, std::to_string(input_size));
+    else if (kv.first == "head_size")
+      emit(kv.first, std::to_string(head_size));
+    else if (kv.first == "slimmable")
+      emit(kv.first, "null");
+    else if (kv.first == "head" && kv.second.is_object())
+    {
+      std::string h = "{";
+      bool hf = true;
+      for (const auto& hk : kv.second.members())
+      {
+        h += (hf ? "\"" : ", \"") + hk.first + "\": " + (hk.first == "out_channels" ? std::to_string(head_size) : hk.second.dump());
+        hf = false;
+      }
+      emit(kv.first, h + "}");
+    }
+    else
+      emit(kv.first, kv.second.dump());
+  }
+  if (!saw_bottleneck)
+    emit("bottleneck", std::to_string(bottleneck));
+  return out + "}";
+}
+
+void build_slimmable_wavenet(ModelSpec& ms, const json::Value& root, const json::Value& config,
+                             const std::vector<float>& weights, const LoadOptions& opts)
+{
+  // the full-size network: validates the configuration and the weight count, gives every tensor's dimensions
+  ModelSpec full = ms;
+  build_wavenet(full, config, weights, opts);
+  const WaveNetSpec& wn = full.wavenet;
+  const auto& layers_json = config.at("layers").items("layers");
+  const size_t n_arrays = wn.arrays.size();
+  // per-array allowed channel counts (SlimmableWavenetConfig::create, slimmable.cpp:540-571)
+  std::vector<std::vector<int>> allowed(n_arrays);
+  bool any = false;
+  for (size_t i = 0; i < n_arrays; i++)
+  {
+    const json::Value& lc = layers_json[i];
+    if (!lc.contains("slimmable") || !lc.at("slimmable").is_object())
+      continue;
+    const json::Value& sc = lc.at("slimmable");
+    const json::Value& mj = sc.get("method");
+    const std::string method = mj.is_string() ? mj.as_string() : std::string();
+    if (method != "slice_channels_uniform")
+      throw std::runtime_error("SlimmableWavenet: unsupported slimmable method '" + method + "'");
+    const json::Value& kw = sc.get("kwargs");
+    if (kw.is_object() && kw.contains("allowed_channels"))
+      for (const auto& ch : kw.at("allowed_channels").items("allowed_channels"))
+        allowed[i].push_back(ch.as_int("allowed_channels[]"));
+    else
+      for (int c = 1; c <= wn.arrays[i].channels; c++)
+        allowed[i].push_back(c);
+    // constructor checks (slimmable.cpp:368-388)
+    for (size_t j = 1; j < allowed[i].size(); j++)
+      if (allowed[i][j] <= allowed[i][j - 1])
+        throw std::runtime_error("SlimmableWavenet: allowed_channels must be sorted ascending");
+    if (!allowed[i].empty())
+    {
+      any = true;
+      if (allowed[i].back() != wn.arrays[i].channels)
+        throw std::runtime_error(
+          "SlimmableWavenet: last allowed_channels entry must equal the full channel count for that array");
+      if (allowed[i].front() < 1)
+        throw std::runtime_error("SlimmableWavenet: allowed_channels must be positive");
+    }
+  }
+  if (!any)
+    throw std::runtime_error("SlimmableWavenet: at least one layer array must have allowed_channels");
+  if (wn.with_head)
+    throw std::runtime_error("SlimmableWavenet: post-stack head is not supported");
+
+  // ratio breakpoints i / len over all arrays (get_ratio_breakpoints, slimmable.cpp:111-125)
+  std::vector<double> bps;
+  for (const auto& al : allowed)
+    for (size_t i = 1; i < al.size(); i++)
+      bps.push_back((double)i / (double)al.size());
+  std::sort(bps.begin(), bps.end());
+  bps.erase(std::unique(bps.begin(), bps.end()), bps.end());
+  auto channels_at = [&](double ratio) { // ratio_to_channels (slimmable.cpp:104-109) per array
+    std::vector<int> t(n_arrays);
+    for (size_t i = 0; i < n_arrays; i++)
+    {
+      const auto& al = allowed[i];
+      if (al.empty())
+        t[i] = wn.arrays[i].channels;
+      else
+        t[i] = al[(size_t)std::min((int)std::floor(ratio * (double)al.size()), (int)al.size() - 1)];
+    }
+    return t;
+  };
+
+  ms.arch = Arch::Container;
+  ms.in_channels = full.in_channels;
+  ms.out_channels = full.out_channels;
+  ms.prewarm_samples = 0; // SlimmableWavenet::GetPrewarmSamples (slimmable.h:71): the active model prewarms itself
+  for (size_t k = 0; k <= bps.size(); k++)
+  {
+    const double lo = (k == 0) ? 0.0 : bps[k - 1], hi = (k == bps.size()) ? 1.0 : bps[k];
+    const std::vector<int> target = channels_at(0.5 * (lo + hi));
+    ModelSpec::Submodel sm;
+    // nam_b200_set_slimmable_size picks the first sub-model with value < max_value; the reference evaluates
+    // floor(value * len) at the breakpoint itself: where rounding puts that below the breakpoint's own index the
+    // breakpoint value still belongs to this interval
+    sm.max_value = (k == bps.size()) ? 1.0 : hi;
+    if (k < bps.size() && channels_at(hi) == target)
+      sm.max_value = std::nextafter(hi, 2.0);
+    bool is_full = true;
+    for (size_t i = 0; i < n_arrays; i++)
+      is_full = is_full && target[i] == wn.arrays[i].channels;
+    const std::vector<float> w = is_full ? weights : slice_wavenet_weights(wn, weights, target);
+    std::string cfg = "{";
+    bool first = true;
+    for (const auto& kv : config.members())
+    {
+      cfg += first ? "\"" : ", \"";
+      first = false;
+      cfg += kv.first + "\": ";
+      if (kv.first != "layers")
+      {
+        cfg += kv.second.dump();
+        continue;
+      }
+      cfg += "[";
+      for (size_t i = 0; i < n_arrays; i++)
+      {
+        const ArraySpec& A = wn.arrays[i];
+        const int in_size = (i == 0) ? A.input_size : target[i - 1];
+        const int head_size = (i + 1 < n_arrays) ? target[i + 1] : A.head_size;
+        cfg += (i ? ", " : "") + slim_layer_json(layers_json[i], target[i], slim_bottleneck(A, target[i]), in_size, head_size);
+      }
+      cfg += "]";
+    }
+    cfg += "}";
+    std::string doc = "{";
+    for (const auto& kv : root.members())
+      if (kv.first != "config" && kv.first != "weights")
+        doc += "\"" + kv.first + "\": " + kv.second.dump() + ", ";
+    doc += "\"config\": " + cfg + ", \"weights\": [";
+    for (size_t i = 0; i < w.size(); i++)
+    {
+      char buf[32];
+      std::snprintf(buf, sizeof(buf), "%s%.9g", i ? ", " : "", (double)w[i]);
+      doc += buf;
+    }
+    doc += "]}";
+    sm.model_json = std::move(doc);
+    ms.submodels.push_back(std::move(sm));
+  }
+}
+
 ModelSpec build_spec(const json::Value& root, const LoadOptions& opts)
 {
   if (!root.is_object())
@@ -675,7 +993,9 @@ ModelSpec build_spec(const json::Value& root, const LoadOptions& opts)
     ms.output_level = extract("output_level_dbu");
   }
   const json::Value& config = root.at("config");
-  if (ms.architecture == "WaveNet")
+  if (ms.architecture == "WaveNet" && config_is_slimmable_wavenet(config))
+    build_slimmable_wavenet(ms, root, config, weights, opts);
+  else if (ms.architecture == "WaveNet")
   {
     ms.arch = Arch::WaveNet;
     build_wavenet(ms, config, weights, opts);

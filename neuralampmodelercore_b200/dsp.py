@@ -334,6 +334,30 @@ def inspect(config, fast_tanh: Optional[bool] = None) -> dict:
     return json.loads(buf.value.decode())
 
 
+def submodels(config) -> list:
+    """Host-only: the sub-models of a slimmable document as [(max_value, .nam dict), ...] -- the entries of a
+    SlimmableContainer file, or the sliced plain WaveNets a "slimmable" WaveNet (NAM/wavenet/slimmable.cpp) stands for.
+    [] for a model that is not slimmable.  Needs no GPU."""
+    import json
+
+    lib = _capi.load()
+    text = (Path(config).read_text() if isinstance(config, os.PathLike) or (isinstance(config, str) and not config.lstrip().startswith("{"))
+            else (config if isinstance(config, str) else json.dumps(config))).encode()
+    n = lib.nam_b200_submodel_json(text, -1, None, None, 0)
+    if n < 0:
+        _raise(int(n), lib)
+    out = []
+    for i in range(int(n)):
+        mv = C.c_double()
+        size = lib.nam_b200_submodel_json(text, i, C.byref(mv), None, 0)
+        if size < 0:
+            _raise(int(size), lib)
+        buf = C.create_string_buffer(int(size) + 1)
+        lib.nam_b200_submodel_json(text, i, C.byref(mv), buf, len(buf))
+        out.append((mv.value, json.loads(buf.value.decode())))
+    return out
+
+
 def measure_fp32_tflops(device: int = -1, packed: bool = True) -> float:
     """Measured FP32 FMA throughput of the device (the compute roofline of the fused kernel)."""
     return float(_capi.load().nam_b200_measure_fp32_tflops(int(device), int(packed)))

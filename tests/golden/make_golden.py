@@ -37,6 +37,7 @@ MODELS = {
     "lstm": "lstm.nam",
     "wavenet_condition_dsp": "wavenet_condition_dsp.nam",
     "wavenet_a2_max": "wavenet_a2_max.nam",
+    "slimmable_wavenet": "slimmable_wavenet.nam",
 }
 # sub-models of the SlimmableContainer example (A2.nam): the plain WaveNets inside it
 A2_SUBMODELS = {"a2_lite": 0, "a2_full": 1}

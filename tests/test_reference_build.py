@@ -207,3 +207,62 @@ def test_convnet(kw, fast):
         assert err <= TOL, f"block at {p}: {err:.3e}"
     r.close()
     o.close()
+
+
+def _slimmable_models():
+    """(label, nam) pairs: the reference's own example and a two-array model that exercises every slicing rule of
+    NAM/wavenet/slimmable.cpp:133-262 (gated conv, bottleneck != channels, head1x1, FiLM with and without shift)."""
+    from oracle import nam_config
+
+    yield "example_models/slimmable_wavenet.nam", fx.load_model("slimmable_wavenet")
+
+    def film(active=True, shift=True):
+        return {"active": active, "shift": shift, "groups": 1}
+
+    slim = lambda allowed: {"method": "slice_channels_uniform", "kwargs": {"allowed_channels": allowed}}  # noqa: E731
+    a0 = {"input_size": 1, "condition_size": 1, "channels": 6, "bottleneck": 4, "head_size": 4, "head_bias": False,
+          "kernel_sizes": [3, 2, 3], "dilations": [1, 2, 5], "activation": "Tanh",
+          "gating_mode": ["gated", "none", "blended"], "secondary_activation": ["Sigmoid", "Sigmoid", "Sigmoid"],
+          "layer1x1": {"active": True, "groups": 1}, "head1x1": {"active": True, "out_channels": 5, "groups": 1},
+          "conv_pre_film": film(), "conv_post_film": film(shift=False), "input_mixin_pre_film": film(),
+          "activation_post_film": film(), "layer1x1_post_film": film(shift=False), "head1x1_post_film": film(),
+          "slimmable": slim([2, 4, 6])}
+    a1 = {"input_size": 6, "condition_size": 1, "channels": 4, "head_size": 1, "head_bias": True, "kernel_size": 3,
+          "dilations": [1, 4], "activation": "ReLU", "gating_mode": "none", "slimmable": slim([1, 4])}
+    nam = fx.make_wavenet_nam([a0, a1], [], head_scale=0.3, version="0.7.0")
+    nam["config"]["layers"][0]["head_size"] = 4  # feeds array 1 (channels 4)
+    n = nam_config.expected_weight_count(nam)
+    w = np.random.default_rng(77).uniform(-0.4, 0.4, size=n).astype(np.float32)
+    w[-1] = 0.3
+    nam["weights"] = [float(v) for v in w]
+    yield "two arrays, gated / blended, head1x1, FiLM", nam
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_slimmable_wavenet_slicing(case):
+    """A WaveNet with "slimmable" layer arrays is a SlimmableWavenet in the reference (model.cpp:1290-1315): the PRODUCT's
+    loader turns it into one sliced plain WaveNet per ratio interval (nam_b200_submodel_json, host only).  Every such
+    document, run by the oracle, must equal the reference build after SetSlimmableSize(ratio) -- at interval midpoints,
+    at the breakpoints themselves and at 0 / 1."""
+    import neuralampmodelercore_b200 as nb
+
+    label, nam = list(_slimmable_models())[case]
+    subs = nb.submodels(nam)
+    assert len(subs) >= 2 and subs[-1][0] >= 1.0
+    r0 = ref.ReferenceModel.from_dict(nam)
+    x = fx.synthetic_batch(1, 1500, seed=41)[0]
+    bps = [mv for mv, _ in subs[:-1]]
+    ratios = sorted({0.0, 1.0, *bps, *[(a + b) / 2 for a, b in zip([0.0] + bps, bps + [1.0])]})
+    for val in ratios:
+        r = ref.ReferenceModel.from_dict(nam)
+        r.reset(48000.0, 64)
+        r.set_slimmable_size(val)
+        yr = r.run(x, 64)
+        r.close()
+        idx = next((i for i, (mv, _) in enumerate(subs) if val < mv), len(subs) - 1)
+        o = oracle.OracleModel.from_dict(subs[idx][1])
+        o.reset(48000.0, 64)
+        yo = o.run(x, 64)
+        o.close()
+        assert _rel(float(np.max(np.abs(yr - yo))), yr) <= TOL, f"{label}: ratio {val} -> sub-model {idx}"
+    r0.close()

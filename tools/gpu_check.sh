@@ -3,7 +3,7 @@
 # usage (from the build container): gpurun --timeout 1500 -- 'bash tools/gpu_check.sh TAG'
 TAG=${1:-x}
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_tile_parallel_gpu.py tests/test_multichannel_gpu.py tests/test_convnet_gpu.py tests/test_generic_kernel_gpu.py -q -m gpu 2>&1 | tail -30 > gpurun_out/tests_new_$TAG.log
+timeout 300 python -m pytest tests/test_tile_parallel_gpu.py tests/test_multichannel_gpu.py tests/test_convnet_gpu.py tests/test_slimmable_wavenet_gpu.py tests/test_generic_kernel_gpu.py -q -m gpu 2>&1 | tail -30 > gpurun_out/tests_new_$TAG.log
 cat gpurun_out/tests_new_$TAG.log
 timeout 700 python -m pytest tests -q -m gpu -x 2>&1 | tail -15 > gpurun_out/tests_all_$TAG.log
 cat gpurun_out/tests_all_$TAG.log
