@@ -114,6 +114,14 @@ class DSP:
     def NumOutputChannels(self) -> int:
         return self._info.out_channels
 
+    @property
+    def in_channels(self) -> int:
+        return self._info.in_channels
+
+    @property
+    def out_channels(self) -> int:
+        return self._info.out_channels
+
     def GetPrewarmSamples(self) -> int:
         return self._info.prewarm_samples
 

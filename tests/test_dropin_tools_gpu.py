@@ -116,3 +116,14 @@ def test_reference_tools_on_a_slimmable_container(tmp_path):
     m = oracle.OracleModel.from_dict(fx.load_model("a2_lite"))
     m.reset(48000.0, 64)
     assert np.max(np.abs(_read_wav_f32(wav_out) - m.run(x, 64))) <= 1e-5
+
+
+@pytest.mark.parametrize("bufsize", [16, 64, 512])
+def test_reference_benchmodel_bufsize_runs_unchanged(tmp_path, bufsize):
+    """tools/benchmodel_bufsize.cpp:19-110: model, buffer size, iterations -> one CSV line 'bufsize,avg_microseconds'."""
+    exe = _need("benchmodel_bufsize")
+    r = subprocess.run([str(exe), str(_write_nam(tmp_path, "wavenet_a1_standard")), str(bufsize), "50"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    b, us = r.stdout.strip().splitlines()[-1].split(",")
+    assert int(b) == bufsize and float(us) > 0.0

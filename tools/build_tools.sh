@@ -2,7 +2,7 @@
 # Build the host tools into build/ (git-ignored, travels to the GPU box):
 #   build/nam_b200_bench        our own C++ tool over the C ABI
 #   build/microbench            design-constant micro-benchmarks (tools/microbench.cu)
-#   build/ref_tools/{benchmodel,loadmodel,render}   -- only when the reference tree is mounted: the
+#   build/ref_tools/{benchmodel,benchmodel_bufsize,loadmodel,render}   -- only when the reference tree is mounted: the
 #       reference's OWN tool sources, compiled UNCHANGED from where they lie, against include/NAM/*.h and
 #       libnam_b200.so.  This is the drop-in proof: nothing of the reference is copied into the repo.
 set -euo pipefail
@@ -18,7 +18,7 @@ fi
 REF=${NAM_REFERENCE:-/root/reference}
 if [ -d "$REF/tools" ]; then
   mkdir -p "$ROOT/build/ref_tools"
-  for t in benchmodel loadmodel render; do
+  for t in benchmodel benchmodel_bufsize loadmodel render; do
     "$CXX" -std=c++20 -O2 -I"$ROOT/include" -o "$ROOT/build/ref_tools/$t" "$REF/tools/$t.cpp" \
       -L"$LIBDIR" -lnam_b200 -Wl,-rpath,'$ORIGIN/../../neuralampmodelercore_b200/lib'
   done
