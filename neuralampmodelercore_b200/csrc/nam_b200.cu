@@ -360,7 +360,7 @@ struct nam_b200_model
   size_t tile_flags_capacity = 0;
   float* d_hist = nullptr; // lock-step tile-parallel mode: per-call history buffer (WaveNetKernelParams::hist)
   size_t hist_floats = 0;
-  int wn_ctas_ls[3] = {0, 0, 0}; // resident CTAs per SM of the lock-step kernels (kLsGeom)
+  int wn_ctas_ls[2] = {0, 0}; // resident CTAs per SM of the lock-step kernels (kLsGeom)
   int wn_ctas_short[2] = {0, 0}; // same for the short-call (multi-stream tile) geometries 2 / 3
   int wn_geometry = 1; // 0 / 1: index into kWnGeom (FFMA kernel); 2: tensor-core kernel (wavenet_tc.cuh)
   float* d_tc_blob = nullptr; // per-layer B-operand images of the tensor-core kernel
@@ -480,18 +480,19 @@ int occupancy_wavenet_variant(size_t smem)
   return n > 0 ? n : 1;
 }
 
-// lock-step tile-parallel kernels (LS = true), one stream per tile.  A lone CTA's layer step is latency-bound
-// (dependent issue, one or two warps per scheduler), so the first choice gives every thread ONE frame: half the
-// instructions per thread and layer step, twice the warps per tile.
-//   LS geometry 0: 256 threads x 1 frame, tile 256, >= 3 CTAs/SM   (default)
-//   LS geometry 1: 128 threads x 2 frames, tile 256, >= 3 CTAs/SM  (kernel_geometry 1)
-//   LS geometry 2: 256 threads x 2 frames, tile 512, >= 2 CTAs/SM  (kernel_geometry 2; also when tile 256 does not fit)
+// lock-step tile-parallel kernels (LS = true), one stream per tile.
+//   LS geometry 0: 128 threads x 2 frames, tile 256, >= 3 CTAs/SM  (default; kernel_geometry 1)
+//   LS geometry 1: 256 threads x 2 frames, tile 512, >= 2 CTAs/SM  (kernel_geometry 2; also when tile 256 does not fit)
+// (A 256 x 1 geometry -- half the instructions per thread and layer step, twice the warps per tile -- measured slower
+// on both shapes that matter: 37.2 vs 41.2 Msamples/s for one stream in 4096-frame calls, 437 vs 487 for one
+// 96,000-frame call: the weight loads per FFMA2 double.)
 struct LsGeometry
 {
   int nt, s, min_ctas, lq;
   int tile_frames() const { return 1 << lq; }
 };
-constexpr LsGeometry kLsGeom[3] = {{256, 1, 3, 8}, {128, 2, 3, 8}, {256, 2, 2, 9}};
+constexpr int kLsGeoms = 2;
+constexpr LsGeometry kLsGeom[kLsGeoms] = {{128, 2, 3, 8}, {256, 2, 2, 9}};
 
 template <int C0, int C1, int S, int NT, int MINB, int LQ>
 void launch_wavenet_ls_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem, cudaStream_t st)
@@ -523,8 +524,7 @@ int occupancy_wavenet_ls_variant(size_t smem)
 
 #define WN_LS_CASE(C0, C1, FN, ...)                                                                                  \
   case (C0) * 100 + (C1):                                                                                            \
-    return geom == 0 ? FN<C0, C1, 1, 256, 3, 8>(__VA_ARGS__)                                                         \
-                     : (geom == 1 ? FN<C0, C1, 2, 128, 3, 8>(__VA_ARGS__) : FN<C0, C1, 2, 256, 2, 9>(__VA_ARGS__));
+    return geom == 0 ? FN<C0, C1, 2, 128, 3, 8>(__VA_ARGS__) : FN<C0, C1, 2, 256, 2, 9>(__VA_ARGS__);
 
 #define WN_LS_DISPATCH(FN, ...)                                                                                      \
   switch (c0 * 100 + c1)                                                                                             \
@@ -622,13 +622,11 @@ long wavenet_ls_capacity(nam_b200_model* m, int g)
   return (long)m->wn_ctas_ls[g] * m->sm_count;
 }
 
-// is LS geometry g a candidate under the handle's options?  kernel_geometry 1 / 2 pin LS geometry 1 / 2; the default
-// tries 0 (tile 256) and then 2 (tile 512: half as many CTAs to keep co-resident)
+// is LS geometry g a candidate under the handle's options?  kernel_geometry 1 / 2 pin LS geometry 0 / 1; the default
+// tries 0 (tile 256) and then 1 (tile 512: half as many CTAs to keep co-resident)
 bool wavenet_ls_candidate(const nam_b200_model* m, int g)
 {
-  if (m->opts.kernel_geometry == 0)
-    return g != 1;
-  return g == m->opts.kernel_geometry;
+  return m->opts.kernel_geometry == 0 || g == m->opts.kernel_geometry - 1;
 }
 
 // The LS geometry the lock-step mode would use for (batch, n_frames): the first candidate whose CTAs are all
@@ -637,7 +635,7 @@ int wavenet_ls_geometry(nam_b200_model* m, int batch, int n_frames, int* tiles_o
 {
   if (m->opts.tile_mode != 0 || m->wn_geometry > 1 || m->use_generic)
     return -1;
-  for (int g = 0; g < 3; g++)
+  for (int g = 0; g < kLsGeoms; g++)
   {
     if (!wavenet_ls_candidate(m, g))
       continue;
@@ -661,7 +659,7 @@ void ensure_hist(nam_b200_model* m)
     return;
   const int planes = wavenet_hist_planes(m->plan);
   size_t need = 0, need_flags = 0;
-  for (int g = 0; g < 3; g++)
+  for (int g = 0; g < kLsGeoms; g++)
   {
     if (!wavenet_ls_candidate(m, g))
       continue;

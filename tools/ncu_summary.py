@@ -55,6 +55,7 @@ def main() -> None:
     shdr = src[1]
     ia, isrc, isamp = shdr.index("Instructions Executed"), shdr.index("Source"), shdr.index("# Samples")
     ops, samp = collections.Counter(), collections.Counter()
+    hot = []  # (samples, executed, instruction text): where the stall samples sit
     phases, cur = [], {"instructions": 0, "samples": 0, "ffma2": 0}
     for r in src[2:]:
         if len(r) <= ia:
@@ -65,6 +66,7 @@ def main() -> None:
         n, sp = int(r[ia] or 0), int(r[isamp] or 0)
         ops[op] += n
         samp[op] += sp
+        hot.append((sp, n, s[:70]))
         cur["instructions"] += n
         cur["samples"] += sp
         if op == "FFMA2":
@@ -80,6 +82,8 @@ def main() -> None:
     summary["phases_between_barriers"] = [
         {"instructions_share": round(p["instructions"] / tot, 4), "sample_share": round(p["samples"] / tots, 4),
          "ffma2_share_of_phase": round(p["ffma2"] / max(p["instructions"], 1), 3)} for p in phases if p["instructions"] > tot * 0.002]
+    summary["top_stall_instructions"] = [{"sample_share": round(sp / tots, 4), "executed": n, "sass": t}
+                                         for sp, n, t in sorted(hot, reverse=True)[:24]]
     with open(out_prefix + ".json", "w") as f:
         json.dump(summary, f, indent=1)
     print(json.dumps(summary, indent=1)[:3000])
