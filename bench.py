@@ -428,9 +428,7 @@ def run_b200(args) -> None:
         quick("wavenet_a1_standard_batch1", MODEL, 1, 4096, steps=32)
         quick("wavenet_a1_standard_batch1_wavefront_tiles", MODEL, 1, 4096, steps=32, tile_mode=1)
         quick("wavenet_a1_standard_batch1_one_96000_frame_call", MODEL, 1, 96000, steps=16)
-        quick("wavenet_a1_standard_batch1_one_96000_frame_call_128x2", MODEL, 1, 96000, steps=16, kernel_geometry=1)
         quick("wavenet_a1_standard_batch1_one_96000_frame_call_tile512", MODEL, 1, 96000, steps=16, kernel_geometry=2)
-        quick("wavenet_a1_standard_batch1_128x2", MODEL, 1, 4096, steps=32, kernel_geometry=1)
         quick("wavenet_a1_standard_batch16", MODEL, 16, 4096, steps=16)
         quick("wavenet_a1_standard_batch256", MODEL, 256, 4096)
         quick("wavenet_a1_standard_batch4096_64frame_calls", MODEL, 4096, 64, steps=32)

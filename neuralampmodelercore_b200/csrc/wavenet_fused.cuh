@@ -190,6 +190,18 @@ __device__ __forceinline__ void tile_publish(const TileSync& ts, int step)
 // have published the same step.  The first barrier also orders this CTA's own shared-tile writes before the reads
 // that follow; lanes 0..m-1 poll one predecessor each.
 constexpr int kLsFinalStep = 1 << 20;
+// Spin on a flag with relaxed loads and take the acquire once at the end: an ld.acquire in the loop costs an L1
+// invalidation (CCTL.IVALL) and an error barrier per iteration (profiles/r01h_lockstep_1x96000.json: 9 % + 10 % of the
+// stall samples of the first version).
+__device__ __forceinline__ void ls_spin_until_above(const int* flag, const int step)
+{
+  int v;
+  do
+  {
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+  } while (v <= step);
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
 __device__ __forceinline__ void ls_publish_wait(const TileSync& ts, const int step, const int m)
 {
   __threadfence(); // this thread's hist stores are visible device-wide
@@ -197,14 +209,7 @@ __device__ __forceinline__ void ls_publish_wait(const TileSync& ts, const int st
   if (threadIdx.x == 0)
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ts.mine), "r"(step + 1) : "memory");
   for (int k = threadIdx.x; k < m; k += blockDim.x)
-  {
-    const int* f = ts.mine - 1 - k;
-    int v;
-    do
-    {
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-    } while (v <= step);
-  }
+    ls_spin_until_above(ts.mine - 1 - k, step);
   __syncthreads();
 }
 
@@ -913,14 +918,7 @@ __global__ void __launch_bounds__(NT, MINB) wavenet_fused_kernel(const __grid_co
         // every tile of the stream is done with the rings -> rewrite them from hist for the next call
         ls_publish_wait(ts, kLsFinalStep, 0);
         for (int k = tid; k < p.tiles_per_stream; k += NT)
-        {
-          const int* f = ts.mine - ts.tile_i + k;
-          int v;
-          do
-          {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-          } while (v <= kLsFinalStep);
-        }
+          ls_spin_until_above(ts.mine - ts.tile_i + k, kLsFinalStep);
         __syncthreads();
         ls_write_back<C0, S, NT, LQ>(p, p.arrays[0], state[0], hist0, t0, tabs0, Tv[0]);
         if constexpr (C1 != 0)

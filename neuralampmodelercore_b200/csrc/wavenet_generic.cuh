@@ -50,23 +50,45 @@ __device__ __forceinline__ float g_act1(const GenThread& c, const GAct& A, float
   }
 }
 
-// acc4[o4] += W_tap x for the outputs o4*4 .. o4*4+3 (weights [in][out_pad], one float4 per input: the four FMA
-// chains of a group are independent, one weight load feeds four of them)
+// y[o .. o+3] (= 0 | += ) W_tap x, four outputs at a time (weights [in][out_pad], one float4 per input: the four FMA
+// chains of a group are independent, one weight load feeds four of them); the bias, when given, is added once the sum
+// is complete -- the reference's order (conv1d.cpp:769, dsp.cpp:832-834).  The models that reach this kernel are narrow
+// (wavenet_a2_max.nam: 3..8 wide), so the input loop is kept rolled: an unrolled-by-8 loop with its remainder
+// handling cost more instructions than the arithmetic (profiles/r01h_general_kernel_*: FFMA 14 % of the issue slots).
 __device__ __forceinline__ void g_accumulate(const float* __restrict__ wt, const int in, const int op, const float* x,
-                                             float* y)
+                                             float* y, const bool from_zero, const float* __restrict__ bias)
 {
   for (int o = 0; o < op; o += 4)
   {
-    float a0 = y[o], a1 = y[o + 1], a2 = y[o + 2], a3 = y[o + 3];
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    if (!from_zero)
+      a0 = y[o], a1 = y[o + 1], a2 = y[o + 2], a3 = y[o + 3];
     const float4* __restrict__ w4 = reinterpret_cast<const float4*>(wt + o);
-    for (int i = 0; i < in; i++)
+    const int stride4 = op >> 2;
+    if ((in & 7) == 0)
     {
-      const float4 w = w4[(size_t)i * (op >> 2)];
-      const float xi = x[i];
-      a0 = fmaf(w.x, xi, a0);
-      a1 = fmaf(w.y, xi, a1);
-      a2 = fmaf(w.z, xi, a2);
-      a3 = fmaf(w.w, xi, a3);
+#pragma unroll 8
+      for (int i = 0; i < in; i++)
+      {
+        const float4 w = w4[(size_t)i * stride4];
+        const float xi = x[i];
+        a0 = fmaf(w.x, xi, a0), a1 = fmaf(w.y, xi, a1), a2 = fmaf(w.z, xi, a2), a3 = fmaf(w.w, xi, a3);
+      }
+    }
+    else
+    {
+#pragma unroll 1
+      for (int i = 0; i < in; i++)
+      {
+        const float4 w = w4[(size_t)i * stride4];
+        const float xi = x[i];
+        a0 = fmaf(w.x, xi, a0), a1 = fmaf(w.y, xi, a1), a2 = fmaf(w.z, xi, a2), a3 = fmaf(w.w, xi, a3);
+      }
+    }
+    if (bias != nullptr)
+    {
+      const float4 b = *reinterpret_cast<const float4*>(bias + o);
+      a0 += b.x, a1 += b.y, a2 += b.z, a3 += b.w;
     }
     y[o] = a0, y[o + 1] = a1, y[o + 2] = a2, y[o + 3] = a3;
   }
@@ -75,13 +97,7 @@ __device__ __forceinline__ void g_accumulate(const float* __restrict__ wt, const
 // y = W x (+ b).  y is written up to out rounded up to 4 (the padding rows are zero): every caller's buffer has room.
 __device__ __forceinline__ void g_matvec(const GenThread& c, const GMat& M, const float* x, float* y)
 {
-  const int op = (M.out + 3) & ~3;
-  for (int o = 0; o < op; o++)
-    y[o] = 0.0f;
-  g_accumulate(c.w + M.w_off, M.in, op, x, y);
-  if (M.b_off >= 0)
-    for (int o = 0; o < M.out; o++)
-      y[o] += c.w[M.b_off + o];
+  g_accumulate(c.w + M.w_off, M.in, (M.out + 3) & ~3, x, y, true, M.b_off >= 0 ? c.w + M.b_off : nullptr);
 }
 
 // causal dilated convolution over the tile: every thread persists its x[t] in the ring, then reads x[t - off]
@@ -101,8 +117,6 @@ __device__ __forceinline__ void g_conv(const GenThread& c, const GConv& V, const
     __syncthreads();
   }
   const int op = (V.out + 3) & ~3;
-  for (int o = 0; o < op; o++)
-    y[o] = 0.0f;
   float tap[kGenMaxVec];
   for (int k = 0; k < K; k++)
   {
@@ -115,11 +129,9 @@ __device__ __forceinline__ void g_conv(const GenThread& c, const GConv& V, const
         tap[i] = __ldcg(rs + i);
       src = tap;
     }
-    g_accumulate(c.w + V.w_off + (long)k * V.in * op, V.in, op, src, y);
+    g_accumulate(c.w + V.w_off + (long)k * V.in * op, V.in, op, src, y, k == 0,
+                 (k + 1 == K && V.b_off >= 0) ? c.w + V.b_off : nullptr);
   }
-  if (V.b_off >= 0)
-    for (int o = 0; o < V.out; o++)
-      y[o] += c.w[V.b_off + o];
   if (K > 1)
     __syncthreads(); // every tap of this tile is read before the next tile's columns land in the ring
 }
