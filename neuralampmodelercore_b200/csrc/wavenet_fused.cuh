@@ -190,17 +190,16 @@ __device__ __forceinline__ void tile_publish(const TileSync& ts, int step)
 // have published the same step.  The first barrier also orders this CTA's own shared-tile writes before the reads
 // that follow; lanes 0..m-1 poll one predecessor each.
 constexpr int kLsFinalStep = 1 << 20;
-// Spin on a flag with relaxed loads and take the acquire once at the end: an ld.acquire in the loop costs an L1
-// invalidation (CCTL.IVALL) and an error barrier per iteration (profiles/r01h_lockstep_1x96000.json: 9 % + 10 % of the
-// stall samples of the first version).
+// Spin on a flag with acquire loads.  (Relaxed loads in the loop plus one fence.acq_rel.gpu at the end -- to avoid the
+// L1 invalidation each ld.acquire costs, profiles/r01h_lockstep_* -- measured SLOWER: 407 vs 487 Msamples/s for one
+// 96,000-frame stream; the fence waits for far more than the flag.)
 __device__ __forceinline__ void ls_spin_until_above(const int* flag, const int step)
 {
   int v;
   do
   {
-    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
   } while (v <= step);
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 __device__ __forceinline__ void ls_publish_wait(const TileSync& ts, const int step, const int m)
 {

@@ -50,6 +50,39 @@ __device__ __forceinline__ float g_act1(const GenThread& c, const GAct& A, float
   }
 }
 
+// out[i] = act(in[i]) for i < n, the activation chosen ONCE for the vector (the per-element switch of g_act1 cost
+// more issue slots than the activation itself on the narrow models this kernel serves); in-place allowed
+__device__ __forceinline__ void g_act_vec(const GenThread& c, const GAct& A, const float* in, float* out, const int n)
+{
+  switch (A.type)
+  {
+    case KACT_TANH:
+      for (int i = 0; i < n; i++)
+        out[i] = tanhf(in[i]);
+      break;
+    case KACT_FASTTANH:
+      for (int i = 0; i < n; i++)
+        out[i] = act_fast_tanh(in[i]);
+      break;
+    case KACT_RELU:
+      for (int i = 0; i < n; i++)
+        out[i] = in[i] > 0.0f ? in[i] : 0.0f;
+      break;
+    case KACT_LEAKYRELU:
+      for (int i = 0; i < n; i++)
+        out[i] = in[i] > 0.0f ? in[i] : A.p0 * in[i];
+      break;
+    case KACT_SIGMOID:
+      for (int i = 0; i < n; i++)
+        out[i] = act_sigmoid(in[i]);
+      break;
+    default: // the rarer ones share the scalar implementation
+      for (int i = 0; i < n; i++)
+        out[i] = g_act1(c, A, in[i], i);
+      break;
+  }
+}
+
 // y[o .. o+3] (= 0 | += ) W_tap x, four outputs at a time (weights [in][out_pad], one float4 per input: the four FMA
 // chains of a group are independent, one weight load feeds four of them); the bias, when given, is added once the sum
 // is complete -- the reference's order (conv1d.cpp:769, dsp.cpp:832-834).  The models that reach this kernel are narrow
@@ -183,18 +216,18 @@ __device__ __forceinline__ void g_layer(const GenThread& c, const GLayer& L, flo
 
   // activation (:234-288); the activated block is the first `bottleneck` entries of z
   if (L.gating == 0)
-  {
-    for (int i = 0; i < Z; i++)
-      z[i] = g_act1(c, L.act, z[i], i);
-  }
+    g_act_vec(c, L.act, z, z, Z);
   else
   {
-    for (int i = 0; i < Bn; i++)
-    {
-      const float a = g_act1(c, L.act, z[i], i);
-      const float g = g_act1(c, L.sec, z[Bn + i], i);
-      z[i] = (L.gating == 1) ? a * g : g * a + (1.0f - g) * z[i]; // gating_activations.h:100-113 | :209-227
-    }
+    // (u is free here: the mixin sum has been added to z)
+    g_act_vec(c, L.act, z, u, Bn);
+    g_act_vec(c, L.sec, z + Bn, u + Bn, Bn);
+    if (L.gating == 1)
+      for (int i = 0; i < Bn; i++)
+        z[i] = u[i] * u[Bn + i]; // gating_activations.h:100-113
+    else
+      for (int i = 0; i < Bn; i++)
+        z[i] = u[Bn + i] * u[i] + (1.0f - u[Bn + i]) * z[i]; // :209-227
   }
   if (L.film[5].active)
     g_film(c, L.film[5], z, cond, z);
@@ -351,8 +384,7 @@ __global__ void __launch_bounds__(kGenTile) convnet_kernel(const __grid_constant
           for (int j = 0; j < N.channels; j++)
             z[j] = __fadd_rn(__fmul_rn(z[j], sc[j]), sc[N.channels + j]);
         }
-        for (int j = 0; j < N.channels; j++)
-          x[j] = g_act1(c, N.act, z[j], j);
+        g_act_vec(c, N.act, z, x, N.channels);
       }
       g_matvec(c, N.head, x, z);
       if (c.valid)
