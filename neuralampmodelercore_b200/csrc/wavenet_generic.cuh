@@ -52,7 +52,7 @@ __device__ __forceinline__ float g_act1(const GenThread& c, const GAct& A, float
 
 // out[i] = act(in[i]) for i < n, the activation chosen ONCE for the vector (the per-element switch of g_act1 cost
 // more issue slots than the activation itself on the narrow models this kernel serves); in-place allowed
-__device__ __noinline__ void g_act_vec(const GenThread& c, const GAct& A, const float* in, float* out, const int n)
+__device__ __forceinline__ void g_act_vec(const GenThread& c, const GAct& A, const float* in, float* out, const int n)
 {
   switch (A.type)
   {
@@ -88,11 +88,11 @@ __device__ __noinline__ void g_act_vec(const GenThread& c, const GAct& A, const 
 // is complete -- the reference's order (conv1d.cpp:769, dsp.cpp:832-834).  The models that reach this kernel are narrow
 // (wavenet_a2_max.nam: 3..8 wide), so the input loop is kept rolled: an unrolled-by-8 loop with its remainder
 // handling cost more instructions than the arithmetic (profiles/r01h_general_kernel_*: FFMA 14 % of the issue slots).
-// NOT inlined: it is called from ~20 places of a layer (convolution taps, mixin, 1x1s, eight FiLM sites, twice over for a
-// condition_dsp); inlined, the kernel was 22,000 instructions (350 KB) and the profile showed 6 stall cycles per
-// issued instruction waiting for instruction fetch (profiles/r01i_general_kernel_*: no_instruction).
-__device__ __noinline__ void g_accumulate(const float* __restrict__ wt, const int in, const int op, const float* x,
-                                          float* y, const bool from_zero, const float* __restrict__ bias)
+// (Taking this and the other helpers out of line shrinks the kernel from 22,000 to 3,700 instructions -- the profile
+// shows instruction-fetch stalls, profiles/r01i_general_kernel_* -- but measured slower, 768 vs 819 Msamples/s on
+// wavenet_a2_max.nam: the calls and the generic-address loads of the local vectors cost more than the fetches.)
+__device__ __forceinline__ void g_accumulate(const float* __restrict__ wt, const int in, const int op, const float* x,
+                                             float* y, const bool from_zero, const float* __restrict__ bias)
 {
   for (int o = 0; o < op; o += 4)
   {
@@ -139,7 +139,7 @@ __device__ __forceinline__ void g_matvec(const GenThread& c, const GMat& M, cons
 // causal dilated convolution over the tile: every thread persists its x[t] in the ring, then reads x[t - off]
 // (earlier threads' columns of this tile, or earlier calls'; zeros before the reset).  Called by all threads of the
 // CTA in step (the control flow depends on the descriptors only).  Sums run taps oldest -> newest, inputs ascending.
-__device__ __noinline__ void g_conv(const GenThread& c, const GConv& V, const float* x, float* y)
+__device__ __forceinline__ void g_conv(const GenThread& c, const GConv& V, const float* x, float* y)
 {
   const int K = V.kernel;
   if (K > 1)
@@ -173,7 +173,7 @@ __device__ __noinline__ void g_conv(const GenThread& c, const GConv& V, const fl
 }
 
 // FiLM (film.h:76-190): out = in * scale(cond) (+ shift(cond)); in place is allowed (out == in)
-__device__ __noinline__ void g_film(const GenThread& c, const GFilm& F, const float* in, const float* cond, float* out)
+__device__ __forceinline__ void g_film(const GenThread& c, const GFilm& F, const float* in, const float* cond, float* out)
 {
   float ss[2 * kGenMaxVec];
   g_matvec(c, F.css, cond, ss);
@@ -259,7 +259,7 @@ __device__ __forceinline__ void g_layer(const GenThread& c, const GLayer& L, flo
 }
 
 // one frame through a whole network: in (in_channels), cond (its condition vector) -> out (out_channels)
-__device__ __noinline__ void g_net(const GenThread& c, const GNet& N, const GLayer* __restrict__ layers,
+__device__ __forceinline__ void g_net(const GenThread& c, const GNet& N, const GLayer* __restrict__ layers,
                                       const float* in, const float* cond, float* out)
 {
   float x[kGenMaxVec], xin[kGenMaxVec], head[kGenMaxVec], hout[kGenMaxVec];

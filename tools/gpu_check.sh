@@ -16,3 +16,14 @@ for k, v in d["secondary"].items():
     print(k, v.get("Msamples_per_s"), v.get("error"))
 PY
 tail -3 gpurun_out/bench_$TAG.err
+# the reference's own benchmodel (1 stream, 1500 x 64-frame process() calls, tools/benchmodel.cpp) on the shim
+if [ -x build/ref_tools/benchmodel ]; then
+  python - <<PY
+import json
+from tests import nam_fixtures as fx
+json.dump(fx.load_model("wavenet_a1_standard"), open("/tmp/a1.nam", "w"))
+PY
+  ./build/ref_tools/benchmodel /tmp/a1.nam 2>&1 | tail -3
+  ./build/ref_tools/benchmodel_bufsize /tmp/a1.nam 64 2000 2>&1 | tail -1
+  ./build/ref_tools/benchmodel_bufsize /tmp/a1.nam 1024 500 2>&1 | tail -1
+fi
