@@ -380,7 +380,8 @@ struct nam_b200_model
   float* d_in = nullptr;
   float* d_out = nullptr;
   size_t staging_floats = 0;
-  float* h_pin = nullptr; // pinned scratch for the planar (single stream) entry points
+  float* h_pin = nullptr; // pinned, device-mapped scratch for the planar (single stream) entry points
+  float* h_pin_dev = nullptr; // its device-side address
   size_t h_pin_floats = 0;
   double flops_per_frame = 0.0;
 
@@ -1105,10 +1106,15 @@ void ensure_pinned(nam_b200_model* m, size_t floats)
     return;
   if (m->h_pin)
     cudaFreeHost(m->h_pin);
-  m->h_pin = nullptr;
+  m->h_pin = m->h_pin_dev = nullptr;
   m->h_pin_floats = 0;
-  CUDA_CHECK(cudaMallocHost(&m->h_pin, floats * sizeof(float)));
+  CUDA_CHECK(cudaHostAlloc(&m->h_pin, floats * sizeof(float), cudaHostAllocMapped));
   m->h_pin_floats = floats;
+  if (cudaHostGetDevicePointer(&m->h_pin_dev, m->h_pin, 0) != cudaSuccess)
+  {
+    cudaGetLastError();
+    m->h_pin_dev = nullptr; // no zero-copy on this device: the planar calls fall back to explicit copies
+  }
 }
 
 // Zero the state, set the trained initial state where the architecture has one.
@@ -1407,6 +1413,56 @@ nam_b200_model* active_model(nam_b200_model* m)
 const nam_b200_model* active_model(const nam_b200_model* m)
 {
   return (m && m->active_sub >= 0) ? m->subs[(size_t)m->active_sub].get() : m;
+}
+
+// nam::DSP::process for stream 0: the caller's channel arrays go through the handle's pinned scratch (double -> float
+// is the cast of model.cpp:817 / lstm.cpp:111).  Small calls -- the plugin protocol: one stream, 64..1024 frames --
+// skip both copies: the scratch is mapped into the device's address space, the kernel reads its input from it and
+// writes its output to it directly (two DMA round trips less per call; the reference's benchmodel spends most of a
+// 64-frame call on latency, not on arithmetic).
+constexpr size_t kZeroCopyFloats = 8192;
+
+template <typename T>
+int process_planar(nam_b200_model* m, const T* const* input, T* const* output, int n_frames)
+{
+  m = active_model(m);
+  return guarded(m, [&]() -> int {
+    if (!input || !output)
+      return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null channel array");
+    const int rc = check_process_args(m, input[0], output[0], 1, n_frames);
+    if (rc != NAM_B200_OK)
+      return rc;
+    if (n_frames == 0)
+      return NAM_B200_OK;
+    const size_t ci = (size_t)m->spec.in_channels, co = (size_t)m->spec.out_channels, n = (size_t)n_frames;
+    float* hin = m->h_pin;
+    float* hout = m->h_pin + (size_t)m->max_frames * std::max(ci, co);
+    for (size_t c = 0; c < ci; c++)
+      for (size_t i = 0; i < n; i++)
+        hin[c * n + i] = (float)input[c][i];
+    if ((ci + co) * n <= kZeroCopyFloats && m->h_pin_dev != nullptr)
+    {
+      float* din = m->h_pin_dev;
+      float* dout = m->h_pin_dev + (hout - hin);
+      CUDA_CHECK(cudaEventRecord(m->ev0, m->stream));
+      run_device(m, din, dout, 1, n_frames, (long)(ci * n), (long)(co * n), m->stream);
+      CUDA_CHECK(cudaEventRecord(m->ev1, m->stream));
+    }
+    else
+    {
+      CUDA_CHECK(cudaMemcpyAsync(m->d_in, hin, ci * n * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+      CUDA_CHECK(cudaEventRecord(m->ev0, m->stream));
+      run_device(m, m->d_in, m->d_out, 1, n_frames, (long)(ci * n), (long)(co * n), m->stream);
+      CUDA_CHECK(cudaEventRecord(m->ev1, m->stream));
+      CUDA_CHECK(cudaMemcpyAsync(hout, m->d_out, co * n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(m->stream));
+    m->timing_valid = true;
+    for (size_t c = 0; c < co; c++)
+      for (size_t i = 0; i < n; i++)
+        output[c][i] = (T)hout[c * n + i];
+    return NAM_B200_OK;
+  });
 }
 
 } // namespace
@@ -1832,56 +1888,12 @@ int nam_b200_process_f32(nam_b200_model* m, const float* in, float* out, int bat
 
 int nam_b200_process_f32_planar(nam_b200_model* m, const float* const* input, float* const* output, int n_frames)
 {
-  if (!input || !output)
-    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null channel array");
-  nam_b200_model* a = active_model(m);
-  if (!a || (a->spec.in_channels == 1 && a->spec.out_channels == 1))
-    return nam_b200_process_f32(m, input[0], output[0], 1, n_frames, n_frames, n_frames);
-  // multi-channel: gather the caller's channel arrays into one row of planes
-  const int rc = check_process_args(a, input[0], output[0], 1, n_frames);
-  if (rc != NAM_B200_OK)
-    return rc;
-  const size_t ci = (size_t)a->spec.in_channels, co = (size_t)a->spec.out_channels, n = (size_t)n_frames;
-  std::vector<float> hin(ci * n), hout(co * n);
-  for (size_t c = 0; c < ci; c++)
-    std::memcpy(hin.data() + c * n, input[c], n * sizeof(float));
-  const int rc2 = nam_b200_process_f32(m, hin.data(), hout.data(), 1, n_frames, (int64_t)(ci * n), (int64_t)(co * n));
-  if (rc2 != NAM_B200_OK)
-    return rc2;
-  for (size_t c = 0; c < co; c++)
-    std::memcpy(output[c], hout.data() + c * n, n * sizeof(float));
-  return NAM_B200_OK;
+  return process_planar<float>(m, input, output, n_frames);
 }
 
 int nam_b200_process_f64_planar(nam_b200_model* m, const double* const* input, double* const* output, int n_frames)
 {
-  m = active_model(m);
-  return guarded(m, [&]() -> int {
-    if (!input || !output)
-      return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null channel array");
-    const int rc = check_process_args(m, input[0], output[0], 1, n_frames);
-    if (rc != NAM_B200_OK)
-      return rc;
-    if (n_frames == 0)
-      return NAM_B200_OK;
-    const size_t ci = (size_t)m->spec.in_channels, co = (size_t)m->spec.out_channels, n = (size_t)n_frames;
-    float* hin = m->h_pin;
-    float* hout = m->h_pin + (size_t)m->max_frames * std::max(ci, co);
-    for (size_t c = 0; c < ci; c++)
-      for (size_t i = 0; i < n; i++)
-        hin[c * n + i] = (float)input[c][i]; // the double -> float cast of model.cpp:817 / lstm.cpp:111
-    CUDA_CHECK(cudaMemcpyAsync(m->d_in, hin, ci * n * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-    CUDA_CHECK(cudaEventRecord(m->ev0, m->stream));
-    run_device(m, m->d_in, m->d_out, 1, n_frames, (long)(ci * n), (long)(co * n), m->stream);
-    CUDA_CHECK(cudaEventRecord(m->ev1, m->stream));
-    CUDA_CHECK(cudaMemcpyAsync(hout, m->d_out, co * n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
-    CUDA_CHECK(cudaStreamSynchronize(m->stream));
-    m->timing_valid = true;
-    for (size_t c = 0; c < co; c++)
-      for (size_t i = 0; i < n; i++)
-        output[c][i] = (double)hout[c * n + i];
-    return NAM_B200_OK;
-  });
+  return process_planar<double>(m, input, output, n_frames);
 }
 
 int nam_b200_set_fast_tanh(nam_b200_model* m, int enabled)
