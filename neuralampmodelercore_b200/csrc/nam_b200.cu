@@ -591,6 +591,41 @@ int occupancy_wavenet_ls_dispatch(int c0, int c1, int geom, size_t smem)
   WN_LS_DISPATCH(occupancy_wavenet_ls_variant, smem)
 }
 
+// ---- few streams, short calls (the plugin protocol: one stream, 64-frame process() calls) ----------------------------
+// Such a call is pure latency: ~22 layer steps, each as long as ONE warp needs for its frames' instructions.  A CTA
+// of 128 threads x 1 frame (tile 128) halves the instructions per warp against the 2-frame geometries.
+constexpr int kSmallNt = 128, kSmallLq = 7;
+template <int C0, int C1>
+void launch_wavenet_small_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem, cudaStream_t st)
+{
+  auto kern = wavenet_fused_kernel<C0, C1, 1, kSmallNt, 3, kSmallLq, false>;
+  static bool configured[64] = {false};
+  if (!configured[m->device & 63])
+  {
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[m->device & 63] = true;
+  }
+  kern<<<grid, kSmallNt, smem, st>>>(kp);
+  CUDA_CHECK(cudaGetLastError());
+}
+#define WN_SMALL_CASE(C0, C1) \
+  case (C0) * 100 + (C1): return launch_wavenet_small_variant<C0, C1>(m, kp, grid, smem, st);
+void launch_wavenet_small_dispatch(int c0, int c1, nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem,
+                                   cudaStream_t st)
+{
+  switch (c0 * 100 + c1)
+  {
+    WN_SMALL_CASE(4, 0) WN_SMALL_CASE(8, 0) WN_SMALL_CASE(16, 0) WN_SMALL_CASE(4, 4) WN_SMALL_CASE(4, 8) WN_SMALL_CASE(4, 16)
+    WN_SMALL_CASE(8, 4) WN_SMALL_CASE(8, 8) WN_SMALL_CASE(8, 16) WN_SMALL_CASE(16, 4) WN_SMALL_CASE(16, 8) WN_SMALL_CASE(16, 16)
+    default: throw std::runtime_error("no fused WaveNet kernel for channel pair " + std::to_string(c0) + "/" + std::to_string(c1));
+  }
+}
+size_t wavenet_small_smem_bytes(const WaveNetPlan& plan)
+{
+  const int cmax = std::max(plan.cp[0], plan.cp[1]);
+  return (plan.blob.size() + 3) / 4 * 16 + (size_t)(cmax / 4) * (kHalo + (1 << kSmallLq)) * 16;
+}
+
 size_t wavenet_ls_smem_bytes(const WaveNetPlan& plan, int g)
 {
   const int cmax = std::max(plan.cp[0], plan.cp[1]);
@@ -849,6 +884,14 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
     const int q = kWnGeom[g].streams_per_tile();
     const int grid_s = std::min((batch + q - 1) / q, m->wn_ctas_short[sg] * m->sm_count);
     launch_wavenet_dispatch(c0, c1, g, m, kp, std::max(grid_s, 1), smem_s, st);
+    m->launches++;
+    return;
+  }
+  // few streams (every CTA alone on its SM), short calls: the 128 x 1 geometry
+  if (m->opts.kernel_geometry == 0 && n_frames <= (1 << kSmallLq) && batch <= m->sm_count
+      && wavenet_small_smem_bytes(plan) <= 227 * 1024)
+  {
+    launch_wavenet_small_dispatch(c0, c1, m, kp, batch, wavenet_small_smem_bytes(plan), st);
     m->launches++;
     return;
   }
