@@ -174,3 +174,36 @@ def test_slimmable_container_parsing():
     bad = dict(full, weights=full["weights"][:-3])
     with pytest.raises(RuntimeError):
         nb.inspect(fx.make_container([(1.0, bad)]))
+
+
+def test_convnet_and_slimmable_wavenet_loaders():
+    """Host only: the ConvNet loader (NAM/convnet.cpp:172-201,321-335) and the slicing of a "slimmable" WaveNet into
+    plain sub-models (NAM/wavenet/slimmable.cpp:133-262), without the reference build."""
+    from tests.test_reference_build import _convnet
+
+    nam = _convnet(channels=8, dilations=[1, 2, 4, 8, 16, 32], batchnorm=True, activation="Tanh", seed=1)
+    info = nb.inspect(nam)
+    assert info["kernel"] == "convnet" and info["prewarm_samples"] == 64 and info["n_weights"] == len(nam["weights"])
+    with pytest.raises(RuntimeError, match="expects more"):
+        nb.inspect({**nam, "weights": nam["weights"][:-1]})
+    with pytest.raises(RuntimeError, match="Didn't touch all the weights"):
+        nb.inspect({**nam, "weights": nam["weights"] + [0.0]})
+    assert nb.submodels(nam) == []  # not slimmable
+
+    slim = fx.load_model("slimmable_wavenet")
+    subs = nb.submodels(slim)
+    assert [mv for mv, _ in subs] == [1 / 3, 2 / 3, 1.0]
+    assert [d["config"]["layers"][0]["channels"] for _, d in subs] == [1, 2, 3]
+    assert [len(d["weights"]) for _, d in subs] == [73, 225, 457]
+    assert all(d["config"]["layers"][0]["slimmable"] is None for _, d in subs)
+    # the full size is the file itself (weights are float32 in the reference, NAM/get_dsp.cpp:130-139)
+    assert np.array_equal(np.asarray(subs[-1][1]["weights"], np.float32), np.asarray(slim["weights"], np.float32))
+    info = nb.inspect(slim)
+    assert info["submodels"] == 3 and info["kernel"] == "fused"
+    bad = json.loads(json.dumps(slim))
+    bad["config"]["layers"][0]["slimmable"]["kwargs"]["allowed_channels"] = [1, 2]  # last entry must be the full count
+    with pytest.raises(RuntimeError, match="last allowed_channels entry"):
+        nb.inspect(bad)
+    bad["config"]["layers"][0]["slimmable"]["method"] = "magic"
+    with pytest.raises(RuntimeError, match="unsupported slimmable method"):
+        nb.inspect(bad)
