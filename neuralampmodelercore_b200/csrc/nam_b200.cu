@@ -360,7 +360,7 @@ struct nam_b200_model
   size_t tile_flags_capacity = 0;
   float* d_hist = nullptr; // lock-step tile-parallel mode: per-call history buffer (WaveNetKernelParams::hist)
   size_t hist_floats = 0;
-  int wn_ctas_ls[2] = {0, 0}; // resident CTAs per SM of the lock-step kernels (kLsGeom)
+  int wn_ctas_ls[3] = {0, 0, 0}; // resident CTAs per SM of the lock-step kernels (kLsGeom)
   int wn_ctas_short[2] = {0, 0}; // same for the short-call (multi-stream tile) geometries 2 / 3
   int wn_geometry = 1; // 0 / 1: index into kWnGeom (FFMA kernel); 2: tensor-core kernel (wavenet_tc.cuh)
   float* d_tc_blob = nullptr; // per-layer B-operand images of the tensor-core kernel
@@ -484,6 +484,8 @@ int occupancy_wavenet_variant(size_t smem)
 // lock-step tile-parallel kernels (LS = true), one stream per tile.
 //   LS geometry 0: 128 threads x 2 frames, tile 256, >= 3 CTAs/SM  (default; kernel_geometry 1)
 //   LS geometry 1: 256 threads x 2 frames, tile 512, >= 2 CTAs/SM  (kernel_geometry 2; also when tile 256 does not fit)
+//   LS geometry 2: 128 threads x 1 frame, tile 128: only while every CTA has an SM to itself (batch x tiles <= SMs:
+//                  one stream in 4096-frame calls), where a layer step is as long as one warp's instruction stream
 // (A 256 x 1 geometry -- half the instructions per thread and layer step, twice the warps per tile -- measured slower
 // on both shapes that matter: 37.2 vs 41.2 Msamples/s for one stream in 4096-frame calls, 437 vs 487 for one
 // 96,000-frame call: the weight loads per FFMA2 double.)
@@ -492,8 +494,8 @@ struct LsGeometry
   int nt, s, min_ctas, lq;
   int tile_frames() const { return 1 << lq; }
 };
-constexpr int kLsGeoms = 2;
-constexpr LsGeometry kLsGeom[kLsGeoms] = {{128, 2, 3, 8}, {256, 2, 2, 9}};
+constexpr int kLsGeoms = 3;
+constexpr LsGeometry kLsGeom[kLsGeoms] = {{128, 2, 3, 8}, {256, 2, 2, 9}, {128, 1, 3, 7}};
 
 template <int C0, int C1, int S, int NT, int MINB, int LQ>
 void launch_wavenet_ls_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem, cudaStream_t st)
@@ -525,7 +527,8 @@ int occupancy_wavenet_ls_variant(size_t smem)
 
 #define WN_LS_CASE(C0, C1, FN, ...)                                                                                  \
   case (C0) * 100 + (C1):                                                                                            \
-    return geom == 0 ? FN<C0, C1, 2, 128, 3, 8>(__VA_ARGS__) : FN<C0, C1, 2, 256, 2, 9>(__VA_ARGS__);
+    return geom == 0 ? FN<C0, C1, 2, 128, 3, 8>(__VA_ARGS__)                                                         \
+                     : (geom == 1 ? FN<C0, C1, 2, 256, 2, 9>(__VA_ARGS__) : FN<C0, C1, 1, 128, 3, 7>(__VA_ARGS__));
 
 #define WN_LS_DISPATCH(FN, ...)                                                                                      \
   switch (c0 * 100 + c1)                                                                                             \
@@ -662,6 +665,8 @@ long wavenet_ls_capacity(nam_b200_model* m, int g)
 // tries 0 (tile 256) and then 1 (tile 512: half as many CTAs to keep co-resident)
 bool wavenet_ls_candidate(const nam_b200_model* m, int g)
 {
+  if (g == 2)
+    return m->opts.kernel_geometry == 0; // (chosen first, and only while batch x tiles <= SMs: wavenet_ls_geometry)
   return m->opts.kernel_geometry == 0 || g == m->opts.kernel_geometry - 1;
 }
 
@@ -671,13 +676,15 @@ int wavenet_ls_geometry(nam_b200_model* m, int batch, int n_frames, int* tiles_o
 {
   if (m->opts.tile_mode != 0 || m->wn_geometry > 1 || m->use_generic)
     return -1;
-  for (int g = 0; g < kLsGeoms; g++)
+  static const int order[kLsGeoms] = {2, 0, 1};
+  for (int oi = 0; oi < kLsGeoms; oi++)
   {
+    const int g = order[oi];
     if (!wavenet_ls_candidate(m, g))
       continue;
     const int tf = kLsGeom[g].tile_frames();
     const int tiles = (n_frames + tf - 1) / tf;
-    const long cap = wavenet_ls_capacity(m, g);
+    const long cap = (g == 2) ? std::min<long>(wavenet_ls_capacity(m, g), m->sm_count) : wavenet_ls_capacity(m, g);
     if (tiles >= 2 && (long)batch * tiles <= cap)
     {
       *tiles_out = tiles;
@@ -701,7 +708,7 @@ void ensure_hist(nam_b200_model* m)
       continue;
     const int tf = kLsGeom[g].tile_frames();
     const long tiles_max = (m->max_frames + tf - 1) / tf;
-    const long cap = wavenet_ls_capacity(m, g);
+    const long cap = (g == 2) ? std::min<long>(wavenet_ls_capacity(m, g), m->sm_count) : wavenet_ls_capacity(m, g);
     if (tiles_max < 2 || cap < 2)
       continue;
     const long ctas = std::min<long>((long)m->opts.max_batch * tiles_max, cap);
