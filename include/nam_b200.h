@@ -63,8 +63,9 @@ typedef struct nam_b200_options
                               thread per frame) that otherwise serves only models outside the fused families */
   int32_t tile_mode; /* few streams x long calls (batch x tiles <= resident CTAs): 0 = library default: lock-step
                         tile-parallel mode (every (stream, tile) its own CTA, all tiles advancing layer by layer; a
-                        history buffer of up to ~150 MB is allocated by reset(); tiles of 256 frames, 128 threads x 2
-                        frames, or 512 frames, 256 x 2, when those do not all fit -- kernel_geometry 1 / 2 pins one); 1 = wavefront
+                        history buffer of up to ~150 MB is allocated by reset(); tiles of 128 frames while every CTA has
+                        an SM to itself, else 256 frames, 128 threads x 2 frames, or 512 frames, 256 x 2, when those do
+                        not all fit -- kernel_geometry 1 / 2 pins one of the last two); 1 = wavefront
                         tile-parallel mode (no buffer, tile c one layer behind tile c-1); 2 = never: one CTA walks a
                         stream's tiles in turn.  Tile-parallel launches need their CTAs co-resident: do not run
                         other kernels on the same GPU concurrently with such a call */
