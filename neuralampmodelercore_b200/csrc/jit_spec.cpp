@@ -1,0 +1,328 @@
+// jit_spec.cpp -- see jit_spec.h.  NVRTC is reached through dlopen (no link-time dependency: the library still
+// loads, and serves every model through the precompiled kernels, on a host without libnvrtc).
+#include "jit_spec.h"
+
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <sstream>
+
+namespace namb200
+{
+
+namespace
+{
+// The kernel source, embedded at build time (neuralampmodelercore_b200/_build.py writes wavenet_spec_src.inc from
+// wavenet_spec.cuh as a raw string literal).
+const char* const kSpecKernelSource =
+#include "wavenet_spec_src.inc"
+  ;
+
+// ---- NVRTC through dlopen ------------------------------------------------------------------------------------------
+typedef struct _nvrtcProgram* nvrtcProgram;
+struct Nvrtc
+{
+  void* handle = nullptr;
+  int (*Version)(int*, int*) = nullptr;
+  int (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*DestroyProgram)(nvrtcProgram*) = nullptr;
+  int (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+  int (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+  int (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+  int (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+  int (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string error;
+  bool ok() const { return handle != nullptr; }
+};
+
+Nvrtc& nvrtc()
+{
+  static Nvrtc n;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                           "/usr/local/cuda/lib64/libnvrtc.so"};
+    for (const char* nm : names)
+    {
+      n.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+      if (n.handle)
+        break;
+    }
+    if (!n.handle)
+    {
+      n.error = "libnvrtc.so.12 not found (dlopen)";
+      return;
+    }
+    bool all = true;
+    auto sym = [&](const char* s) {
+      void* p = dlsym(n.handle, s);
+      if (!p)
+        all = false;
+      return p;
+    };
+    n.Version = reinterpret_cast<decltype(n.Version)>(sym("nvrtcVersion"));
+    n.CreateProgram = reinterpret_cast<decltype(n.CreateProgram)>(sym("nvrtcCreateProgram"));
+    n.DestroyProgram = reinterpret_cast<decltype(n.DestroyProgram)>(sym("nvrtcDestroyProgram"));
+    n.CompileProgram = reinterpret_cast<decltype(n.CompileProgram)>(sym("nvrtcCompileProgram"));
+    n.GetCUBINSize = reinterpret_cast<decltype(n.GetCUBINSize)>(sym("nvrtcGetCUBINSize"));
+    n.GetCUBIN = reinterpret_cast<decltype(n.GetCUBIN)>(sym("nvrtcGetCUBIN"));
+    n.GetProgramLogSize = reinterpret_cast<decltype(n.GetProgramLogSize)>(sym("nvrtcGetProgramLogSize"));
+    n.GetProgramLog = reinterpret_cast<decltype(n.GetProgramLog)>(sym("nvrtcGetProgramLog"));
+    n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(sym("nvrtcGetErrorString"));
+    if (!all)
+    {
+      dlclose(n.handle);
+      n.handle = nullptr;
+      n.error = "libnvrtc lacks an expected entry point";
+    }
+  });
+  return n;
+}
+
+// ---- helpers ----------------------------------------------------------------------------------------------------------
+uint64_t fnv1a(uint64_t h, const void* data, size_t n)
+{
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < n; i++)
+  {
+    h ^= p[i];
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+// A float as a C++17 hexadecimal literal built from integers only (no locale, exact): [-]0x<24-bit mantissa>p<exp>f
+std::string float_literal(float v)
+{
+  if (v == 0.0f)
+    return std::signbit(v) ? "-0.0f" : "0.0f";
+  int e = 0;
+  const float m = std::frexp(std::fabs(v), &e); // |v| = m * 2^e, m in [0.5, 1)
+  const long mi = (long)std::ldexp((double)m, 24); // exact: 24 significant bits
+  char buf[64];
+  std::snprintf(buf, sizeof buf, "%s0x%lXp%df", v < 0.0f ? "-" : "", mi, e - 24);
+  return buf;
+}
+
+std::string library_dir()
+{
+  Dl_info info{};
+  if (dladdr(reinterpret_cast<const void*>(&library_dir), &info) && info.dli_fname)
+  {
+    std::string p = info.dli_fname;
+    const size_t s = p.find_last_of('/');
+    return s == std::string::npos ? "." : p.substr(0, s);
+  }
+  return ".";
+}
+
+std::string cache_dir()
+{
+  if (const char* e = std::getenv("NAM_B200_JIT_CACHE"))
+    if (*e)
+      return e;
+  return library_dir() + "/jit_cache";
+}
+
+bool read_file(const std::string& path, std::vector<char>& out)
+{
+  std::ifstream f(path, std::ios::binary);
+  if (!f)
+    return false;
+  f.seekg(0, std::ios::end);
+  const std::streamoff n = f.tellg();
+  if (n <= 0)
+    return false;
+  f.seekg(0);
+  out.resize((size_t)n);
+  f.read(out.data(), n);
+  return (bool)f;
+}
+
+void write_file_atomic(const std::string& dir, const std::string& name, const std::vector<char>& data)
+{
+  ::mkdir(dir.c_str(), 0755); // best effort: a read-only install simply never caches
+  const std::string tmp = dir + "/." + name + "." + std::to_string((long)::getpid()) + ".tmp";
+  {
+    std::ofstream f(tmp, std::ios::binary);
+    if (!f)
+      return;
+    f.write(data.data(), (std::streamsize)data.size());
+    if (!f)
+    {
+      ::unlink(tmp.c_str());
+      return;
+    }
+  }
+  if (::rename(tmp.c_str(), (dir + "/" + name).c_str()) != 0)
+    ::unlink(tmp.c_str());
+}
+
+} // namespace
+
+bool spec_eligible(const WaveNetPlan& plan, const SpecGeometry& g, std::string* why_not)
+{
+  auto no = [&](const std::string& w) {
+    if (why_not)
+      *why_not = w;
+    return false;
+  };
+  if (!plan.eligible)
+    return no("not in the fused family: " + plan.why_not);
+  if (plan.n_arrays < 1 || plan.n_arrays > 2)
+    return no("more than two layer arrays");
+  int pmax = 0;
+  for (int a = 0; a < plan.n_arrays; a++)
+  {
+    if (plan.arrays[a].head_kernel != 1)
+      return no("convolutional head");
+    pmax = std::max(pmax, plan.cp[a] / 4);
+  }
+  for (const LayerDesc& L : plan.layers)
+    for (float v : {L.ap0, L.ap1, L.ap2, L.ap3})
+      if (!std::isfinite(v))
+        return no("non-finite activation parameter");
+  for (float v : plan.blob)
+    if (!std::isfinite(v))
+      return no("non-finite weight");
+  const size_t smem = (size_t)pmax * (size_t)(plan.max_lookback + g.tile()) * 16;
+  if (smem * (size_t)g.min_ctas > 226u * 1024u || smem > 226u * 1024u)
+    return no("history window (" + std::to_string(plan.max_lookback) + " columns) + tile do not fit in shared memory");
+  return true;
+}
+
+std::string spec_header_source(const WaveNetPlan& plan)
+{
+  std::ostringstream o;
+  o << "// generated by jit_spec.cpp: one model, as compile-time data\n"
+       "#define NAMB200_SPEC_HEADER_INCLUDED 1\n"
+       "namespace spec {\n"
+       "struct Layer { int K, dil, act, w_off, ring_off, ring_mask; float ap0, ap1, ap2, ap3; };\n"
+       "struct Array { int C, CIN, HOUT, n_layers, layer0, rech_off, head_off, head_kernel; };\n";
+  o << "constexpr int NA = " << plan.n_arrays << ";\n";
+  o << "constexpr int NL = " << plan.layers.size() << ";\n";
+  o << "constexpr int LS = " << plan.max_lookback << ";\n";
+  o << "constexpr float head_scale = " << float_literal(plan.head_scale) << ";\n";
+  o << "constexpr Array A[NA] = {\n";
+  for (int a = 0; a < plan.n_arrays; a++)
+  {
+    const ArrayDesc& A = plan.arrays[a];
+    const int cin = a == 0 ? 1 : plan.cp[a - 1];
+    const int hout = a + 1 == plan.n_arrays ? 1 : plan.cp[a + 1];
+    o << "  {" << plan.cp[a] << ", " << cin << ", " << hout << ", " << A.n_layers << ", " << A.layer0 << ", " << A.rech_off
+      << ", " << A.head_off << ", " << A.head_kernel << "},\n";
+  }
+  o << "};\nconstexpr Layer L[NL] = {\n";
+  for (const LayerDesc& L : plan.layers)
+    o << "  {" << L.kernel << ", " << L.dilation << ", " << L.act << ", " << L.w_off << ", " << L.ring_off << ", " << L.ring_mask
+      << ", " << float_literal(L.ap0) << ", " << float_literal(L.ap1) << ", " << float_literal(L.ap2) << ", "
+      << float_literal(L.ap3) << "},\n";
+  // the weights as bit patterns (exact, locale-free); wavenet_spec.cuh reads them through spec::w(i), and after full
+  // unrolling every index is a constant, so the loads fold into FFMA immediates
+  o << "};\n__device__ const unsigned Wb[" << plan.blob.size() << "] = {\n";
+  char buf[16];
+  for (size_t i = 0; i < plan.blob.size(); i++)
+  {
+    uint32_t u;
+    std::memcpy(&u, &plan.blob[i], 4);
+    std::snprintf(buf, sizeof buf, "0x%08Xu,", u);
+    o << buf << ((i % 8 == 7) ? "\n" : " ");
+  }
+  o << "};\n__device__ __forceinline__ float w(const int i) { return __uint_as_float(Wb[i]); }\n}  // namespace spec\n";
+  return o.str();
+}
+
+SpecBuild build_spec_kernel(const WaveNetPlan& plan, const SpecGeometry& g)
+{
+  SpecBuild r;
+  r.geom = g;
+  if (!spec_eligible(plan, g, &r.why_not))
+    return r;
+  r.staged_cols = plan.max_lookback;
+  for (int a = 0; a < plan.n_arrays; a++)
+    r.max_planes = std::max(r.max_planes, plan.cp[a] / 4);
+
+  const std::string header = spec_header_source(plan);
+  const std::string opts_text = "-arch=sm_100a -std=c++17 -DNT=" + std::to_string(g.nt) + " -DS=" + std::to_string(g.s)
+                                + " -DMINB=" + std::to_string(g.min_ctas);
+  Nvrtc& n = nvrtc();
+  int vmaj = 0, vmin = 0;
+  if (n.ok())
+    n.Version(&vmaj, &vmin);
+  uint64_t h = 1469598103934665603ull;
+  h = fnv1a(h, header.data(), header.size());
+  h = fnv1a(h, kSpecKernelSource, std::strlen(kSpecKernelSource));
+  h = fnv1a(h, opts_text.data(), opts_text.size());
+  char name[64];
+  std::snprintf(name, sizeof name, "wavenet_spec_%016llx.cubin", (unsigned long long)h);
+  const std::string dir = cache_dir();
+  if (read_file(dir + "/" + name, r.cubin))
+  {
+    r.ok = true;
+    r.from_cache = true;
+    return r;
+  }
+  if (!n.ok())
+  {
+    r.why_not = "NVRTC unavailable: " + n.error;
+    return r;
+  }
+
+  const auto t0 = std::chrono::steady_clock::now();
+  const std::string source = header + "\n#include \"wavenet_spec.cuh\"\n";
+  const char* hdr_src[] = {kSpecKernelSource};
+  const char* hdr_name[] = {"wavenet_spec.cuh"};
+  nvrtcProgram prog = nullptr;
+  int rc = n.CreateProgram(&prog, source.c_str(), "wavenet_spec_model.cu", 1, hdr_src, hdr_name);
+  if (rc != 0)
+  {
+    r.why_not = std::string("nvrtcCreateProgram: ") + n.GetErrorString(rc);
+    return r;
+  }
+  const std::string d_nt = "-DNAMB200_SPEC_NT=" + std::to_string(g.nt);
+  const std::string d_s = "-DNAMB200_SPEC_S=" + std::to_string(g.s);
+  const std::string d_mb = "-DNAMB200_SPEC_MINB=" + std::to_string(g.min_ctas);
+  const char* copts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", d_nt.c_str(), d_s.c_str(), d_mb.c_str()};
+  rc = n.CompileProgram(prog, (int)(sizeof copts / sizeof copts[0]), copts);
+  if (rc != 0)
+  {
+    size_t ls = 0;
+    n.GetProgramLogSize(prog, &ls);
+    std::string log(ls, '\0');
+    if (ls)
+      n.GetProgramLog(prog, &log[0]);
+    r.why_not = std::string("nvrtcCompileProgram: ") + n.GetErrorString(rc) + "\n" + log.substr(0, 4000);
+    n.DestroyProgram(&prog);
+    return r;
+  }
+  size_t cs = 0;
+  rc = n.GetCUBINSize(prog, &cs);
+  if (rc == 0 && cs > 0)
+  {
+    r.cubin.resize(cs);
+    rc = n.GetCUBIN(prog, r.cubin.data());
+  }
+  n.DestroyProgram(&prog);
+  if (rc != 0 || cs == 0)
+  {
+    r.why_not = "nvrtcGetCUBIN failed";
+    r.cubin.clear();
+    return r;
+  }
+  r.compile_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  write_file_atomic(dir, name, r.cubin);
+  r.ok = true;
+  return r;
+}
+
+} // namespace namb200

@@ -1,0 +1,55 @@
+// jit_spec.h -- load-time specialisation of the fused WaveNet kernel (wavenet_spec.cuh) to ONE model.
+//
+// The reference builds a graph of Eigen objects per model at load time (NAM/wavenet/model.cpp:580-683); this library's
+// throughput path goes one step further and compiles the model: NVRTC turns wavenet_spec.cuh + a generated header
+// (layer table as constexpr data, weights as `__device__ const float[]`) into sm_100a SASS in which every weight is the
+// immediate operand of an FFMA.  The cubin is cached on disk, keyed by a hash of everything that went into it.
+// Host only; no CUDA runtime types in this header.
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "wavenet_pack.h"
+
+namespace namb200
+{
+
+struct SpecGeometry
+{
+  int nt = 512; // threads per CTA
+  int s = 1; // frames per thread
+  int min_ctas = 2; // __launch_bounds__ second argument
+  int tile() const { return nt * s; }
+};
+
+struct SpecBuild
+{
+  bool ok = false;
+  std::string why_not; // !ok: the reason (not eligible / NVRTC missing / compile error + log)
+  std::vector<char> cubin;
+  SpecGeometry geom;
+  int staged_cols = 0; // spec::LS: columns of history staged in front of the tile (max look-back of the model)
+  int max_planes = 0; // widest array, in planes of 4 channels
+  bool from_cache = false;
+  double compile_seconds = 0.0;
+  size_t smem_bytes() const { return (size_t)max_planes * (size_t)(staged_cols + geom.tile()) * 16; }
+};
+
+/// Can wavenet_spec.cuh serve this plan?  (The plan must already be eligible for the generic fused kernel.)
+bool spec_eligible(const WaveNetPlan& plan, const SpecGeometry& g, std::string* why_not);
+
+/// The generated model header (namespace spec).  Deterministic: the cache key hashes it.
+std::string spec_header_source(const WaveNetPlan& plan);
+
+/// Compile (or fetch from the disk cache) the specialised kernel for `plan`.
+/// Cache directory: $NAM_B200_JIT_CACHE, else <directory of libnam_b200.so>/jit_cache.  Never throws.
+SpecBuild build_spec_kernel(const WaveNetPlan& plan, const SpecGeometry& g);
+
+/// Name of the kernel entry point inside the cubin.
+inline const char* spec_kernel_name()
+{
+  return "wavenet_spec_kernel";
+}
+
+} // namespace namb200

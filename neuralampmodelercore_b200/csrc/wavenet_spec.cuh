@@ -1,0 +1,562 @@
+// wavenet_spec.cuh -- the MODEL-SPECIALISED fused WaveNet kernel for sm_100a.
+//
+// This file is compiled once per model (NVRTC at load time, jit_spec.cpp; or nvcc for tools/spec_proto.cu) together
+// with a generated header that defines namespace `spec`: the layer table as constexpr data and the weights as
+// `__device__ const unsigned Wb[]` bit patterns read through spec::w(i).  Every loop below has compile-time bounds and is fully unrolled, so every weight
+// becomes the 32-bit IMMEDIATE of an FFMA (`FFMA R, Rx, 0.1234, R`): no weight loads, no weight registers, no
+// shared-memory copy of the weights.  Why: the generic fused kernel (wavenet_fused.cuh) broadcasts weights from shared
+// memory, and at two frames per thread one uniform LDS.128 (2 wavefronts) feeds only 4 FFMA2 -- the shared-memory pipe
+// runs at 67 % while the FMA pipe reaches 59 % (profiles/r01g_*): the two saturate together.  With immediates the FMA
+// pipe is fed by the instruction stream alone; shared memory carries only the activations.
+//
+// What it computes (reference file:line, all under NAM/): the same path as wavenet_fused.cuh --
+//   wavenet/model.cpp:822-910 WaveNet::process, :463-549 LayerArray::Process, :183-393 Layer::Process (non-gated, no
+//   FiLM, no head1x1), conv1d.cpp:666-683 Conv1D::Process, ring_buffer.cpp:7-109 RingBuffer, dsp.cpp:436-836 Conv1x1,
+//   activations.h:59-133 -- in the same summation order (bias + mixin first, taps oldest to newest, input channels
+//   ascending), so its results are bit-identical to the generic fused kernel's.
+//
+// Mapping: one persistent CTA owns one stream at a time and walks its call in tiles of T = S * NT frames; thread t owns
+// frames {t, t + NT, ..} for the whole depth of the network (see wavenet_fused.cuh).  What is new here:
+//   * TMA-engine staging of the history (cp.async.bulk, SASS UBLKCP): before a layer runs, the last `lookback` columns of
+//     its input ring are copied global -> shared by bulk-async copies that complete on an mbarrier, into the columns
+//     directly in front of the tile: buf[plane][LS - lookback .. LS) | tile columns [LS .. LS + T).  Every dilated tap
+//     of every layer is then ONE shared-memory load at a compile-time offset from the thread's own column: no ring
+//     addressing, no branch, no per-thread global load in the compute path.  The copy of layer l+1's history is issued
+//     right after layer l's last tap read (barrier B1) and lands under layer l's 1x1 phase.
+//   * the tile's newest columns go back to the ring with bulk-async stores shared -> global, issued by the same lanes
+//     (so the async-proxy store -> load order on a ring is per-thread program order + wait_group).
+// Ring layout and semantics are those of wavenet_fused.cuh ([C/4][R][4] floats, R a power of two >= lookback, indexed
+// by absolute frame number), so calls served by this kernel and by the generic kernels can be mixed on one handle.
+#pragma once
+
+#ifndef NAMB200_SPEC_HEADER_INCLUDED
+#error "include the generated model header (namespace spec) before wavenet_spec.cuh"
+#endif
+
+namespace namb200_spec
+{
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// Activation codes == namb200::KACT_* (wavenet_desc.h)
+enum : int
+{
+  ACT_TANH = 0,
+  ACT_HARDTANH = 1,
+  ACT_FASTTANH = 2,
+  ACT_RELU = 3,
+  ACT_LEAKYRELU = 4,
+  ACT_PRELU = 5,
+  ACT_SIGMOID = 6,
+  ACT_SILU = 7,
+  ACT_HARDSWISH = 8,
+  ACT_LEAKYHARDTANH = 9,
+  ACT_SOFTSIGN = 10
+};
+
+struct SpecParams
+{
+  float* state; // [batch][state_stride]: the rings of wavenet_fused.cuh
+  long state_stride; // floats
+  const float* in; // [batch][in_stride]
+  float* out;
+  long in_stride, out_stride;
+  int batch, n_frames;
+  u32 t_base; // absolute frame index of in[:, 0] (mod 2^32)
+};
+
+// ---- scalar helpers (same arithmetic as wavenet_fused.cuh) ------------------------------------------------------
+__device__ __forceinline__ float rcp_approx(float x)
+{
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ u64 pack2(const float lo, const float hi)
+{
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(const u64 v, float& lo, float& hi)
+{
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+{
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b)
+{
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b)
+{
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 dup2(float v)
+{
+  return pack2(v, v);
+}
+// the reference's rational fast_tanh (activations.h:91-98) on a packed pair: identical operation order to
+// namb200::tc_fast_tanh2 (wavenet_fused.cuh)
+__device__ __forceinline__ u64 fast_tanh2(u64 x)
+{
+  constexpr u64 kAbs = 0x7FFFFFFF7FFFFFFFull;
+  const u64 ax = x & kAbs;
+  const u64 x2 = mul2(x, x);
+  const u64 c0 = dup2(2.45550750702956f);
+  const u64 t1 = fma2(dup2(0.821226666969744f), ax, dup2(0.893229853513558f));
+  const u64 t0 = fma2(c0, ax, c0);
+  const u64 num = mul2(x, fma2(t1, x2, t0));
+  const u64 s = fma2(dup2(0.814642734961073f), mul2(x, ax), x) & kAbs;
+  const u64 d0 = dup2(2.44506634652299f);
+  const u64 den = fma2(add2(x2, d0), s, d0);
+  float dl, dh;
+  unpack2(den, dl, dh);
+  return mul2(num, pack2(rcp_approx(dl), rcp_approx(dh)));
+}
+__device__ __forceinline__ float act_sigmoid(float x)
+{
+  return rcp_approx(1.0f + expf(-x));
+}
+
+template <int LI, int C>
+__device__ __forceinline__ void apply_activation(float (&v)[C])
+{
+  constexpr spec::Layer Ld = spec::L[LI];
+  if constexpr (Ld.act == ACT_FASTTANH)
+  {
+#pragma unroll
+    for (int q = 0; q < C / 2; q++)
+      unpack2(fast_tanh2(pack2(v[2 * q], v[2 * q + 1])), v[2 * q], v[2 * q + 1]);
+  }
+  else
+  {
+#pragma unroll
+    for (int i = 0; i < C; i++)
+    {
+      const float x = v[i];
+      if constexpr (Ld.act == ACT_TANH)
+        v[i] = tanhf(x);
+      else if constexpr (Ld.act == ACT_HARDTANH)
+        v[i] = fminf(fmaxf(x, -1.0f), 1.0f);
+      else if constexpr (Ld.act == ACT_RELU)
+        v[i] = x > 0.0f ? x : 0.0f;
+      else if constexpr (Ld.act == ACT_LEAKYRELU)
+        v[i] = x > 0.0f ? x : Ld.ap0 * x;
+      else if constexpr (Ld.act == ACT_PRELU)
+        v[i] = x > 0.0f ? x : spec::w(Ld.w_off + Ld.K * C * C + C + C + C * C + C + i) * x;
+      else if constexpr (Ld.act == ACT_SIGMOID)
+        v[i] = act_sigmoid(x);
+      else if constexpr (Ld.act == ACT_SILU)
+        v[i] = x * act_sigmoid(x);
+      else if constexpr (Ld.act == ACT_HARDSWISH)
+      {
+        const float t = x + 3.0f;
+        const float cl = t < 0.0f ? 0.0f : (t > 6.0f ? 6.0f : t);
+        v[i] = x * cl * (1.0f / 6.0f);
+      }
+      else if constexpr (Ld.act == ACT_LEAKYHARDTANH)
+        v[i] = x < Ld.ap0 ? (x - Ld.ap0) * Ld.ap2 + Ld.ap0 : (x > Ld.ap1 ? (x - Ld.ap1) * Ld.ap3 + Ld.ap1 : x);
+      else if constexpr (Ld.act == ACT_SOFTSIGN)
+        v[i] = x * rcp_approx(1.0f + fabsf(x));
+    }
+  }
+}
+
+// ---- mbarrier / bulk-async copy primitives ------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_addr(const void* p)
+{
+  return (u32)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(u64* bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity)
+{
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "WAIT_%=:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "@p bra DONE_%=;\n"
+    "bra WAIT_%=;\n"
+    "DONE_%=:\n"
+    "}\n" ::"r"(smem_addr(bar)),
+    "r"(parity)
+    : "memory");
+}
+// global -> shared, completes `bytes` on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                 smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u32 bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit()
+{
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all()
+{
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (the bulk stores that read the tile)
+__device__ __forceinline__ void fence_async_smem()
+{
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- one ring <-> the staging buffer --------------------------------------------------------------------------------
+// A "history unit" = one ring of P planes: a layer's input ring or an array's head-accumulator ring.
+// Lane `pl` (< P) of warp 0 moves plane pl: at most two contiguous pieces when the range wraps around the ring.
+//   load : ring columns [tabs0 - L, tabs0)            -> buf[pl][LS - L, LS)
+//   store: tile columns [tv - n, tv), n = min(L, tv)  -> ring columns [tabs0 + tv - n, tabs0 + tv)
+template <int P, int L, int RMASK, int W>
+__device__ __forceinline__ void hist_load(float4* buf, float* ring_f, const u32 tabs0, u64* bar, const int lane)
+{
+  constexpr int R = RMASK + 1;
+  static_assert(L <= R && L <= spec::LS, "ring / staging geometry");
+  if (lane == 0)
+    mbar_expect_tx(bar, (u32)(P * L * 16)); // (a kernel-size-1 layer has no history: the phase completes at once)
+  __syncwarp();
+  if (L > 0 && lane < P)
+  {
+    const float4* ring = reinterpret_cast<const float4*>(ring_f) + lane * R;
+    float4* dst = buf + lane * W + (spec::LS - L);
+    const int start = (int)((tabs0 - (u32)L) & (u32)RMASK);
+    const int n1 = min(L, R - start);
+    bulk_g2s(dst, ring + start, (u32)n1 * 16u, bar);
+    if (n1 < L)
+      bulk_g2s(dst + n1, ring, (u32)(L - n1) * 16u, bar);
+  }
+}
+template <int P, int L, int RMASK, int W>
+__device__ __forceinline__ void hist_store(const float4* buf, float* ring_f, const u32 tabs0, const int tv, const int lane)
+{
+  constexpr int R = RMASK + 1;
+  if (L > 0 && lane < P)
+  {
+    float4* ring = reinterpret_cast<float4*>(ring_f) + lane * R;
+    const int n = min(L, tv);
+    const float4* src = buf + lane * W + spec::LS + (tv - n);
+    const int start = (int)((tabs0 + (u32)(tv - n)) & (u32)RMASK);
+    const int n1 = min(n, R - start);
+    bulk_s2g(ring + start, src, (u32)n1 * 16u);
+    if (n1 < n)
+      bulk_s2g(ring, src + n1, (u32)(n - n1) * 16u);
+    bulk_commit();
+  }
+}
+
+// compile-time loop over the layers of an array
+template <int V>
+struct IntC
+{
+  static constexpr int value = V;
+};
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+  if constexpr (I < N)
+  {
+    f(IntC<I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+struct TileCtx
+{
+  float4* buf; // staging buffer: [plane][W] columns
+  u64* bar; // the history mbarrier
+  u32 phase; // its parity
+  float* state; // this stream's rings
+  u32 tabs0; // absolute frame number of the tile's first frame
+  int tv; // valid frames in this tile
+  int warp, lane;
+};
+
+// history of the unit that follows (AI, LI) in program order is requested right after the current unit's last read
+template <int AI, int NT, int S, int LI>
+__device__ __forceinline__ void request_layer_history(TileCtx& c, IntC<LI>)
+{
+  constexpr spec::Layer Ld = spec::L[LI];
+  constexpr int C = spec::A[AI].C;
+  constexpr int W = spec::LS + NT * S;
+  if (c.warp == 0)
+    hist_load<C / 4, (Ld.K - 1) * Ld.dil, Ld.ring_mask, W>(c.buf, c.state + Ld.ring_off, c.tabs0, c.bar, c.lane);
+}
+
+// One layer array for the S frames a thread owns (cf. namb200::array_forward).
+//   hin[j][CIN]: the array's input (the raw sample for the first array, the previous array's last layer output after)
+//   head[j][C]: the head accumulator, initialised by the caller (zeros, or the previous array's head output)
+//   headout[j][HOUT]: this array's head output
+//   NEXT_AI: the array that follows (-1: none) -- its first layer's history is requested after this array's last tap read
+template <int AI, int NEXT_AI, int NT, int S>
+__device__ __forceinline__ void array_forward(TileCtx& c, const float (&hin)[S][spec::A[AI].CIN], const float (&cond)[S],
+                                              float (&head)[S][spec::A[AI].C], float (&hout)[S][spec::A[AI].C],
+                                              float (&headout)[S][spec::A[AI].HOUT])
+{
+  constexpr spec::Array A = spec::A[AI];
+  constexpr int C = A.C, CIN = A.CIN, HOUT = A.HOUT, P = C / 4;
+  constexpr int T = NT * S;
+  constexpr int W = spec::LS + T;
+  static_assert(A.head_kernel == 1, "convolutional heads are served by the generic fused kernel");
+  const int tid = threadIdx.x;
+  float4* const col0 = c.buf + spec::LS + tid; // this thread's first column of plane 0
+
+  // ---- rechannel (Conv1x1, no bias; model.cpp:492) -> this thread's columns of the tile
+#pragma unroll
+  for (int j = 0; j < S; j++)
+  {
+    float h[C];
+#pragma unroll
+    for (int o = 0; o < C; o++)
+      h[o] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < CIN; i++)
+#pragma unroll
+      for (int o = 0; o < C; o++)
+        h[o] = fmaf(spec::w(A.rech_off + i * C + o), hin[j][i], h[o]);
+#pragma unroll
+    for (int pl = 0; pl < P; pl++)
+      col0[pl * W + j * NT] = make_float4(h[4 * pl], h[4 * pl + 1], h[4 * pl + 2], h[4 * pl + 3]);
+  }
+
+  static_for<0, A.n_layers>([&](auto li_c) {
+    constexpr int LI = A.layer0 + decltype(li_c)::value;
+    constexpr bool last = (decltype(li_c)::value + 1 == A.n_layers);
+    constexpr spec::Layer Ld = spec::L[LI];
+    constexpr int K = Ld.K, dil = Ld.dil, L = (K - 1) * dil;
+    constexpr int w_conv = Ld.w_off, w_bias = w_conv + K * C * C, w_mix = w_bias + C, w_p = w_mix + C,
+                  w_pb = w_p + C * C;
+
+    fence_async_smem(); // my tile columns (generic stores) -> the bulk store below
+    __syncthreads(); // B0: the layer input is complete in the tile
+    mbar_wait(c.bar, c.phase); // .. and its history has landed in front of it
+    c.phase ^= 1u;
+    if (c.warp == 0) // newest columns -> ring (reads the tile until B1)
+      hist_store<P, L, Ld.ring_mask, W>(c.buf, c.state + Ld.ring_off, c.tabs0, c.tv, c.lane);
+
+    // ---- phase 1: z = b + M c + sum_k W_k h[t - (K-1-k) d];  a = act(z);  head += a
+    float acc[S][C];
+#pragma unroll
+    for (int j = 0; j < S; j++)
+#pragma unroll
+      for (int o = 0; o < C; o++)
+        acc[j][o] = fmaf(spec::w(w_mix + o), cond[j], spec::w(w_bias + o));
+#pragma unroll
+    for (int k = 0; k < K; k++)
+    {
+      const int off = (K - 1 - k) * dil;
+#pragma unroll
+      for (int pl = 0; pl < P; pl++)
+      {
+        float4 xq[S];
+#pragma unroll
+        for (int j = 0; j < S; j++)
+          xq[j] = col0[pl * W + j * NT - off];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < S; j++)
+          {
+            const float xs = (i == 0) ? xq[j].x : (i == 1) ? xq[j].y : (i == 2) ? xq[j].z : xq[j].w;
+#pragma unroll
+            for (int o = 0; o < C; o++)
+              acc[j][o] = fmaf(spec::w(w_conv + (k * C + 4 * pl + i) * C + o), xs, acc[j][o]);
+          }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < S; j++)
+    {
+      apply_activation<LI, C>(acc[j]);
+#pragma unroll
+      for (int q = 0; q < C / 2; q++) // model.cpp:530 (packed add: half the issue slots)
+        unpack2(add2(pack2(head[j][2 * q], head[j][2 * q + 1]), pack2(acc[j][2 * q], acc[j][2 * q + 1])), head[j][2 * q],
+                head[j][2 * q + 1]);
+    }
+    if (c.warp == 0 && c.lane < P)
+      bulk_wait_all(); // my ring stores are done: the tile may be rewritten, the rings may be re-read
+    __syncthreads(); // B1: every tap read of this layer's input is done
+    // the next unit's history lands under this layer's 1x1 phase
+    if constexpr (!last)
+      request_layer_history<AI, NT, S>(c, IntC<LI + 1>{});
+    else if constexpr (NEXT_AI >= 0)
+      request_layer_history<NEXT_AI, NT, S>(c, IntC<spec::A[NEXT_AI < 0 ? 0 : NEXT_AI].layer0>{});
+
+    // ---- phase 2: h_{l+1} = h_l + p + P a  (model.cpp:243,376)
+#pragma unroll
+    for (int j = 0; j < S; j++)
+    {
+      float hn[C];
+#pragma unroll
+      for (int pl = 0; pl < P; pl++)
+      {
+        const float4 own = col0[pl * W + j * NT];
+        hn[4 * pl] = own.x + spec::w(w_pb + 4 * pl);
+        hn[4 * pl + 1] = own.y + spec::w(w_pb + 4 * pl + 1);
+        hn[4 * pl + 2] = own.z + spec::w(w_pb + 4 * pl + 2);
+        hn[4 * pl + 3] = own.w + spec::w(w_pb + 4 * pl + 3);
+      }
+#pragma unroll
+      for (int i = 0; i < C; i++)
+#pragma unroll
+        for (int o = 0; o < C; o++)
+          hn[o] = fmaf(spec::w(w_p + i * C + o), acc[j][i], hn[o]);
+      if constexpr (!last)
+      {
+#pragma unroll
+        for (int pl = 0; pl < P; pl++)
+          col0[pl * W + j * NT] = make_float4(hn[4 * pl], hn[4 * pl + 1], hn[4 * pl + 2], hn[4 * pl + 3]);
+      }
+      else
+      {
+#pragma unroll
+        for (int o = 0; o < C; o++)
+          hout[j][o] = hn[o];
+      }
+    }
+  });
+
+  // ---- head rechannel (kernel size 1; model.cpp:548): headout = H head (+ g)
+#pragma unroll
+  for (int j = 0; j < S; j++)
+  {
+#pragma unroll
+    for (int ho = 0; ho < HOUT; ho++)
+      headout[j][ho] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < C; i++)
+#pragma unroll
+      for (int ho = 0; ho < HOUT; ho++)
+        headout[j][ho] = fmaf(spec::w(A.head_off + i * HOUT + ho), head[j][i], headout[j][ho]);
+#pragma unroll
+    for (int ho = 0; ho < HOUT; ho++)
+      headout[j][ho] += spec::w(A.head_off + C * HOUT + ho); // bias (zero when the head has none)
+  }
+}
+
+template <int NT, int S, int MINB>
+__device__ __forceinline__ void wavenet_spec_body(const SpecParams& p)
+{
+  constexpr int T = NT * S;
+  constexpr int W = spec::LS + T;
+  static_assert(spec::NA == 1 || spec::NA == 2, "one or two layer arrays");
+  extern __shared__ float4 spec_smem[]; // [Pmax][W] float4
+  __shared__ u64 bar;
+  const int tid = threadIdx.x;
+  TileCtx c;
+  c.buf = spec_smem;
+  c.bar = &bar;
+  c.phase = 0u;
+  c.warp = tid >> 5;
+  c.lane = tid & 31;
+  if (tid == 0)
+  {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  for (int stream = blockIdx.x; stream < p.batch; stream += gridDim.x)
+  {
+    c.state = p.state + (size_t)stream * p.state_stride;
+    const float* xin = p.in + (size_t)stream * p.in_stride;
+    float* yout = p.out + (size_t)stream * p.out_stride;
+    for (int t0 = 0; t0 < p.n_frames; t0 += T)
+    {
+      c.tv = min(T, p.n_frames - t0);
+      c.tabs0 = p.t_base + (u32)t0;
+      request_layer_history<0, NT, S>(c, IntC<spec::A[0].layer0>{});
+      float x[S][1], cond[S];
+#pragma unroll
+      for (int j = 0; j < S; j++)
+      {
+        const int f = j * NT + tid;
+        x[j][0] = (f < c.tv) ? __ldg(xin + t0 + f) : 0.0f;
+        cond[j] = x[j][0]; // no condition_dsp: condition == input (model.cpp:781)
+      }
+      float y[S];
+      constexpr int C0 = spec::A[0].C;
+      float head0[S][C0], hout0[S][C0], ho0[S][spec::A[0].HOUT];
+#pragma unroll
+      for (int j = 0; j < S; j++)
+#pragma unroll
+        for (int o = 0; o < C0; o++)
+          head0[j][o] = 0.0f; // model.cpp:469
+      if constexpr (spec::NA == 1)
+      {
+        array_forward<0, -1, NT, S>(c, x, cond, head0, hout0, ho0);
+#pragma unroll
+        for (int j = 0; j < S; j++)
+          y[j] = ho0[j][0];
+      }
+      else
+      {
+        array_forward<0, spec::NA - 1, NT, S>(c, x, cond, head0, hout0, ho0);
+        // second array: layer input = the previous array's layer output, head accumulator starts from the previous
+        // array's head output (model.cpp:846-848, :473-486)
+        constexpr int AI1 = spec::NA - 1;
+        constexpr int C1 = spec::A[AI1].C;
+        float head1[S][C1], hout1[S][C1], ho1[S][spec::A[AI1].HOUT];
+#pragma unroll
+        for (int j = 0; j < S; j++)
+#pragma unroll
+          for (int o = 0; o < C1; o++)
+            head1[j][o] = ho0[j][o];
+        array_forward<AI1, -1, NT, S>(c, hout0, cond, head1, hout1, ho1);
+#pragma unroll
+        for (int j = 0; j < S; j++)
+          y[j] = ho1[j][0];
+      }
+#pragma unroll
+      for (int j = 0; j < S; j++)
+      {
+        const int f = j * NT + tid;
+        if (f < c.tv)
+          yout[t0 + f] = spec::head_scale * y[j]; // model.cpp:888-897
+      }
+      // (no barrier here: the last layer's B1 already fenced every tap read before anything of the next tile is written)
+    }
+  }
+}
+
+} // namespace namb200_spec
+
+#ifndef NAMB200_SPEC_NT
+#define NAMB200_SPEC_NT 512
+#endif
+#ifndef NAMB200_SPEC_S
+#define NAMB200_SPEC_S 1
+#endif
+#ifndef NAMB200_SPEC_MINB
+#define NAMB200_SPEC_MINB 2
+#endif
+
+extern "C" __global__ void __launch_bounds__(NAMB200_SPEC_NT, NAMB200_SPEC_MINB)
+  wavenet_spec_kernel(const __grid_constant__ namb200_spec::SpecParams p)
+{
+  namb200_spec::wavenet_spec_body<NAMB200_SPEC_NT, NAMB200_SPEC_S, NAMB200_SPEC_MINB>(p);
+}
