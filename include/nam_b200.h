@@ -69,7 +69,13 @@ typedef struct nam_b200_options
                         tile-parallel mode (no buffer, tile c one layer behind tile c-1); 2 = never: one CTA walks a
                         stream's tiles in turn.  Tile-parallel launches need their CTAs co-resident: do not run
                         other kernels on the same GPU concurrently with such a call */
-  int32_t reserved[6];
+  int32_t jit; /* model-specialised WaveNet kernel (the model compiled to SASS by NVRTC at load time, weights as FFMA
+                  immediates; cubins cached under $NAM_B200_JIT_CACHE or <library dir>/jit_cache): 0 = library default
+                  (on for handles with max_batch >= 256; $NAM_B200_JIT=0/1 overrides), 1 = required (create fails
+                  with the reason if NVRTC or the model's shape rules it out), 2 = off.  Only calls that take the
+                  persistent one-CTA-per-stream path use it; every other mode runs the precompiled kernels on the
+                  same state */
+  int32_t reserved[5];
 } nam_b200_options;
 
 typedef struct nam_b200_info
@@ -86,7 +92,8 @@ typedef struct nam_b200_info
   int64_t state_bytes_per_stream; /* device bytes of per-stream history */
   double flops_per_frame; /* algorithmic FLOPs (2 x MACs) per frame per stream */
   int32_t kernel_variant; /* which CUDA specialisation serves this model (diagnostic) */
-  int32_t reserved[7];
+  int32_t jit_state; /* model-specialised kernel: 1 = active, 0 = not requested, -1 = requested but unavailable */
+  int32_t reserved[6];
 } nam_b200_info;
 
 /* Fill with defaults: device -1, max_batch 1, fast_tanh 0, prewarm_on_reset 1. */
@@ -156,6 +163,13 @@ double nam_b200_last_kernel_ms(nam_b200_model* m);
  * machine without a GPU (host-logic tests).  Returns 0, or the same error codes as create. */
 int nam_b200_inspect_json(const char* nam_json_text, int fast_tanh, char* out, int64_t capacity);
 int nam_b200_inspect_file(const char* nam_path, int fast_tanh, char* out, int64_t capacity);
+
+/* Host-only: build (or fetch from the cache) the model-specialised kernel of a WaveNet document without touching a
+ * GPU -- NVRTC cross-compiles -- and describe the outcome as a small JSON object: ok, from_cache, compile_seconds,
+ * cubin_bytes, threads, frames_per_thread, smem_bytes, why_not.  Used to pre-populate the cache at install time. */
+int nam_b200_jit_prepare_json(const char* nam_json_text, int fast_tanh, char* out, int64_t capacity);
+/* Diagnostic: how this handle's specialised kernel was obtained, or why it has none.  Returns the text's length. */
+int64_t nam_b200_jit_note(const nam_b200_model* m, char* out, int64_t capacity);
 
 /* Host-only: the sub-models of a slimmable document -- a "SlimmableContainer" file (NAM/container.cpp) or a WaveNet
  * whose layer arrays carry {"slimmable": {"method": "slice_channels_uniform"}} (NAM/wavenet/model.cpp:1290-1315,

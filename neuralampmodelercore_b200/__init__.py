@@ -14,6 +14,7 @@ from .dsp import (  # noqa: F401
     enable_fast_tanh,
     get_dsp,
     inspect,
+    jit_prepare,
     measure_fp32_tflops,
     submodels,
     using_fast_tanh,
@@ -25,6 +26,7 @@ __all__ = [
     "DSP",
     "get_dsp",
     "inspect",
+    "jit_prepare",
     "submodels",
     "enable_fast_tanh",
     "disable_fast_tanh",

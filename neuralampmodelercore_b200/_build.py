@@ -16,7 +16,8 @@ LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libnam_b200.so"
 INCLUDE = PKG.parent / "include"
 
-SOURCES = ["nam_b200.cu", "nam_model_spec.cpp", "json_lite.cpp", "wavenet_pack.cpp", "generic_pack.cpp", "nam_dsp_shim.cpp"]
+SOURCES = ["nam_b200.cu", "nam_model_spec.cpp", "json_lite.cpp", "wavenet_pack.cpp", "generic_pack.cpp", "nam_dsp_shim.cpp",
+           "jit_spec.cpp"]
 
 NVCC_FLAGS = [
     "-gencode",
@@ -49,20 +50,63 @@ def _stale() -> bool:
     return any(p.stat().st_mtime > t for p in deps if p.is_file())
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA/C++ source of the product into lib/libnam_b200.so (cross-compiles without a GPU)."""
-    if not force and not _stale():
-        return LIB_PATH
-    LIB_DIR.mkdir(exist_ok=True)
-    tmp = LIB_DIR / "libnam_b200.so.tmp"
-    cmd = [_nvcc(), *NVCC_FLAGS, f"-I{INCLUDE}", "-o", str(tmp), *[str(s) for s in sources()]]
+def embed_spec_source() -> Path:
+    """wavenet_spec.cuh -> csrc/wavenet_spec_src.inc, a C++ raw string literal: the library carries the source of the
+    model-specialised kernel and hands it to NVRTC at model-load time (jit_spec.cpp)."""
+    src = (CSRC / "wavenet_spec.cuh").read_text()
+    delim = "NAMB200SPEC"
+    assert f"){delim}\"" not in src
+    # a string literal may not exceed 64 KiB on some compilers: split into adjacent literals
+    parts, chunk = [], 12000
+    for i in range(0, len(src), chunk):
+        parts.append(f'R"{delim}({src[i:i + chunk]}){delim}"')
+    inc = CSRC / "wavenet_spec_src.inc"
+    text = "// generated from wavenet_spec.cuh by _build.py -- do not edit\n" + "\n".join(parts) + "\n"
+    if not inc.exists() or inc.read_text() != text:
+        inc.write_text(text)
+    return inc
+
+
+def _compile_object(src: Path, obj: Path, verbose: bool) -> str:
+    cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f != "-shared"], f"-I{INCLUDE}", "-c", "-o", str(obj), str(src)]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
+        cmd[1:1] = ["-Xptxas", "-v"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    return proc.stderr
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every CUDA/C++ source of the product into lib/libnam_b200.so (cross-compiles without a GPU).
+    One object per source under lib/obj/ (recompiled when the source or any header is newer), compiled in parallel,
+    then linked: touching the JIT host code does not recompile the kernels."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    embed_spec_source()
+    if not force and not _stale():
+        return LIB_PATH
+    LIB_DIR.mkdir(exist_ok=True)
+    obj_dir = LIB_DIR / "obj"
+    obj_dir.mkdir(exist_ok=True)
+    headers = [p for p in list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inc")) + list(INCLUDE.rglob("*.h"))]
+    # which headers a source pulls in, by name (cheap and conservative enough: a miss only costs a rebuild)
+    jobs = []
+    for src in sources():
+        obj = obj_dir / (src.name + ".o")
+        text = src.read_text()
+        deps = [src] + [h for h in headers if h.name in text or src.suffix == ".cu"]
+        if force or not obj.exists() or any(d.stat().st_mtime > obj.stat().st_mtime for d in deps):
+            jobs.append((src, obj))
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        logs = list(ex.map(lambda j: _compile_object(j[0], j[1], verbose), jobs))
+    tmp = LIB_DIR / "libnam_b200.so.tmp"
+    cmd = [_nvcc(), "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp),
+           *[str(obj_dir / (s.name + ".o")) for s in sources()], "-ldl"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     os.replace(tmp, LIB_PATH)
     if verbose:
-        print(proc.stderr)
+        print("\n".join(logs))
     return LIB_PATH

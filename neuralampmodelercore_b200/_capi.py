@@ -22,7 +22,8 @@ class Options(C.Structure):
         ("ctas_per_sm", C.c_int32),
         ("kernel_geometry", C.c_int32),
         ("tile_mode", C.c_int32),
-        ("reserved", C.c_int32 * 6),
+        ("jit", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -46,7 +47,8 @@ class Info(C.Structure):
         ("state_bytes_per_stream", C.c_int64),
         ("flops_per_frame", C.c_double),
         ("kernel_variant", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("jit_state", C.c_int32),
+        ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -75,6 +77,8 @@ EXPORTED_SYMBOLS = [
     "nam_b200_inspect_json",
     "nam_b200_inspect_file",
     "nam_b200_submodel_json",
+    "nam_b200_jit_prepare_json",
+    "nam_b200_jit_note",
 ]
 
 
@@ -127,6 +131,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.nam_b200_inspect_file.restype = C.c_int
     lib.nam_b200_submodel_json.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_double), C.c_char_p, C.c_int64]
     lib.nam_b200_submodel_json.restype = C.c_int64
+    lib.nam_b200_jit_prepare_json.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int64]
+    lib.nam_b200_jit_prepare_json.restype = C.c_int
+    lib.nam_b200_jit_note.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    lib.nam_b200_jit_note.restype = C.c_int64
     lib.nam_b200_measure_fp32_tflops.argtypes = [C.c_int, C.c_int]
     lib.nam_b200_measure_fp32_tflops.restype = C.c_double
     for name in (

@@ -252,8 +252,16 @@ SpecBuild build_spec_kernel(const WaveNetPlan& plan, const SpecGeometry& g)
   for (int a = 0; a < plan.n_arrays; a++)
     r.max_planes = std::max(r.max_planes, plan.cp[a] / 4);
 
+  // development aid: $NAM_B200_SPEC_SOURCE names a wavenet_spec.cuh to use instead of the embedded copy
+  std::string kernel_source = kSpecKernelSource;
+  if (const char* e = std::getenv("NAM_B200_SPEC_SOURCE"))
+  {
+    std::vector<char> txt;
+    if (*e && read_file(e, txt))
+      kernel_source.assign(txt.begin(), txt.end());
+  }
   const std::string header = spec_header_source(plan);
-  const std::string opts_text = "-arch=sm_100a -std=c++17 -DNT=" + std::to_string(g.nt) + " -DS=" + std::to_string(g.s)
+  const std::string opts_text = "-arch=sm_100a -std=c++17 -default-device -DNT=" + std::to_string(g.nt) + " -DS=" + std::to_string(g.s)
                                 + " -DMINB=" + std::to_string(g.min_ctas);
   Nvrtc& n = nvrtc();
   int vmaj = 0, vmin = 0;
@@ -261,7 +269,7 @@ SpecBuild build_spec_kernel(const WaveNetPlan& plan, const SpecGeometry& g)
     n.Version(&vmaj, &vmin);
   uint64_t h = 1469598103934665603ull;
   h = fnv1a(h, header.data(), header.size());
-  h = fnv1a(h, kSpecKernelSource, std::strlen(kSpecKernelSource));
+  h = fnv1a(h, kernel_source.data(), kernel_source.size());
   h = fnv1a(h, opts_text.data(), opts_text.size());
   char name[64];
   std::snprintf(name, sizeof name, "wavenet_spec_%016llx.cubin", (unsigned long long)h);
@@ -280,7 +288,7 @@ SpecBuild build_spec_kernel(const WaveNetPlan& plan, const SpecGeometry& g)
 
   const auto t0 = std::chrono::steady_clock::now();
   const std::string source = header + "\n#include \"wavenet_spec.cuh\"\n";
-  const char* hdr_src[] = {kSpecKernelSource};
+  const char* hdr_src[] = {kernel_source.c_str()};
   const char* hdr_name[] = {"wavenet_spec.cuh"};
   nvrtcProgram prog = nullptr;
   int rc = n.CreateProgram(&prog, source.c_str(), "wavenet_spec_model.cu", 1, hdr_src, hdr_name);
@@ -292,7 +300,9 @@ SpecBuild build_spec_kernel(const WaveNetPlan& plan, const SpecGeometry& g)
   const std::string d_nt = "-DNAMB200_SPEC_NT=" + std::to_string(g.nt);
   const std::string d_s = "-DNAMB200_SPEC_S=" + std::to_string(g.s);
   const std::string d_mb = "-DNAMB200_SPEC_MINB=" + std::to_string(g.min_ctas);
-  const char* copts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", d_nt.c_str(), d_s.c_str(), d_mb.c_str()};
+  // -default-device: the layer loop is a generic lambda, which NVRTC would otherwise take for a host function
+  const char* copts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device",
+                         d_nt.c_str(),                 d_s.c_str(),  d_mb.c_str()};
   rc = n.CompileProgram(prog, (int)(sizeof copts / sizeof copts[0]), copts);
   if (rc != 0)
   {

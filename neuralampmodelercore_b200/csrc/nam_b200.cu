@@ -21,6 +21,7 @@
 #include "wavenet_tc.cuh"
 #include "generic_pack.h"
 #include "wavenet_generic.cuh"
+#include "jit_spec.h"
 
 using namespace namb200;
 
@@ -364,6 +365,14 @@ struct nam_b200_model
   int wn_ctas_short[2] = {0, 0}; // same for the short-call (multi-stream tile) geometries 2 / 3
   int wn_geometry = 1; // 0 / 1: index into kWnGeom (FFMA kernel); 2: tensor-core kernel (wavenet_tc.cuh)
   float* d_tc_blob = nullptr; // per-layer B-operand images of the tensor-core kernel
+  // model-specialised kernel (wavenet_spec.cuh compiled for this model by NVRTC, jit_spec.cpp): the throughput path
+  cudaLibrary_t spec_lib = nullptr;
+  cudaKernel_t spec_kernel = nullptr;
+  SpecGeometry spec_geom;
+  size_t spec_smem = 0;
+  int spec_ctas_per_sm = 0;
+  int spec_state = 0; // 0 = not used, 1 = active, -1 = wanted but unavailable (spec_note says why)
+  std::string spec_note;
   // general WaveNet kernel (wavenet_generic.cuh): every option the fused kernels do not specialise
   bool use_generic = false;
   GenericPlan gplan;
@@ -404,6 +413,8 @@ struct nam_b200_model
       cudaFree(d_tc_blob);
     if (d_glayers)
       cudaFree(d_glayers);
+    if (spec_lib)
+      cudaLibraryUnload(spec_lib);
     if (d_tile_flags)
       cudaFree(d_tile_flags);
     if (d_hist)
@@ -798,6 +809,88 @@ int occupancy_tc_dispatch(int c0, int c1, size_t smem)
 }
 
 // `stream0`: index of the handle's stream that d_in / d_out row 0 belongs to (chunked host calls)
+// ---- model-specialised kernel (wavenet_spec.cuh, compiled per model by jit_spec.cpp) ----------------------------------
+// Mirror of namb200_spec::SpecParams (wavenet_spec.cuh): the kernel's single by-value parameter.
+struct SpecKernelParams
+{
+  float* state;
+  long state_stride;
+  const float* in;
+  float* out;
+  long in_stride, out_stride;
+  int batch, n_frames;
+  uint32_t t_base;
+};
+
+// Decide whether this handle gets a specialised kernel, build / fetch it, load it.  jit option: 0 = auto (on for
+// throughput handles: max_batch >= 256, where one compilation pays for itself within the first calls), 1 = required
+// (creation fails with the reason if it cannot be had), 2 = off.  $NAM_B200_JIT=0/1 overrides "auto".
+void setup_spec_kernel(nam_b200_model* m)
+{
+  int mode = m->opts.jit;
+  if (mode == 0)
+  {
+    const char* e = std::getenv("NAM_B200_JIT");
+    if (e && *e)
+      mode = (e[0] == '0') ? 2 : 1;
+  }
+  const bool wanted = mode == 1 || (mode == 0 && m->opts.max_batch >= 256);
+  if (!wanted || m->opts.kernel_geometry != 0)
+    return;
+  SpecGeometry g;
+  SpecBuild b = build_spec_kernel(m->plan, g);
+  if (!b.ok)
+  {
+    m->spec_state = -1;
+    m->spec_note = b.why_not;
+    if (mode == 1)
+      throw std::runtime_error("model-specialised kernel unavailable: " + b.why_not);
+    return;
+  }
+  auto check = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess)
+      throw CudaError(std::string(what) + " failed: " + cudaGetErrorString(e));
+  };
+  try
+  {
+    check(cudaLibraryLoadData(&m->spec_lib, b.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0), "cudaLibraryLoadData");
+    check(cudaLibraryGetKernel(&m->spec_kernel, m->spec_lib, spec_kernel_name()), "cudaLibraryGetKernel");
+    m->spec_geom = b.geom;
+    m->spec_smem = b.smem_bytes();
+    check(cudaFuncSetAttribute((const void*)m->spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->spec_smem),
+          "cudaFuncSetAttribute(spec kernel)");
+    int occ = 0;
+    check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)m->spec_kernel, b.geom.nt, m->spec_smem),
+          "cudaOccupancyMaxActiveBlocksPerMultiprocessor(spec kernel)");
+    if (occ < 1)
+      throw CudaError("the specialised kernel does not fit on an SM");
+    m->spec_ctas_per_sm = occ;
+    m->spec_state = 1;
+    m->spec_note = b.from_cache ? "cubin from cache" : "compiled in " + std::to_string(b.compile_seconds) + " s";
+  }
+  catch (const CudaError& ex)
+  {
+    if (m->spec_lib)
+      cudaLibraryUnload(m->spec_lib);
+    m->spec_lib = nullptr;
+    m->spec_kernel = nullptr;
+    m->spec_state = -1;
+    m->spec_note = ex.what();
+    if (mode == 1)
+      throw;
+  }
+}
+
+void launch_wavenet_spec(nam_b200_model* m, const WaveNetKernelParams& kp, cudaStream_t st)
+{
+  SpecKernelParams sp{kp.state, kp.state_stride, kp.in, kp.out, kp.in_stride, kp.out_stride, kp.batch, kp.n_frames, kp.t_base};
+  void* args[] = {&sp};
+  int grid = std::min(kp.batch, m->spec_ctas_per_sm * m->sm_count);
+  if (grid < 1)
+    grid = 1;
+  CUDA_CHECK(cudaLaunchKernel((const void*)m->spec_kernel, dim3(grid), dim3(m->spec_geom.nt), args, m->spec_smem, st));
+}
+
 void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batch, int n_frames, long in_stride,
                     long out_stride, cudaStream_t st, int stream0 = 0)
 {
@@ -959,6 +1052,12 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
       return;
     }
   }
+  if (m->spec_state == 1 && m->opts.kernel_geometry == 0)
+  {
+    launch_wavenet_spec(m, kp, st);
+    m->launches++;
+    return;
+  }
   int grid = std::min(batch, per_sm * m->sm_count);
   if (grid < 1)
     grid = 1;
@@ -1082,6 +1181,8 @@ int wavenet_chunk_streams(nam_b200_model* m)
 {
   if (m->spec.arch != Arch::WaveNet || m->use_generic)
     return 0;
+  if (m->spec_state == 1)
+    return 4 * m->spec_ctas_per_sm * m->sm_count;
   const int per_sm = m->wn_ctas_per_sm > 0 ? m->wn_ctas_per_sm : (m->wn_geometry == 0 ? 3 : 2);
   return 4 * per_sm * m->sm_count;
 }
@@ -1347,6 +1448,7 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
           m->wn_geometry = (m->opts.kernel_geometry == 1) ? 0 : 1;
         if (m->wn_geometry < 2 && wavenet_smem_bytes(m->plan, m->wn_geometry) > 227 * 1024)
           return fail(NAM_B200_ERR_UNSUPPORTED, "WaveNet weights do not fit in shared memory");
+        setup_spec_kernel(m.get());
         break;
       }
       case Arch::LSTM:
@@ -1721,6 +1823,58 @@ int nam_b200_inspect_json(const char* nam_json_text, int fast_tanh, char* out, i
   }
 }
 
+int nam_b200_jit_prepare_json(const char* nam_json_text, int fast_tanh, char* out, int64_t capacity)
+{
+  if (!nam_json_text)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null argument");
+  LoadOptions lo;
+  lo.fast_tanh = fast_tanh != 0;
+  try
+  {
+    const ModelSpec ms = model_spec_from_text(nam_json_text, lo);
+    if (ms.arch != Arch::WaveNet)
+      return fail(NAM_B200_ERR_UNSUPPORTED, "only WaveNets have a model-specialised kernel");
+    const WaveNetPlan plan = plan_wavenet(ms);
+    const SpecBuild b = build_spec_kernel(plan, SpecGeometry{});
+    std::string why;
+    for (char c : b.why_not.substr(0, 600))
+      why += (c == '"' || c == '\\') ? '\'' : (c == '\n' ? ' ' : c);
+    char buf[1024];
+    std::snprintf(buf, sizeof buf,
+                  "{\"ok\": %s, \"from_cache\": %s, \"compile_seconds\": %.3f, \"cubin_bytes\": %zu, \"threads\": %d, "
+                  "\"frames_per_thread\": %d, \"smem_bytes\": %zu, \"why_not\": \"%s\"}",
+                  b.ok ? "true" : "false", b.from_cache ? "true" : "false", b.compile_seconds, b.cubin.size(), b.geom.nt,
+                  b.geom.s, b.ok ? b.smem_bytes() : (size_t)0, why.c_str());
+    if (out && capacity > 0)
+    {
+      std::strncpy(out, buf, (size_t)capacity - 1);
+      out[capacity - 1] = '\0';
+    }
+    return NAM_B200_OK;
+  }
+  catch (const json::ParseError& ex)
+  {
+    return fail(NAM_B200_ERR_FILE, ex.what());
+  }
+  catch (const std::exception& ex)
+  {
+    return fail(NAM_B200_ERR_MODEL, ex.what());
+  }
+}
+
+int64_t nam_b200_jit_note(const nam_b200_model* m, char* out, int64_t capacity)
+{
+  m = active_model(m);
+  if (!m)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null model handle");
+  if (out && capacity > 0)
+  {
+    std::strncpy(out, m->spec_note.c_str(), (size_t)capacity - 1);
+    out[capacity - 1] = '\0';
+  }
+  return (int64_t)m->spec_note.size();
+}
+
 int nam_b200_inspect_file(const char* nam_path, int fast_tanh, char* out, int64_t capacity)
 {
   if (!nam_path)
@@ -1797,6 +1951,7 @@ int nam_b200_get_info(const nam_b200_model* m, nam_b200_info* info)
   r.state_bytes_per_stream = (int64_t)m->state_stride * 4;
   r.flops_per_frame = m->flops_per_frame;
   r.kernel_variant = m->variant;
+  r.jit_state = m->spec_state;
   const size_t n = std::min<size_t>(sizeof(r), (size_t)std::max(info->struct_size, 0));
   const int32_t user_size = info->struct_size;
   std::memcpy(info, &r, n);

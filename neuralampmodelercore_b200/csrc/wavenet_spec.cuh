@@ -127,46 +127,145 @@ __device__ __forceinline__ float act_sigmoid(float x)
   return rcp_approx(1.0f + expf(-x));
 }
 
+// ---- frame vectors -------------------------------------------------------------------------------------------------------
+// A thread owns S frames of the tile: {tid} for S = 1 (V = float), {tid, tid + NT} for S = 2 (V = a packed f32x2 pair,
+// low half = frame tid).  Everything a layer does is written once over V.  For S = 2 one instruction serves both
+// frames: `FFMA2 Racc, Rx.F32x2, <imm32>, Racc` -- the packed FMA takes the weight as a BROADCAST IMMEDIATE, so the
+// weight stream costs one issue slot per weight for two frames and the kernel is bound by the FMA pipe itself instead
+// of by instruction issue (profiles/r02a_*: S = 1 issues 16,800 instructions per warp-frame, 79 % of them FFMA).
+template <int S>
+struct FrameVec;
+template <>
+struct FrameVec<1>
+{
+  typedef float type;
+};
+template <>
+struct FrameVec<2>
+{
+  typedef u64 type;
+};
+
+__device__ __forceinline__ float vfma(const float x, const float w, const float a)
+{
+  return fmaf(w, x, a);
+}
+__device__ __forceinline__ u64 vfma(const u64 x, const float w, const u64 a)
+{
+  return fma2(x, dup2(w), a);
+}
+__device__ __forceinline__ float vadd(const float a, const float b)
+{
+  return a + b;
+}
+__device__ __forceinline__ u64 vadd(const u64 a, const u64 b)
+{
+  return add2(a, b);
+}
+__device__ __forceinline__ float vaddc(const float a, const float c)
+{
+  return a + c;
+}
+__device__ __forceinline__ u64 vaddc(const u64 a, const float c)
+{
+  return add2(a, dup2(c));
+}
+__device__ __forceinline__ void vsplat(float& v, const float c)
+{
+  v = c;
+}
+__device__ __forceinline__ void vsplat(u64& v, const float c)
+{
+  v = dup2(c);
+}
+// the 4 channels of one plane at this thread's column(s), `p` = address of the frame-tid column
+template <int NT>
+__device__ __forceinline__ void vload4(const float4* p, float (&x)[4])
+{
+  const float4 q = *p;
+  x[0] = q.x, x[1] = q.y, x[2] = q.z, x[3] = q.w;
+}
+template <int NT>
+__device__ __forceinline__ void vload4(const float4* p, u64 (&x)[4])
+{
+  const float4 a = p[0], b = p[NT];
+  x[0] = pack2(a.x, b.x), x[1] = pack2(a.y, b.y), x[2] = pack2(a.z, b.z), x[3] = pack2(a.w, b.w);
+}
+template <int NT>
+__device__ __forceinline__ void vstore4(float4* p, const float (&x)[4])
+{
+  *p = make_float4(x[0], x[1], x[2], x[3]);
+}
+template <int NT>
+__device__ __forceinline__ void vstore4(float4* p, const u64 (&x)[4])
+{
+  float4 a, b;
+  unpack2(x[0], a.x, b.x), unpack2(x[1], a.y, b.y), unpack2(x[2], a.z, b.z), unpack2(x[3], a.w, b.w);
+  p[0] = a, p[NT] = b;
+}
+
+// one element of layer LI's activation, channel i (activations.h:59-133)
+template <int LI, int C>
+__device__ __forceinline__ float act_scalar(const float x, const int i)
+{
+  constexpr spec::Layer Ld = spec::L[LI];
+  if constexpr (Ld.act == ACT_TANH)
+    return tanhf(x);
+  else if constexpr (Ld.act == ACT_HARDTANH)
+    return fminf(fmaxf(x, -1.0f), 1.0f);
+  else if constexpr (Ld.act == ACT_RELU)
+    return x > 0.0f ? x : 0.0f;
+  else if constexpr (Ld.act == ACT_LEAKYRELU)
+    return x > 0.0f ? x : Ld.ap0 * x;
+  else if constexpr (Ld.act == ACT_PRELU)
+    return x > 0.0f ? x : spec::w(Ld.w_off + Ld.K * C * C + C + C + C * C + C + i) * x;
+  else if constexpr (Ld.act == ACT_SIGMOID)
+    return act_sigmoid(x);
+  else if constexpr (Ld.act == ACT_SILU)
+    return x * act_sigmoid(x);
+  else if constexpr (Ld.act == ACT_HARDSWISH)
+  {
+    const float t = x + 3.0f;
+    const float cl = t < 0.0f ? 0.0f : (t > 6.0f ? 6.0f : t);
+    return x * cl * (1.0f / 6.0f);
+  }
+  else if constexpr (Ld.act == ACT_LEAKYHARDTANH)
+    return x < Ld.ap0 ? (x - Ld.ap0) * Ld.ap2 + Ld.ap0 : (x > Ld.ap1 ? (x - Ld.ap1) * Ld.ap3 + Ld.ap1 : x);
+  else if constexpr (Ld.act == ACT_SOFTSIGN)
+    return x * rcp_approx(1.0f + fabsf(x));
+  else
+    return x;
+}
+
 template <int LI, int C>
 __device__ __forceinline__ void apply_activation(float (&v)[C])
 {
-  constexpr spec::Layer Ld = spec::L[LI];
-  if constexpr (Ld.act == ACT_FASTTANH)
+  if constexpr (spec::L[LI].act == ACT_FASTTANH)
   {
 #pragma unroll
-    for (int q = 0; q < C / 2; q++)
+    for (int q = 0; q < C / 2; q++) // two channels of the frame per packed operation
       unpack2(fast_tanh2(pack2(v[2 * q], v[2 * q + 1])), v[2 * q], v[2 * q + 1]);
   }
   else
   {
 #pragma unroll
     for (int i = 0; i < C; i++)
+      v[i] = act_scalar<LI, C>(v[i], i);
+  }
+}
+template <int LI, int C>
+__device__ __forceinline__ void apply_activation(u64 (&v)[C])
+{
+#pragma unroll
+  for (int i = 0; i < C; i++)
+  {
+    if constexpr (spec::L[LI].act == ACT_FASTTANH)
+      v[i] = fast_tanh2(v[i]); // the two frames of the channel per packed operation
+    else
     {
-      const float x = v[i];
-      if constexpr (Ld.act == ACT_TANH)
-        v[i] = tanhf(x);
-      else if constexpr (Ld.act == ACT_HARDTANH)
-        v[i] = fminf(fmaxf(x, -1.0f), 1.0f);
-      else if constexpr (Ld.act == ACT_RELU)
-        v[i] = x > 0.0f ? x : 0.0f;
-      else if constexpr (Ld.act == ACT_LEAKYRELU)
-        v[i] = x > 0.0f ? x : Ld.ap0 * x;
-      else if constexpr (Ld.act == ACT_PRELU)
-        v[i] = x > 0.0f ? x : spec::w(Ld.w_off + Ld.K * C * C + C + C + C * C + C + i) * x;
-      else if constexpr (Ld.act == ACT_SIGMOID)
-        v[i] = act_sigmoid(x);
-      else if constexpr (Ld.act == ACT_SILU)
-        v[i] = x * act_sigmoid(x);
-      else if constexpr (Ld.act == ACT_HARDSWISH)
-      {
-        const float t = x + 3.0f;
-        const float cl = t < 0.0f ? 0.0f : (t > 6.0f ? 6.0f : t);
-        v[i] = x * cl * (1.0f / 6.0f);
-      }
-      else if constexpr (Ld.act == ACT_LEAKYHARDTANH)
-        v[i] = x < Ld.ap0 ? (x - Ld.ap0) * Ld.ap2 + Ld.ap0 : (x > Ld.ap1 ? (x - Ld.ap1) * Ld.ap3 + Ld.ap1 : x);
-      else if constexpr (Ld.act == ACT_SOFTSIGN)
-        v[i] = x * rcp_approx(1.0f + fabsf(x));
+      float a, b;
+      unpack2(v[i], a, b);
+      v[i] = pack2(act_scalar<LI, C>(a, i), act_scalar<LI, C>(b, i));
     }
   }
 }
@@ -307,40 +406,39 @@ __device__ __forceinline__ void request_layer_history(TileCtx& c, IntC<LI>)
     hist_load<C / 4, (Ld.K - 1) * Ld.dil, Ld.ring_mask, W>(c.buf, c.state + Ld.ring_off, c.tabs0, c.bar, c.lane);
 }
 
-// One layer array for the S frames a thread owns (cf. namb200::array_forward).
-//   hin[j][CIN]: the array's input (the raw sample for the first array, the previous array's last layer output after)
-//   head[j][C]: the head accumulator, initialised by the caller (zeros, or the previous array's head output)
-//   headout[j][HOUT]: this array's head output
+// One layer array for the S frames a thread owns (cf. namb200::array_forward), V = FrameVec<S>.
+//   hin[CIN]: the array's input (the raw sample for the first array, the previous array's last layer output after)
+//   head[C]: the head accumulator, initialised by the caller (zeros, or the previous array's head output)
+//   headout[HOUT]: this array's head output
 //   NEXT_AI: the array that follows (-1: none) -- its first layer's history is requested after this array's last tap read
-template <int AI, int NEXT_AI, int NT, int S>
-__device__ __forceinline__ void array_forward(TileCtx& c, const float (&hin)[S][spec::A[AI].CIN], const float (&cond)[S],
-                                              float (&head)[S][spec::A[AI].C], float (&hout)[S][spec::A[AI].C],
-                                              float (&headout)[S][spec::A[AI].HOUT])
+template <int AI, int NEXT_AI, int NT, int S, typename V>
+__device__ __forceinline__ void array_forward(TileCtx& c, const V (&hin)[spec::A[AI].CIN], const V cond, V (&head)[spec::A[AI].C],
+                                              V (&hout)[spec::A[AI].C], V (&headout)[spec::A[AI].HOUT])
 {
   constexpr spec::Array A = spec::A[AI];
   constexpr int C = A.C, CIN = A.CIN, HOUT = A.HOUT, P = C / 4;
   constexpr int T = NT * S;
   constexpr int W = spec::LS + T;
   static_assert(A.head_kernel == 1, "convolutional heads are served by the generic fused kernel");
-  const int tid = threadIdx.x;
-  float4* const col0 = c.buf + spec::LS + tid; // this thread's first column of plane 0
+  float4* const col0 = c.buf + spec::LS + threadIdx.x; // this thread's (first) column of plane 0
 
   // ---- rechannel (Conv1x1, no bias; model.cpp:492) -> this thread's columns of the tile
-#pragma unroll
-  for (int j = 0; j < S; j++)
   {
-    float h[C];
+    V h[C];
 #pragma unroll
     for (int o = 0; o < C; o++)
-      h[o] = 0.0f;
+      vsplat(h[o], 0.0f);
 #pragma unroll
     for (int i = 0; i < CIN; i++)
 #pragma unroll
       for (int o = 0; o < C; o++)
-        h[o] = fmaf(spec::w(A.rech_off + i * C + o), hin[j][i], h[o]);
+        h[o] = vfma(hin[i], spec::w(A.rech_off + i * C + o), h[o]);
 #pragma unroll
     for (int pl = 0; pl < P; pl++)
-      col0[pl * W + j * NT] = make_float4(h[4 * pl], h[4 * pl + 1], h[4 * pl + 2], h[4 * pl + 3]);
+    {
+      const V q[4] = {h[4 * pl], h[4 * pl + 1], h[4 * pl + 2], h[4 * pl + 3]};
+      vstore4<NT>(col0 + pl * W, q);
+    }
   }
 
   static_for<0, A.n_layers>([&](auto li_c) {
@@ -359,12 +457,14 @@ __device__ __forceinline__ void array_forward(TileCtx& c, const float (&hin)[S][
       hist_store<P, L, Ld.ring_mask, W>(c.buf, c.state + Ld.ring_off, c.tabs0, c.tv, c.lane);
 
     // ---- phase 1: z = b + M c + sum_k W_k h[t - (K-1-k) d];  a = act(z);  head += a
-    float acc[S][C];
+    V acc[C];
 #pragma unroll
-    for (int j = 0; j < S; j++)
-#pragma unroll
-      for (int o = 0; o < C; o++)
-        acc[j][o] = fmaf(spec::w(w_mix + o), cond[j], spec::w(w_bias + o));
+    for (int o = 0; o < C; o++)
+    {
+      V b;
+      vsplat(b, spec::w(w_bias + o));
+      acc[o] = vfma(cond, spec::w(w_mix + o), b);
+    }
 #pragma unroll
     for (int k = 0; k < K; k++)
     {
@@ -372,30 +472,27 @@ __device__ __forceinline__ void array_forward(TileCtx& c, const float (&hin)[S][
 #pragma unroll
       for (int pl = 0; pl < P; pl++)
       {
-        float4 xq[S];
-#pragma unroll
-        for (int j = 0; j < S; j++)
-          xq[j] = col0[pl * W + j * NT - off];
+        V x[4];
+        vload4<NT>(col0 + pl * W - off, x);
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
-          for (int j = 0; j < S; j++)
-          {
-            const float xs = (i == 0) ? xq[j].x : (i == 1) ? xq[j].y : (i == 2) ? xq[j].z : xq[j].w;
-#pragma unroll
-            for (int o = 0; o < C; o++)
-              acc[j][o] = fmaf(spec::w(w_conv + (k * C + 4 * pl + i) * C + o), xs, acc[j][o]);
-          }
+          for (int o = 0; o < C; o++)
+            acc[o] = vfma(x[i], spec::w(w_conv + (k * C + 4 * pl + i) * C + o), acc[o]);
       }
     }
-#pragma unroll
-    for (int j = 0; j < S; j++)
+    apply_activation<LI, C>(acc);
+    if constexpr (S == 1)
     {
-      apply_activation<LI, C>(acc[j]);
 #pragma unroll
-      for (int q = 0; q < C / 2; q++) // model.cpp:530 (packed add: half the issue slots)
-        unpack2(add2(pack2(head[j][2 * q], head[j][2 * q + 1]), pack2(acc[j][2 * q], acc[j][2 * q + 1])), head[j][2 * q],
-                head[j][2 * q + 1]);
+      for (int q = 0; q < C / 2; q++) // model.cpp:530 (packed add over channel pairs: half the issue slots)
+        unpack2(add2(pack2(head[2 * q], head[2 * q + 1]), pack2(acc[2 * q], acc[2 * q + 1])), head[2 * q], head[2 * q + 1]);
+    }
+    else
+    {
+#pragma unroll
+      for (int o = 0; o < C; o++)
+        head[o] = vadd(head[o], acc[o]); // model.cpp:530
     }
     if (c.warp == 0 && c.lane < P)
       bulk_wait_all(); // my ring stores are done: the tile may be rewritten, the rings may be re-read
@@ -407,62 +504,56 @@ __device__ __forceinline__ void array_forward(TileCtx& c, const float (&hin)[S][
       request_layer_history<NEXT_AI, NT, S>(c, IntC<spec::A[NEXT_AI < 0 ? 0 : NEXT_AI].layer0>{});
 
     // ---- phase 2: h_{l+1} = h_l + p + P a  (model.cpp:243,376)
+    V hn[C];
 #pragma unroll
-    for (int j = 0; j < S; j++)
+    for (int pl = 0; pl < P; pl++)
     {
-      float hn[C];
+      V own[4];
+      vload4<NT>(col0 + pl * W, own);
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        hn[4 * pl + i] = vaddc(own[i], spec::w(w_pb + 4 * pl + i));
+    }
+#pragma unroll
+    for (int i = 0; i < C; i++)
+#pragma unroll
+      for (int o = 0; o < C; o++)
+        hn[o] = vfma(acc[i], spec::w(w_p + i * C + o), hn[o]);
+    if constexpr (!last)
+    {
 #pragma unroll
       for (int pl = 0; pl < P; pl++)
       {
-        const float4 own = col0[pl * W + j * NT];
-        hn[4 * pl] = own.x + spec::w(w_pb + 4 * pl);
-        hn[4 * pl + 1] = own.y + spec::w(w_pb + 4 * pl + 1);
-        hn[4 * pl + 2] = own.z + spec::w(w_pb + 4 * pl + 2);
-        hn[4 * pl + 3] = own.w + spec::w(w_pb + 4 * pl + 3);
+        const V q[4] = {hn[4 * pl], hn[4 * pl + 1], hn[4 * pl + 2], hn[4 * pl + 3]};
+        vstore4<NT>(col0 + pl * W, q);
       }
+    }
+    else
+    {
 #pragma unroll
-      for (int i = 0; i < C; i++)
-#pragma unroll
-        for (int o = 0; o < C; o++)
-          hn[o] = fmaf(spec::w(w_p + i * C + o), acc[j][i], hn[o]);
-      if constexpr (!last)
-      {
-#pragma unroll
-        for (int pl = 0; pl < P; pl++)
-          col0[pl * W + j * NT] = make_float4(hn[4 * pl], hn[4 * pl + 1], hn[4 * pl + 2], hn[4 * pl + 3]);
-      }
-      else
-      {
-#pragma unroll
-        for (int o = 0; o < C; o++)
-          hout[j][o] = hn[o];
-      }
+      for (int o = 0; o < C; o++)
+        hout[o] = hn[o];
     }
   });
 
   // ---- head rechannel (kernel size 1; model.cpp:548): headout = H head (+ g)
 #pragma unroll
-  for (int j = 0; j < S; j++)
-  {
+  for (int ho = 0; ho < HOUT; ho++)
+    vsplat(headout[ho], 0.0f);
+#pragma unroll
+  for (int i = 0; i < C; i++)
 #pragma unroll
     for (int ho = 0; ho < HOUT; ho++)
-      headout[j][ho] = 0.0f;
+      headout[ho] = vfma(head[i], spec::w(A.head_off + i * HOUT + ho), headout[ho]);
 #pragma unroll
-    for (int i = 0; i < C; i++)
-#pragma unroll
-      for (int ho = 0; ho < HOUT; ho++)
-        headout[j][ho] = fmaf(spec::w(A.head_off + i * HOUT + ho), head[j][i], headout[j][ho]);
-#pragma unroll
-    for (int ho = 0; ho < HOUT; ho++)
-      headout[j][ho] += spec::w(A.head_off + C * HOUT + ho); // bias (zero when the head has none)
-  }
+  for (int ho = 0; ho < HOUT; ho++)
+    headout[ho] = vaddc(headout[ho], spec::w(A.head_off + C * HOUT + ho)); // bias (zero when the head has none)
 }
 
 template <int NT, int S, int MINB>
 __device__ __forceinline__ void wavenet_spec_body(const SpecParams& p)
 {
   constexpr int T = NT * S;
-  constexpr int W = spec::LS + T;
   static_assert(spec::NA == 1 || spec::NA == 2, "one or two layer arrays");
   extern __shared__ float4 spec_smem[]; // [Pmax][W] float4
   __shared__ u64 bar;
@@ -480,6 +571,8 @@ __device__ __forceinline__ void wavenet_spec_body(const SpecParams& p)
   }
   __syncthreads();
 
+  typedef typename FrameVec<S>::type V;
+  static_assert(S == 1 || S == 2, "one frame per thread, or a packed pair");
   for (int stream = blockIdx.x; stream < p.batch; stream += gridDim.x)
   {
     c.state = p.state + (size_t)stream * p.state_stride;
@@ -490,53 +583,54 @@ __device__ __forceinline__ void wavenet_spec_body(const SpecParams& p)
       c.tv = min(T, p.n_frames - t0);
       c.tabs0 = p.t_base + (u32)t0;
       request_layer_history<0, NT, S>(c, IntC<spec::A[0].layer0>{});
-      float x[S][1], cond[S];
-#pragma unroll
-      for (int j = 0; j < S; j++)
+      V x[1];
       {
-        const int f = j * NT + tid;
-        x[j][0] = (f < c.tv) ? __ldg(xin + t0 + f) : 0.0f;
-        cond[j] = x[j][0]; // no condition_dsp: condition == input (model.cpp:781)
+        const float xa = (tid < c.tv) ? __ldg(xin + t0 + tid) : 0.0f;
+        if constexpr (S == 1)
+          x[0] = xa;
+        else
+          x[0] = pack2(xa, (tid + NT < c.tv) ? __ldg(xin + t0 + tid + NT) : 0.0f);
       }
-      float y[S];
+      const V cond = x[0]; // no condition_dsp: condition == input (model.cpp:781)
+      V y;
       constexpr int C0 = spec::A[0].C;
-      float head0[S][C0], hout0[S][C0], ho0[S][spec::A[0].HOUT];
+      V head0[C0], hout0[C0], ho0[spec::A[0].HOUT];
 #pragma unroll
-      for (int j = 0; j < S; j++)
-#pragma unroll
-        for (int o = 0; o < C0; o++)
-          head0[j][o] = 0.0f; // model.cpp:469
+      for (int o = 0; o < C0; o++)
+        vsplat(head0[o], 0.0f); // model.cpp:469
       if constexpr (spec::NA == 1)
       {
-        array_forward<0, -1, NT, S>(c, x, cond, head0, hout0, ho0);
-#pragma unroll
-        for (int j = 0; j < S; j++)
-          y[j] = ho0[j][0];
+        array_forward<0, -1, NT, S, V>(c, x, cond, head0, hout0, ho0);
+        y = ho0[0];
       }
       else
       {
-        array_forward<0, spec::NA - 1, NT, S>(c, x, cond, head0, hout0, ho0);
+        array_forward<0, spec::NA - 1, NT, S, V>(c, x, cond, head0, hout0, ho0);
         // second array: layer input = the previous array's layer output, head accumulator starts from the previous
         // array's head output (model.cpp:846-848, :473-486)
         constexpr int AI1 = spec::NA - 1;
         constexpr int C1 = spec::A[AI1].C;
-        float head1[S][C1], hout1[S][C1], ho1[S][spec::A[AI1].HOUT];
+        V head1[C1], hout1[C1], ho1[spec::A[AI1].HOUT];
 #pragma unroll
-        for (int j = 0; j < S; j++)
-#pragma unroll
-          for (int o = 0; o < C1; o++)
-            head1[j][o] = ho0[j][o];
-        array_forward<AI1, -1, NT, S>(c, hout0, cond, head1, hout1, ho1);
-#pragma unroll
-        for (int j = 0; j < S; j++)
-          y[j] = ho1[j][0];
+        for (int o = 0; o < C1; o++)
+          head1[o] = ho0[o];
+        array_forward<AI1, -1, NT, S, V>(c, hout0, cond, head1, hout1, ho1);
+        y = ho1[0];
       }
-#pragma unroll
-      for (int j = 0; j < S; j++)
+      // model.cpp:888-897
+      if constexpr (S == 1)
       {
-        const int f = j * NT + tid;
-        if (f < c.tv)
-          yout[t0 + f] = spec::head_scale * y[j]; // model.cpp:888-897
+        if (tid < c.tv)
+          yout[t0 + tid] = spec::head_scale * y;
+      }
+      else
+      {
+        float ya, yb;
+        unpack2(y, ya, yb);
+        if (tid < c.tv)
+          yout[t0 + tid] = spec::head_scale * ya;
+        if (tid + NT < c.tv)
+          yout[t0 + tid + NT] = spec::head_scale * yb;
       }
       // (no barrier here: the last layer's B1 already fenced every tap read before anything of the next tile is written)
     }

@@ -167,6 +167,18 @@ class DSP:
     def state_bytes_per_stream(self) -> int:
         return self._info.state_bytes_per_stream
 
+    @property
+    def jit_state(self) -> int:
+        """1 = the model-specialised (NVRTC) kernel serves this handle's throughput calls, 0 = not requested,
+        -1 = requested but unavailable (jit_note says why)."""
+        self._refresh_info()
+        return int(self._info.jit_state)
+
+    def jit_note(self) -> str:
+        buf = C.create_string_buffer(4096)
+        self._lib.nam_b200_jit_note(self._h, buf, len(buf))
+        return buf.value.decode(errors="replace")
+
     def launch_count(self) -> int:
         return int(self._lib.nam_b200_launch_count(self._h))
 
@@ -219,15 +231,21 @@ class DSP:
         """
         n = int(num_frames)
         ins = [np.ascontiguousarray(a) for a in input]
+        outs = list(output)
+        # the C side reads in_channels pointers and writes out_channels pointers of n frames each: check all of it here
+        if len(ins) != self.in_channels or len(outs) != self.out_channels:
+            raise ValueError(f"process() needs {self.in_channels} input and {self.out_channels} output channel buffers "
+                             f"(got {len(ins)} and {len(outs)})")
+        if n < 0 or any(a.ndim != 1 or len(a) < n or a.dtype != ins[0].dtype for a in ins):
+            raise ValueError("input buffers must be 1-D, of one dtype, and hold num_frames")
         if ins[0].dtype == np.float64:
             ptr_t, fn = _capi.f64p, self._lib.nam_b200_process_f64_planar
         elif ins[0].dtype == np.float32:
             ptr_t, fn = _capi.f32p, self._lib.nam_b200_process_f32_planar
         else:
             raise TypeError("process() takes float64 (NAM_SAMPLE) or float32 (NAM_SAMPLE_FLOAT) buffers")
-        outs = list(output)
         for o in outs:
-            if o.dtype != ins[0].dtype or not o.flags["C_CONTIGUOUS"] or len(o) < n:
+            if not isinstance(o, np.ndarray) or o.ndim != 1 or o.dtype != ins[0].dtype or not o.flags["C_CONTIGUOUS"] or len(o) < n:
                 raise ValueError("output buffers must be contiguous, of the input dtype, and hold num_frames")
         ip = (ptr_t * len(ins))(*[a.ctypes.data_as(ptr_t) for a in ins])
         op = (ptr_t * len(outs))(*[o.ctypes.data_as(ptr_t) for o in outs])
@@ -249,6 +267,9 @@ class DSP:
         b, n = x.shape
         if out is None:
             out = np.empty_like(x)
+        elif (not isinstance(out, np.ndarray) or out.dtype != np.float32 or out.shape != x.shape
+              or not out.flags["C_CONTIGUOUS"]):
+            raise ValueError("out must be a C-contiguous float32 array of x's shape")  # the C side writes b rows of n floats
         # numpy may report an arbitrary stride for a length-1 axis
         xs = x.strides[0] // 4 if b > 1 else n
         os_ = out.strides[0] // 4 if b > 1 else n
@@ -286,7 +307,7 @@ class DSP:
 
 
 def _options(lib, batch: int, device: int, prewarm: Optional[bool], fast_tanh: Optional[bool], ctas_per_sm: int,
-             kernel_geometry: int = 0, tile_mode: int = 0):
+             kernel_geometry: int = 0, tile_mode: int = 0, jit: int = 0):
     o = _capi.Options()
     lib.nam_b200_default_options(C.byref(o))
     o.device = int(device)
@@ -296,23 +317,25 @@ def _options(lib, batch: int, device: int, prewarm: Optional[bool], fast_tanh: O
     o.ctas_per_sm = int(ctas_per_sm)
     o.kernel_geometry = int(kernel_geometry)
     o.tile_mode = int(tile_mode)
+    o.jit = int(jit)
     return o
 
 
 def get_dsp(config, batch: int = 1, device: int = -1, prewarm: Optional[bool] = None,
             fast_tanh: Optional[bool] = None, ctas_per_sm: int = 0, kernel_geometry: int = 0,
-            tile_mode: int = 0) -> DSP:
+            tile_mode: int = 0, jit: int = 0) -> DSP:
     """nam::get_dsp: `config` is a path to a .nam file, a dict (parsed .nam) or a JSON string.
 
     batch      number of independent streams the handle carries (the reference: one DSP object each)
     prewarm    DspLoadOptions.prewarm (NAM/get_dsp.h:70-78): None = reference default (Reset prewarms)
     fast_tanh  None = use the process-wide switch (enable_fast_tanh()), like the reference
     kernel_geometry / tile_mode / ctas_per_sm   tuning knobs, see nam_b200_options (include/nam_b200.h)
+    jit         model-specialised kernel (NVRTC at load): 0 = default (on for batch >= 256), 1 = required, 2 = off
     """
     import json
 
     lib = _capi.load()
-    o = _options(lib, batch, device, prewarm, fast_tanh, ctas_per_sm, kernel_geometry, tile_mode)
+    o = _options(lib, batch, device, prewarm, fast_tanh, ctas_per_sm, kernel_geometry, tile_mode, jit)
     h = C.c_void_p()
     if isinstance(config, (str, os.PathLike)) and not (isinstance(config, str) and config.lstrip().startswith("{")):
         rc = lib.nam_b200_create_from_file(str(Path(config)).encode(), C.byref(o), C.byref(h))
@@ -322,6 +345,24 @@ def get_dsp(config, batch: int = 1, device: int = -1, prewarm: Optional[bool] = 
     if rc != 0:
         _raise(rc, lib)
     return DSP(h.value, lib, int(batch))
+
+
+def jit_prepare(config, fast_tanh: Optional[bool] = None) -> dict:
+    """Host-only: compile (or fetch from the cache) the model-specialised kernel of a WaveNet .nam (path, dict or JSON
+    text).  Needs no GPU: NVRTC cross-compiles for sm_100a.  Returns the library's report as a dict."""
+    import json
+
+    lib = _capi.load()
+    if isinstance(config, (str, os.PathLike)) and not (isinstance(config, str) and config.lstrip().startswith("{")):
+        text = Path(config).read_text()
+    else:
+        text = config if isinstance(config, str) else json.dumps(config)
+    ft = int(_using_fast_tanh if fast_tanh is None else bool(fast_tanh))
+    buf = C.create_string_buffer(2048)
+    rc = lib.nam_b200_jit_prepare_json(text.encode(), ft, buf, len(buf))
+    if rc != 0:
+        _raise(rc, lib)
+    return json.loads(buf.value.decode())
 
 
 def inspect(config, fast_tanh: Optional[bool] = None) -> dict:

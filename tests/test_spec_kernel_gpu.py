@@ -1,0 +1,155 @@
+"""GPU parity of the model-specialised kernel (csrc/wavenet_spec.cuh: the model compiled by NVRTC at load time, weights
+as FFMA immediates, history staged by cp.async.bulk): against the CPU oracle (<= 1e-5 max-abs, BASELINE.json) and, bit
+for bit, against the precompiled fused kernel that serves the same rings.
+
+`jit=1` makes the specialised kernel mandatory (creation fails otherwise); `tile_mode=2` keeps small test batches off
+the lock-step mode so that every long call really takes the specialised kernel.
+"""
+import numpy as np
+import pytest
+
+import neuralampmodelercore_b200 as nb
+from oracle import oracle
+from tests import nam_fixtures as fx
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _spec(nam, batch, fast, **kw):
+    d = nb.get_dsp(nam, batch=batch, fast_tanh=fast, jit=1, tile_mode=2, **kw)
+    assert d.jit_state == 1, d.jit_note()
+    return d
+
+
+def _oracle_batch(nam, x, fast, block=64):
+    proto = oracle.OracleModel.from_dict(nam, fast_tanh=fast)
+    proto.reset(48000.0, block)
+    return proto.run_batch(x, block)
+
+
+@pytest.mark.parametrize("fast", [False, True], ids=["exact_tanh", "fast_tanh"])
+def test_a1_standard_vs_oracle_and_vs_fused_kernel(fast):
+    nam = fx.load_model("wavenet_a1_standard")
+    B, N = 16, 3000  # 5 full 512-frame tiles + a partial one
+    x = fx.synthetic_batch(B, N, seed=11)
+    ref = _oracle_batch(nam, x, fast)
+    d = _spec(nam, B, fast)
+    d.Reset(48000.0, N)
+    n0 = d.launch_count()
+    got = d.process_batch(x)
+    assert d.launch_count() == n0 + 1
+    d.close()
+    err = float(np.max(np.abs(got - ref)))
+    assert err <= TOL, f"max-abs vs oracle {err:.3e}"
+    g = nb.get_dsp(nam, batch=B, fast_tanh=fast, jit=2, tile_mode=2)
+    assert g.jit_state == 0
+    g.Reset(48000.0, N)
+    fused = g.process_batch(x)
+    g.close()
+    # same summation order, same operations: with the library tanh the two kernels agree to the last bit; the packed
+    # rational fast-tanh comes out of the two compilers (nvcc for the library, NVRTC for the model) one ulp apart in places
+    d_fused = float(np.max(np.abs(got - fused)))
+    assert (d_fused <= 2.5e-7) if fast else np.array_equal(got, fused), f"max-abs vs fused kernel {d_fused:.3e}"
+
+
+def test_call_splitting_and_mixed_kernels_on_one_handle():
+    """Long calls (specialised kernel), 64-frame calls (multi-stream geometry of the precompiled kernel), odd lengths
+    (the absolute frame counter becomes odd, ring pieces wrap): all on the same rings, equal to one oracle run."""
+    nam = fx.load_model("wavenet_a1_standard")
+    B, N = 32, 6001
+    x = fx.synthetic_batch(B, N, seed=5)
+    ref = _oracle_batch(nam, x, True)
+    d = _spec(nam, B, True)
+    d.Reset(48000.0, 2048)
+    chunks = [700, 64, 1, 2048, 63, 513, 64, 999, 1500, 49]
+    assert sum(chunks) == N
+    out, pos = [], 0
+    for n in chunks:
+        out.append(d.process_batch(np.ascontiguousarray(x[:, pos:pos + n])))
+        pos += n
+    d.close()
+    got = np.concatenate(out, axis=1)
+    err = float(np.max(np.abs(got - ref)))
+    assert err <= TOL, f"max-abs {err:.3e}"
+
+
+@pytest.mark.parametrize("case", [
+    dict(channels=(16, 8), kernel_size=3, dilations=[[1, 2, 4, 8, 16, 32], [1, 3, 9, 27, 81]], activation="Tanh"),
+    dict(channels=(8, 4), kernel_sizes=[[2, 3, 4, 5], [5, 2, 3]], dilations=[[1, 7, 13, 64], [2, 5, 128]], activation="ReLU"),
+    dict(channels=(12, 6), kernel_size=3, dilations=[[1, 2, 4, 300], [1, 2, 512]], activation="Sigmoid"),  # padded channels
+    dict(channels=(3,), kernel_size=3, dilations=[[1, 2, 8]], activation="Hardtanh"),  # one array, like wavenet.nam's first
+    dict(channels=(16,), kernel_sizes=[[1, 3, 1, 2]], dilations=[[1, 1, 5, 1024]], activation="SiLU"),  # kernel-size-1 layers: no history
+    dict(channels=(4, 16), kernel_size=4, dilations=[[1, 2], [3, 100, 341]], activation="LeakyReLU"),  # look-back 1023
+], ids=["a1_like_odd_dilations", "kernels_2_to_5", "padded_12_6", "single_array", "kernel_1_layers", "narrow_then_wide"])
+def test_shape_family(case):
+    nam = fx.random_wavenet(seed=3, **case)
+    B, N = 8, 1400
+    x = fx.synthetic_batch(B, N, seed=2)
+    ref = _oracle_batch(nam, x, False)
+    d = _spec(nam, B, False)
+    d.Reset(48000.0, 1024)
+    got = np.concatenate([d.process_batch(np.ascontiguousarray(x[:, p:p + 1024])) for p in range(0, N, 1024)], axis=1)
+    d.close()
+    scale = max(1.0, float(np.max(np.abs(ref))))
+    err = float(np.max(np.abs(got - ref)))
+    assert err <= TOL * scale, f"max-abs {err:.3e} (|y| up to {scale:.2f})"
+
+
+@pytest.mark.parametrize("act", ["Tanh", "Hardtanh", "Fasttanh", "ReLU", "LeakyReLU", "PReLU", "Sigmoid", "SiLU", "Hardswish",
+                                 "LeakyHardtanh", "Softsign"])
+def test_activation_set(act):
+    """All eleven activations of NAM/activations.h:26-39 compiled into the specialised kernel."""
+    activation = act
+    if act == "PReLU":
+        activation = {"type": "PReLU", "negative_slopes": [0.05 * (i + 1) for i in range(8)]}
+    elif act == "LeakyHardtanh":
+        activation = {"type": "LeakyHardtanh", "min_val": -0.5, "max_val": 0.7, "min_slope": 0.1, "max_slope": 0.2}
+    elif act == "LeakyReLU":
+        activation = {"type": "LeakyReLU", "negative_slope": 0.2}
+    nam = fx.random_wavenet(channels=(8,), kernel_size=3, dilations=[[1, 2, 4]], activation=activation, seed=9)
+    B, N = 4, 700
+    x = fx.synthetic_batch(B, N, seed=8) * 4.0  # drive the saturating activations into both branches
+    ref = _oracle_batch(nam, x, False)
+    d = _spec(nam, B, False)
+    d.Reset(48000.0, N)
+    got = d.process_batch(x)
+    d.close()
+    scale = max(1.0, float(np.max(np.abs(ref))))
+    assert float(np.max(np.abs(got - ref))) <= TOL * scale
+
+
+def test_prewarmed_state_and_second_reset():
+    """Reset prewarms through the precompiled kernels (short blocks); the specialised kernel continues from that state,
+    and a second Reset returns to it."""
+    nam = fx.load_model("wavenet_a1_standard")
+    x = fx.synthetic_batch(4, 2000, seed=1)
+    ref = _oracle_batch(nam, x, True)
+    d = _spec(nam, 4, True)
+    for _ in range(2):
+        d.Reset(48000.0, 2000)
+        got = d.process_batch(x)
+        assert float(np.max(np.abs(got - ref))) <= TOL
+    d.close()
+
+
+def test_jit_required_refuses_what_it_cannot_serve():
+    """A convolutional head (A2 family) is outside the specialised kernel: jit=1 must fail loudly, jit=0 must fall back
+    to the precompiled fused kernel and say why."""
+    nam = fx.load_model("a2_full")
+    with pytest.raises(Exception, match="convolutional head"):
+        nb.get_dsp(nam, batch=512, jit=1)
+    d = nb.get_dsp(nam, batch=512, jit=0)
+    assert d.jit_state == -1 and "convolutional head" in d.jit_note()
+    d.close()
+
+
+def test_default_policy_uses_it_for_throughput_handles():
+    nam = fx.load_model("wavenet_a1_standard")
+    d = nb.get_dsp(nam, batch=256, fast_tanh=True)
+    assert d.jit_state == 1, d.jit_note()
+    d.close()
+    d = nb.get_dsp(nam, batch=1, fast_tanh=True)
+    assert d.jit_state == 0
+    d.close()
