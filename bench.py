@@ -58,7 +58,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the quick batch-1/256, A2, LSTM, a2_max lines")
-    ap.add_argument("--gather", action="store_true", help="also time an NCCL all_gather of one step's outputs")
+    ap.add_argument("--no-gather", action="store_true",
+                    help="N > 1: skip the second timed pass that all-gathers every step's outputs over NCCL")
     return ap.parse_args()
 
 
@@ -378,20 +379,62 @@ def run_b200(args) -> None:
                "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(y_host.numel() * 4),
                "ms_per_step": float(t.item()) / args.steps * 1e3, "checksum": loss}
 
+    # ---- N > 1: the same K steps again, now with the NCCL all-gather of every step's outputs (BASELINE.json config 5:
+    # "batch sharded 4096/GPU, NCCL gather of output buffers").  The streams are independent, so the gather is the only
+    # collective the path can have; it runs on a side stream and overlaps the NEXT step's kernel (outputs double-buffered),
+    # the way a host that wants all outputs on every rank would drive it.  Timed like `value`: CUDA events, max over ranks.
     gather = None
-    if args.gather and dist is not None:
-        outs = [torch.empty_like(y_dev) for _ in range(world)]
-        dist.all_gather(outs, y_dev)
+    value_with_gather = None
+    if dist is not None and not args.no_gather:
+        y2 = [y_dev, torch.empty_like(y_dev)]
+        gathered = [torch.empty((world,) + tuple(y_dev.shape), dtype=y_dev.dtype, device="cuda") for _ in range(2)]
+        side = torch.cuda.Stream()
+        done = [torch.cuda.Event() for _ in range(2)]  # gather of buffer b finished (side stream)
+        ready = torch.cuda.Event()
+
+        def step_with_gather(i):
+            b = i & 1
+            stream.wait_event(done[b])  # buffer b's previous gather has read it
+            model.process_batch_device(x_dev.data_ptr(), y2[b].data_ptr(), B, n, n, n, stream.cuda_stream)
+            ready.record(stream)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                dist.all_gather_into_tensor(gathered[b].view(-1), y2[b].view(-1))
+                done[b].record(side)
+
+        for i in range(max(args.warmup, 2)):
+            step_with_gather(i)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
+        g0.record(stream)
+        for i in range(args.steps):
+            step_with_gather(i)
+        stream.wait_stream(side)
+        g1.record(stream)
+        barrier()
+        t = torch.tensor([g0.elapsed_time(g1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        with_ms = float(t.item()) / args.steps
+        value_with_gather = world * B * n / (with_ms * 1e-3) / 1e6
+        # the collective alone, back to back, for its bus bandwidth
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
         for _ in range(5):
-            dist.all_gather(outs, y_dev)
-        g1.record()
+            dist.all_gather_into_tensor(gathered[0].view(-1), y2[0].view(-1))
+        a1.record()
         torch.cuda.synchronize()
-        gms = g0.elapsed_time(g1) / 5
+        t = torch.tensor([a0.elapsed_time(a1) / 5], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gms = float(t.item())
         gather = {"ms_per_step": gms, "bytes_per_rank": int(y_dev.numel() * 4),
-                  "busbw_GBs": y_dev.numel() * 4 * (world - 1) / (gms * 1e-3) / 1e9}
+                  "busbw_GBs": y_dev.numel() * 4 * (world - 1) / (gms * 1e-3) / 1e9,
+                  "step_ms_with_gather_overlapped": with_ms, "step_ms_without": total_ms_max / args.steps,
+                  "hidden_fraction": max(0.0, 1.0 - (with_ms - total_ms_max / args.steps) / gms) if gms > 0 else None,
+                  "what": "ncclAllGather (torch.distributed all_gather_into_tensor) of each rank's outputs on a side "
+                          "stream, overlapped with the next step's kernel; every rank ends up with all N x batch streams"}
+        # the gathered block really holds every rank's outputs
+        torch.cuda.synchronize()
+        assert torch.equal(gathered[(args.steps - 1) & 1][rank], y2[(args.steps - 1) & 1])
 
     if rank != 0:
         if dist is not None:
@@ -399,6 +442,9 @@ def run_b200(args) -> None:
         return
 
     # ---- the other configurations BASELINE.json names, device-resident, a few steps each (N = 1 only) ----
+    fp32_packed = nb.measure_fp32_tflops(local_rank, packed=True)
+    fp32_scalar = nb.measure_fp32_tflops(local_rank, packed=False)
+    fp32_peak = max(fp32_packed, fp32_scalar)  # the roof is the best FP32 FMA rate the SMs can be measured to issue
     secondary = None
     if world == 1 and not args.no_secondary and args.model == MODEL:
         secondary = {}
@@ -422,7 +468,9 @@ def run_b200(args) -> None:
                 v = b * frames / (ms * 1e-3) / 1e6
                 secondary[name] = {"Msamples_per_s": v, "ms_per_step": ms, "streams": b, "frames_per_step": frames,
                                    "rtf_48k_per_stream": v * 1e6 / 48000.0 / b,
-                                   "tflops": m2.flops_per_frame * v * 1e6 / 1e12}
+                                   "tflops": m2.flops_per_frame * v * 1e6 / 1e12,
+                                   "frac_of_fp32_fma_peak": m2.flops_per_frame * v * 1e6 / 1e12 / fp32_peak,
+                                   "jit": m2.jit_state}
                 m2.close()
             except Exception as exc:  # a secondary workload must never cost the headline line
                 secondary[name] = {"error": str(exc)[:200]}
@@ -442,9 +490,6 @@ def run_b200(args) -> None:
     # ---- roofline of the fused kernel (one launch per step) ----
     peaks = load_peaks()
     kernel_ms = statistics.mean(step_ms)  # one kernel per step on this stream: event-to-event == launch duration
-    fp32_packed = nb.measure_fp32_tflops(local_rank, packed=True)
-    fp32_scalar = nb.measure_fp32_tflops(local_rank, packed=False)
-    fp32_peak = max(fp32_packed, fp32_scalar)  # the roof is the best FP32 FMA rate the SMs can be measured to issue
     flops_per_launch = flops_per_frame * B * n
     achieved_tf = flops_per_launch / (kernel_ms * 1e-3) / 1e12
     alg_bytes = B * n * 8.0 + 2.0 * state_bytes * B  # in + out + history read & written once per launch
@@ -512,6 +557,7 @@ def run_b200(args) -> None:
         "secondary": secondary,
     }
     if gather is not None:
+        line["value_with_gather"] = value_with_gather
         line["nccl_gather"] = gather
     print(json.dumps(line), flush=True)
     if dist is not None:

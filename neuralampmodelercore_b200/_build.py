@@ -89,13 +89,23 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     LIB_DIR.mkdir(exist_ok=True)
     obj_dir = LIB_DIR / "obj"
     obj_dir.mkdir(exist_ok=True)
-    headers = [p for p in list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inc")) + list(INCLUDE.rglob("*.h"))]
-    # which headers a source pulls in, by name (cheap and conservative enough: a miss only costs a rebuild)
+    import re
+
+    def closure(path: Path, seen: set) -> set:
+        """Files reachable through #include "..." (searched next to the includer, in csrc/ and in include/)."""
+        for name in re.findall(r'#include\s+"([^"]+)"', path.read_text()):
+            for base in (path.parent, CSRC, INCLUDE):
+                cand = (base / name).resolve()
+                if cand.is_file() and cand not in seen:
+                    seen.add(cand)
+                    closure(cand, seen)
+                    break
+        return seen
+
     jobs = []
     for src in sources():
         obj = obj_dir / (src.name + ".o")
-        text = src.read_text()
-        deps = [src] + [h for h in headers if h.name in text or src.suffix == ".cu"]
+        deps = [src, *closure(src, set())]
         if force or not obj.exists() or any(d.stat().st_mtime > obj.stat().st_mtime for d in deps):
             jobs.append((src, obj))
     with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:

@@ -185,11 +185,18 @@ __device__ __forceinline__ void vload4(const float4* p, float (&x)[4])
   const float4 q = *p;
   x[0] = q.x, x[1] = q.y, x[2] = q.z, x[3] = q.w;
 }
+// S = 2: the pair (frame tid, frame tid + NT) of a channel lives in two different columns.  Eight scalar loads put
+// every value straight into its half of a register pair; two 16-byte loads would need eight MOVs to re-pair them
+// (measured: 8,400 MOVs per tile pass, 1,610 instead of 1,760 Msamples/s).  `volatile` only keeps the compiler from
+// merging them back into vector loads; the shared-memory wavefronts are the same (8 per plane either way).
 template <int NT>
 __device__ __forceinline__ void vload4(const float4* p, u64 (&x)[4])
 {
-  const float4 a = p[0], b = p[NT];
-  x[0] = pack2(a.x, b.x), x[1] = pack2(a.y, b.y), x[2] = pack2(a.z, b.z), x[3] = pack2(a.w, b.w);
+  const volatile float* a = reinterpret_cast<const volatile float*>(p);
+  const volatile float* b = reinterpret_cast<const volatile float*>(p + NT);
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    x[i] = pack2(a[i], b[i]);
 }
 template <int NT>
 __device__ __forceinline__ void vstore4(float4* p, const float (&x)[4])
@@ -199,9 +206,15 @@ __device__ __forceinline__ void vstore4(float4* p, const float (&x)[4])
 template <int NT>
 __device__ __forceinline__ void vstore4(float4* p, const u64 (&x)[4])
 {
-  float4 a, b;
-  unpack2(x[0], a.x, b.x), unpack2(x[1], a.y, b.y), unpack2(x[2], a.z, b.z), unpack2(x[3], a.w, b.w);
-  p[0] = a, p[NT] = b;
+  volatile float* a = reinterpret_cast<volatile float*>(p);
+  volatile float* b = reinterpret_cast<volatile float*>(p + NT);
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+  {
+    float lo, hi;
+    unpack2(x[i], lo, hi);
+    a[i] = lo, b[i] = hi;
+  }
 }
 
 // one element of layer LI's activation, channel i (activations.h:59-133)
