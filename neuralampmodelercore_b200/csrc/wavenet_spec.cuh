@@ -104,8 +104,9 @@ __device__ __forceinline__ u64 dup2(float v)
 {
   return pack2(v, v);
 }
-// the reference's rational fast_tanh (activations.h:91-98) on a packed pair: identical operation order to
-// namb200::tc_fast_tanh2 (wavenet_fused.cuh)
+// the reference's rational fast_tanh (activations.h:91-98) on a packed pair.  The denominator's |x + c x |x|| is
+// evaluated as |x| + c x^2 (the same number: c > 0, so the factor 1 + c |x| is positive; one rounding differs, < 1e-7
+// relative): one packed multiply and one 64-bit AND fewer per pair than the literal form in wavenet_fused.cuh.
 __device__ __forceinline__ u64 fast_tanh2(u64 x)
 {
   constexpr u64 kAbs = 0x7FFFFFFF7FFFFFFFull;
@@ -115,7 +116,7 @@ __device__ __forceinline__ u64 fast_tanh2(u64 x)
   const u64 t1 = fma2(dup2(0.821226666969744f), ax, dup2(0.893229853513558f));
   const u64 t0 = fma2(c0, ax, c0);
   const u64 num = mul2(x, fma2(t1, x2, t0));
-  const u64 s = fma2(dup2(0.814642734961073f), mul2(x, ax), x) & kAbs;
+  const u64 s = fma2(dup2(0.814642734961073f), x2, ax);
   const u64 d0 = dup2(2.44506634652299f);
   const u64 den = fma2(add2(x2, d0), s, d0);
   float dl, dh;

@@ -23,7 +23,9 @@ _LIBS: dict[str, C.CDLL] = {}
 
 
 def lib_path(variant: str = "default") -> Path:
-    return REF_DIR / ("libnam_ref.so" if variant == "default" else "libnam_ref_generic.so")
+    names = {"default": "libnam_ref.so", "generic": "libnam_ref_generic.so", "fast": "libnam_ref_fast.so",
+             "fast512": "libnam_ref_fast512.so"}
+    return REF_DIR / names[variant]
 
 
 def available(variant: str = "default") -> bool:
@@ -136,3 +138,57 @@ class ReferenceModel:
         if self._lib.namref_run_f32(self._h, x.ctypes.data, y.ctypes.data, len(x), int(block)) != 0:
             raise ReferenceError_(self._lib.namref_last_error().decode(errors="replace"))
         return y
+
+
+def best_timed_variant() -> str | None:
+    """The -Ofast build (tools/CMakeLists.txt:106) for the best ISA level this host has: "fast512" (x86-64-v4) or "fast"
+    (x86-64-v3); None when neither was built."""
+    try:
+        flags = Path("/proc/cpuinfo").read_text()
+    except OSError:
+        flags = ""
+    if all(f in flags for f in ("avx512f", "avx512bw", "avx512dq", "avx512vl")) and available("fast512"):
+        return "fast512"
+    if "avx2" in flags and "fma" in flags and available("fast"):
+        return "fast"
+    return None
+
+
+class ReferencePool:
+    """`streams` independent reference DSP objects (nam::get_dsp of the same file), each carrying its own state across
+    process() calls, spread over host threads -- the reference's own code under the reference tools' protocol
+    (tools/benchmodel.cpp:116-133: Reset(sr, 64), then 64-frame process() calls).  CPU-baseline timing only."""
+
+    def __init__(self, nam: dict, streams: int, fast_tanh: bool, variant: str, block: int = 64):
+        self.block = int(block)
+        self.models = []
+        with tempfile.NamedTemporaryFile("w", suffix=".nam", delete=False) as f:
+            json.dump(nam, f)
+            path = f.name
+        try:
+            for _ in range(int(streams)):
+                m = ReferenceModel(path, fast_tanh, variant)
+                m.reset(48000.0, self.block)
+                self.models.append(m)
+        finally:
+            os.unlink(path)
+
+    def process(self, x: np.ndarray, out: np.ndarray, threads: int) -> None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        assert x.dtype == np.float32 and x.shape[0] == len(self.models) and x.flags["C_CONTIGUOUS"]
+        lib = self.models[0]._lib
+        n = x.shape[1]
+
+        def work(t: int) -> None:  # ctypes releases the GIL for the duration of the foreign call
+            for i in range(t, len(self.models), threads):
+                if lib.namref_run_f32(self.models[i]._h, x[i].ctypes.data, out[i].ctypes.data, n, self.block) != 0:
+                    raise ReferenceError_(lib.namref_last_error().decode(errors="replace"))
+
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(work, range(threads)))
+
+    def close(self) -> None:
+        for m in self.models:
+            m.close()
+        self.models = []
