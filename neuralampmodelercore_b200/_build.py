@@ -50,18 +50,23 @@ def _stale() -> bool:
     return any(p.stat().st_mtime > t for p in deps if p.is_file())
 
 
-def embed_spec_source() -> Path:
-    """wavenet_spec.cuh -> csrc/wavenet_spec_src.inc, a C++ raw string literal: the library carries the source of the
-    model-specialised kernel and hands it to NVRTC at model-load time (jit_spec.cpp)."""
-    src = (CSRC / "wavenet_spec.cuh").read_text()
+def embed_spec_source() -> None:
+    """wavenet_spec.cuh / lstm_spec.cuh -> csrc/*_src.inc, C++ raw string literals: the library carries the sources of the
+    model-specialised kernels and hands them to NVRTC at model-load time (jit_spec.cpp)."""
+    for stem in ("wavenet_spec", "lstm_spec"):
+        _embed(stem)
+
+
+def _embed(stem: str) -> Path:
+    src = (CSRC / f"{stem}.cuh").read_text()
     delim = "NAMB200SPEC"
     assert f"){delim}\"" not in src
     # a string literal may not exceed 64 KiB on some compilers: split into adjacent literals
     parts, chunk = [], 12000
     for i in range(0, len(src), chunk):
         parts.append(f'R"{delim}({src[i:i + chunk]}){delim}"')
-    inc = CSRC / "wavenet_spec_src.inc"
-    text = "// generated from wavenet_spec.cuh by _build.py -- do not edit\n" + "\n".join(parts) + "\n"
+    inc = CSRC / f"{stem}_src.inc"
+    text = f"// generated from {stem}.cuh by _build.py -- do not edit\n" + "\n".join(parts) + "\n"
     if not inc.exists() or inc.read_text() != text:
         inc.write_text(text)
     return inc

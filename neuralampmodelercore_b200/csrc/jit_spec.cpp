@@ -26,6 +26,9 @@ namespace
 const char* const kSpecKernelSource =
 #include "wavenet_spec_src.inc"
   ;
+const char* const kLstmSpecKernelSource =
+#include "lstm_spec_src.inc"
+  ;
 
 // ---- NVRTC through dlopen ------------------------------------------------------------------------------------------
 typedef struct _nvrtcProgram* nvrtcProgram;
@@ -168,6 +171,96 @@ void write_file_atomic(const std::string& dir, const std::string& name, const st
     ::unlink(tmp.c_str());
 }
 
+struct CompiledKernel
+{
+  bool ok = false, from_cache = false;
+  std::string why_not;
+  std::vector<char> cubin;
+  double compile_seconds = 0.0;
+};
+
+// header + `#include "<kernel_file>"` -> sm_100a cubin, through the disk cache.  `env_override`: development aid, an
+// environment variable that names a file to use instead of the embedded kernel source.
+CompiledKernel compile_or_fetch(const std::string& tag, const std::string& header, const char* kernel_file,
+                                const char* embedded_source, const char* env_override, const std::vector<std::string>& defines)
+{
+  CompiledKernel r;
+  std::string kernel_source = embedded_source;
+  if (const char* e = std::getenv(env_override))
+  {
+    std::vector<char> txt;
+    if (*e && read_file(e, txt))
+      kernel_source.assign(txt.begin(), txt.end());
+  }
+  std::string opts_text = "-arch=sm_100a -std=c++17 -default-device";
+  for (const std::string& d : defines)
+    opts_text += " " + d;
+  uint64_t h = 1469598103934665603ull;
+  h = fnv1a(h, header.data(), header.size());
+  h = fnv1a(h, kernel_source.data(), kernel_source.size());
+  h = fnv1a(h, opts_text.data(), opts_text.size());
+  char name[96];
+  std::snprintf(name, sizeof name, "%s_%016llx.cubin", tag.c_str(), (unsigned long long)h);
+  const std::string dir = cache_dir();
+  if (read_file(dir + "/" + name, r.cubin))
+  {
+    r.ok = true;
+    r.from_cache = true;
+    return r;
+  }
+  Nvrtc& n = nvrtc();
+  if (!n.ok())
+  {
+    r.why_not = "NVRTC unavailable: " + n.error;
+    return r;
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  const std::string source = header + "\n#include \"" + kernel_file + "\"\n";
+  const char* hdr_src[] = {kernel_source.c_str()};
+  const char* hdr_name[] = {kernel_file};
+  nvrtcProgram prog = nullptr;
+  int rc = n.CreateProgram(&prog, source.c_str(), (tag + "_model.cu").c_str(), 1, hdr_src, hdr_name);
+  if (rc != 0)
+  {
+    r.why_not = std::string("nvrtcCreateProgram: ") + n.GetErrorString(rc);
+    return r;
+  }
+  // -default-device: the layer loop is a generic lambda, which NVRTC would otherwise take for a host function
+  std::vector<const char*> copts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+  for (const std::string& d : defines)
+    copts.push_back(d.c_str());
+  rc = n.CompileProgram(prog, (int)copts.size(), copts.data());
+  if (rc != 0)
+  {
+    size_t ls = 0;
+    n.GetProgramLogSize(prog, &ls);
+    std::string log(ls, '\0');
+    if (ls)
+      n.GetProgramLog(prog, &log[0]);
+    r.why_not = std::string("nvrtcCompileProgram: ") + n.GetErrorString(rc) + "\n" + log.substr(0, 4000);
+    n.DestroyProgram(&prog);
+    return r;
+  }
+  size_t cs = 0;
+  rc = n.GetCUBINSize(prog, &cs);
+  if (rc == 0 && cs > 0)
+  {
+    r.cubin.resize(cs);
+    rc = n.GetCUBIN(prog, r.cubin.data());
+  }
+  n.DestroyProgram(&prog);
+  if (rc != 0 || cs == 0)
+  {
+    r.why_not = "nvrtcGetCUBIN failed";
+    r.cubin.clear();
+    return r;
+  }
+  r.compile_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  write_file_atomic(dir, name, r.cubin);
+  r.ok = true;
+  return r;
+}
+
 } // namespace
 
 bool spec_eligible(const WaveNetPlan& plan, const SpecGeometry& g, std::string* why_not)
@@ -252,86 +345,91 @@ SpecBuild build_spec_kernel(const WaveNetPlan& plan, const SpecGeometry& g)
   for (int a = 0; a < plan.n_arrays; a++)
     r.max_planes = std::max(r.max_planes, plan.cp[a] / 4);
 
-  // development aid: $NAM_B200_SPEC_SOURCE names a wavenet_spec.cuh to use instead of the embedded copy
-  std::string kernel_source = kSpecKernelSource;
-  if (const char* e = std::getenv("NAM_B200_SPEC_SOURCE"))
-  {
-    std::vector<char> txt;
-    if (*e && read_file(e, txt))
-      kernel_source.assign(txt.begin(), txt.end());
-  }
   const std::string header = spec_header_source(plan);
-  const std::string opts_text = "-arch=sm_100a -std=c++17 -default-device -DNT=" + std::to_string(g.nt) + " -DS=" + std::to_string(g.s)
-                                + " -DMINB=" + std::to_string(g.min_ctas);
-  Nvrtc& n = nvrtc();
-  int vmaj = 0, vmin = 0;
-  if (n.ok())
-    n.Version(&vmaj, &vmin);
-  uint64_t h = 1469598103934665603ull;
-  h = fnv1a(h, header.data(), header.size());
-  h = fnv1a(h, kernel_source.data(), kernel_source.size());
-  h = fnv1a(h, opts_text.data(), opts_text.size());
-  char name[64];
-  std::snprintf(name, sizeof name, "wavenet_spec_%016llx.cubin", (unsigned long long)h);
-  const std::string dir = cache_dir();
-  if (read_file(dir + "/" + name, r.cubin))
-  {
-    r.ok = true;
-    r.from_cache = true;
-    return r;
-  }
-  if (!n.ok())
-  {
-    r.why_not = "NVRTC unavailable: " + n.error;
-    return r;
-  }
+  const std::vector<std::string> defs = {"-DNAMB200_SPEC_NT=" + std::to_string(g.nt), "-DNAMB200_SPEC_S=" + std::to_string(g.s),
+                                         "-DNAMB200_SPEC_MINB=" + std::to_string(g.min_ctas)};
+  const CompiledKernel ck = compile_or_fetch("wavenet_spec", header, "wavenet_spec.cuh", kSpecKernelSource, "NAM_B200_SPEC_SOURCE", defs);
+  r.ok = ck.ok;
+  r.why_not = ck.why_not;
+  r.cubin = ck.cubin;
+  r.from_cache = ck.from_cache;
+  r.compile_seconds = ck.compile_seconds;
+  return r;
+}
 
-  const auto t0 = std::chrono::steady_clock::now();
-  const std::string source = header + "\n#include \"wavenet_spec.cuh\"\n";
-  const char* hdr_src[] = {kernel_source.c_str()};
-  const char* hdr_name[] = {"wavenet_spec.cuh"};
-  nvrtcProgram prog = nullptr;
-  int rc = n.CreateProgram(&prog, source.c_str(), "wavenet_spec_model.cu", 1, hdr_src, hdr_name);
-  if (rc != 0)
+bool lstm_spec_eligible(const ModelSpec& ms, std::string* why_not)
+{
+  auto no = [&](const std::string& w) {
+    if (why_not)
+      *why_not = w;
+    return false;
+  };
+  if (ms.arch != Arch::LSTM)
+    return no("not an LSTM");
+  const LstmSpec& ls = ms.lstm;
+  if (ms.in_channels != 1 || ms.out_channels != 1 || ls.input_size != 1)
+    return no("multi-channel LSTM");
+  if (ls.num_layers < 1 || ls.num_layers > 4)
+    return no("more than four layers");
+  long fmas = 0;
+  for (int l = 0; l < ls.num_layers; l++)
+    fmas += 4L * ls.hidden * ((l == 0 ? ls.input_size : ls.hidden) + ls.hidden);
+  if (fmas > 320) // beyond this a lane group per stream (lstm_group.cuh) has the shorter step
+    return no("cell too large for one thread per stream (" + std::to_string(fmas) + " FMAs per step)");
+  for (const auto& c : ls.cells)
   {
-    r.why_not = std::string("nvrtcCreateProgram: ") + n.GetErrorString(rc);
+    for (float v : c.w)
+      if (!std::isfinite(v))
+        return no("non-finite weight");
+    for (float v : c.b)
+      if (!std::isfinite(v))
+        return no("non-finite weight");
+  }
+  return true;
+}
+
+std::string lstm_spec_header_source(const ModelSpec& ms)
+{
+  const LstmSpec& ls = ms.lstm;
+  std::vector<float> blob; // per layer W[4H][I+H] | b[4H]; then head_w[H] | head_b -- the order of nam_b200.cu's blob
+  for (const auto& c : ls.cells)
+  {
+    blob.insert(blob.end(), c.w.begin(), c.w.end());
+    blob.insert(blob.end(), c.b.begin(), c.b.end());
+  }
+  blob.insert(blob.end(), ls.head_w.begin(), ls.head_w.end());
+  blob.insert(blob.end(), ls.head_b.begin(), ls.head_b.end());
+  std::ostringstream o;
+  o << "// generated by jit_spec.cpp: one LSTM, as compile-time data\n"
+       "#define NAMB200_LSTM_SPEC_HEADER_INCLUDED 1\n"
+       "namespace spec {\n";
+  o << "constexpr int H = " << ls.hidden << ";\nconstexpr int L = " << ls.num_layers << ";\nconstexpr int I = " << ls.input_size
+    << ";\n";
+  o << "__device__ const unsigned Wb[" << blob.size() << "] = {\n";
+  char buf[16];
+  for (size_t i = 0; i < blob.size(); i++)
+  {
+    uint32_t u;
+    std::memcpy(&u, &blob[i], 4);
+    std::snprintf(buf, sizeof buf, "0x%08Xu,", u);
+    o << buf << ((i % 8 == 7) ? "\n" : " ");
+  }
+  o << "};\n__device__ __forceinline__ float w(const int i) { return __uint_as_float(Wb[i]); }\n}  // namespace spec\n";
+  return o.str();
+}
+
+SpecBuild build_lstm_spec_kernel(const ModelSpec& ms)
+{
+  SpecBuild r;
+  if (!lstm_spec_eligible(ms, &r.why_not))
     return r;
-  }
-  const std::string d_nt = "-DNAMB200_SPEC_NT=" + std::to_string(g.nt);
-  const std::string d_s = "-DNAMB200_SPEC_S=" + std::to_string(g.s);
-  const std::string d_mb = "-DNAMB200_SPEC_MINB=" + std::to_string(g.min_ctas);
-  // -default-device: the layer loop is a generic lambda, which NVRTC would otherwise take for a host function
-  const char* copts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device",
-                         d_nt.c_str(),                 d_s.c_str(),  d_mb.c_str()};
-  rc = n.CompileProgram(prog, (int)(sizeof copts / sizeof copts[0]), copts);
-  if (rc != 0)
-  {
-    size_t ls = 0;
-    n.GetProgramLogSize(prog, &ls);
-    std::string log(ls, '\0');
-    if (ls)
-      n.GetProgramLog(prog, &log[0]);
-    r.why_not = std::string("nvrtcCompileProgram: ") + n.GetErrorString(rc) + "\n" + log.substr(0, 4000);
-    n.DestroyProgram(&prog);
-    return r;
-  }
-  size_t cs = 0;
-  rc = n.GetCUBINSize(prog, &cs);
-  if (rc == 0 && cs > 0)
-  {
-    r.cubin.resize(cs);
-    rc = n.GetCUBIN(prog, r.cubin.data());
-  }
-  n.DestroyProgram(&prog);
-  if (rc != 0 || cs == 0)
-  {
-    r.why_not = "nvrtcGetCUBIN failed";
-    r.cubin.clear();
-    return r;
-  }
-  r.compile_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  write_file_atomic(dir, name, r.cubin);
-  r.ok = true;
+  const CompiledKernel ck =
+    compile_or_fetch("lstm_spec", lstm_spec_header_source(ms), "lstm_spec.cuh", kLstmSpecKernelSource, "NAM_B200_LSTM_SPEC_SOURCE", {});
+  r.ok = ck.ok;
+  r.why_not = ck.why_not;
+  r.cubin = ck.cubin;
+  r.from_cache = ck.from_cache;
+  r.compile_seconds = ck.compile_seconds;
   return r;
 }
 

@@ -46,6 +46,12 @@ std::string spec_header_source(const WaveNetPlan& plan);
 /// Cache directory: $NAM_B200_JIT_CACHE, else <directory of libnam_b200.so>/jit_cache.  Never throws.
 SpecBuild build_spec_kernel(const WaveNetPlan& plan, const SpecGeometry& g);
 
+/// The same for a small mono LSTM (lstm_spec.cuh: one thread per stream, weights as FFMA immediates); the cubin holds
+/// lstm_spec_kernel_exact and lstm_spec_kernel_fast (the fast-tanh switch is read at run time, lstm.cpp:48).
+bool lstm_spec_eligible(const ModelSpec& ms, std::string* why_not);
+std::string lstm_spec_header_source(const ModelSpec& ms);
+SpecBuild build_lstm_spec_kernel(const ModelSpec& ms);
+
 /// Name of the kernel entry point inside the cubin.
 inline const char* spec_kernel_name()
 {

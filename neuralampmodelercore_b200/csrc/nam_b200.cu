@@ -368,6 +368,7 @@ struct nam_b200_model
   // model-specialised kernel (wavenet_spec.cuh compiled for this model by NVRTC, jit_spec.cpp): the throughput path
   cudaLibrary_t spec_lib = nullptr;
   cudaKernel_t spec_kernel = nullptr;
+  cudaKernel_t lstm_spec_kernels[2] = {nullptr, nullptr}; // lstm_spec.cuh: exact / fast activation regime
   SpecGeometry spec_geom;
   size_t spec_smem = 0;
   int spec_ctas_per_sm = 0;
@@ -1065,9 +1066,74 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
   m->launches++;
 }
 
+// ---- model-specialised LSTM kernel (lstm_spec.cuh through jit_spec.cpp): same policy as setup_spec_kernel ------------
+struct LstmSpecKernelParams // mirror of namb200_lstm_spec::LstmSpecParams
+{
+  float* state;
+  long state_stride;
+  const float* in;
+  float* out;
+  long in_stride, out_stride;
+  int batch, n_frames;
+};
+
+void setup_lstm_spec_kernel(nam_b200_model* m)
+{
+  int mode = m->opts.jit;
+  if (mode == 0)
+  {
+    const char* e = std::getenv("NAM_B200_JIT");
+    if (e && *e)
+      mode = (e[0] == '0') ? 2 : 1;
+  }
+  if (!(mode == 1 || (mode == 0 && m->opts.max_batch >= 256)))
+    return;
+  SpecBuild b = build_lstm_spec_kernel(m->spec);
+  if (!b.ok)
+  {
+    m->spec_state = -1;
+    m->spec_note = b.why_not;
+    if (mode == 1)
+      throw std::runtime_error("model-specialised kernel unavailable: " + b.why_not);
+    return;
+  }
+  auto check = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess)
+      throw CudaError(std::string(what) + " failed: " + cudaGetErrorString(e));
+  };
+  try
+  {
+    check(cudaLibraryLoadData(&m->spec_lib, b.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0), "cudaLibraryLoadData");
+    check(cudaLibraryGetKernel(&m->lstm_spec_kernels[0], m->spec_lib, "lstm_spec_kernel_exact"), "cudaLibraryGetKernel");
+    check(cudaLibraryGetKernel(&m->lstm_spec_kernels[1], m->spec_lib, "lstm_spec_kernel_fast"), "cudaLibraryGetKernel");
+    m->spec_state = 1;
+    m->spec_note = b.from_cache ? "cubin from cache" : "compiled in " + std::to_string(b.compile_seconds) + " s";
+  }
+  catch (const CudaError& ex)
+  {
+    if (m->spec_lib)
+      cudaLibraryUnload(m->spec_lib);
+    m->spec_lib = nullptr;
+    m->spec_state = -1;
+    m->spec_note = ex.what();
+    if (mode == 1)
+      throw;
+  }
+}
+
 void launch_lstm(nam_b200_model* m, const float* d_in, float* d_out, int batch, int n_frames, long in_stride,
                  long out_stride, cudaStream_t st)
 {
+  if (m->spec_state == 1)
+  {
+    // one thread per stream, one warp per CTA (lstm_spec.cuh)
+    LstmSpecKernelParams sp{m->d_state, m->state_stride, d_in, d_out, in_stride, out_stride, batch, n_frames};
+    void* args[] = {&sp};
+    CUDA_CHECK(cudaLaunchKernel((const void*)m->lstm_spec_kernels[m->fast_tanh_runtime ? 1 : 0], dim3((batch + 31) / 32), dim3(32),
+                                args, 0, st));
+    m->launches++;
+    return;
+  }
   const LstmSpec& ls = m->spec.lstm;
   LstmKernelParams kp{};
   kp.weights = m->d_weights;
@@ -1475,6 +1541,7 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
         m->state_stride = ((long)ls.num_layers * 2 * ls.hidden + 3) & ~3L;
         m->flops_per_frame = 2.0 * macs;
         m->variant = 2000 + ls.hidden;
+        setup_lstm_spec_kernel(m.get());
         break;
       }
       case Arch::Linear:
@@ -1832,10 +1899,9 @@ int nam_b200_jit_prepare_json(const char* nam_json_text, int fast_tanh, char* ou
   try
   {
     const ModelSpec ms = model_spec_from_text(nam_json_text, lo);
-    if (ms.arch != Arch::WaveNet)
-      return fail(NAM_B200_ERR_UNSUPPORTED, "only WaveNets have a model-specialised kernel");
-    const WaveNetPlan plan = plan_wavenet(ms);
-    const SpecBuild b = build_spec_kernel(plan, SpecGeometry{});
+    if (ms.arch != Arch::WaveNet && ms.arch != Arch::LSTM)
+      return fail(NAM_B200_ERR_UNSUPPORTED, "only WaveNets and LSTMs have model-specialised kernels");
+    const SpecBuild b = ms.arch == Arch::LSTM ? build_lstm_spec_kernel(ms) : build_spec_kernel(plan_wavenet(ms), SpecGeometry{});
     std::string why;
     for (char c : b.why_not.substr(0, 600))
       why += (c == '"' || c == '\\') ? '\'' : (c == '\n' ? ' ' : c);

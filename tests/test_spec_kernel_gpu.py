@@ -153,3 +153,53 @@ def test_default_policy_uses_it_for_throughput_handles():
     d = nb.get_dsp(nam, batch=1, fast_tanh=True)
     assert d.jit_state == 0
     d.close()
+
+
+# ---- the model-specialised LSTM kernel (csrc/lstm_spec.cuh) ---------------------------------------------------------------
+def _random_lstm(H, nl, seed=4):
+    rng = np.random.default_rng(seed)
+    n = sum(4 * H * ((1 if l == 0 else H) + H) + 4 * H + 2 * H for l in range(nl)) + H + 1
+    return {"version": "0.5.4", "architecture": "LSTM", "config": {"input_size": 1, "hidden_size": H, "num_layers": nl},
+            "weights": [float(v) for v in rng.uniform(-0.4, 0.4, n)], "sample_rate": 48000}
+
+
+def test_lstm_spec_example_model_both_regimes_and_runtime_switch():
+    """lstm.nam on one thread per stream: 70 streams (two full warps + a partial one), 64-frame calls; the fast-tanh
+    switch is read at run time like the reference (lstm.cpp:48): one handle, both kernels of the cubin."""
+    nam = fx.load_model("lstm")
+    x = fx.synthetic_batch(70, 1999, seed=9)
+    d = nb.get_dsp(nam, batch=70, fast_tanh=False, jit=1)
+    assert d.jit_state == 1, d.jit_note()
+    for fast in (False, True):
+        proto = oracle.OracleModel.from_dict(nam, fast_tanh=fast)
+        proto.reset(48000.0, 64)
+        ref = proto.run_batch(x, 64)
+        d.set_fast_tanh(fast)
+        d.Reset(48000.0, 64)
+        got = np.concatenate([d.process_batch(np.ascontiguousarray(x[:, p:p + 64])) for p in range(0, 1999, 64)], axis=1)
+        err = float(np.max(np.abs(got - ref)))
+        assert err <= TOL, f"fast={fast}: {err:.3e}"
+    d.close()
+
+
+@pytest.mark.parametrize("H,nl", [(1, 1), (3, 1), (3, 3), (5, 2), (8, 1)])
+def test_lstm_spec_random_cells(H, nl):
+    nam = _random_lstm(H, nl)
+    x = fx.synthetic_batch(37, 1000, seed=1)
+    proto = oracle.OracleModel.from_dict(nam)
+    proto.reset(48000.0, 256)
+    ref = proto.run_batch(x, 256)
+    d = nb.get_dsp(nam, batch=37, jit=1)
+    assert d.jit_state == 1, d.jit_note()
+    d.Reset(48000.0, 256)
+    got = np.concatenate([d.process_batch(np.ascontiguousarray(x[:, p:p + c])) for p, c in ((0, 1), (1, 31), (32, 256), (288, 33), (321, 256), (577, 256), (833, 167))], axis=1)
+    d.close()
+    assert float(np.max(np.abs(got - ref))) <= TOL
+
+
+def test_lstm_spec_refuses_large_cells_loudly():
+    with pytest.raises(Exception, match="too large"):
+        nb.get_dsp(_random_lstm(16, 1), batch=4, jit=1)
+    d = nb.get_dsp(_random_lstm(16, 1), batch=256)  # default policy: falls back to the lane-group kernel
+    assert d.jit_state == -1 and "too large" in d.jit_note()
+    d.close()
