@@ -72,7 +72,9 @@ typedef struct nam_b200_options
   int32_t jit; /* model-specialised WaveNet kernel (the model compiled to SASS by NVRTC at load time, weights as FFMA
                   immediates; cubins cached under $NAM_B200_JIT_CACHE or <library dir>/jit_cache): 0 = library default
                   (on for handles with max_batch >= 256; $NAM_B200_JIT=0/1 overrides), 1 = required (create fails
-                  with the reason if NVRTC or the model's shape rules it out), 2 = off.  Only calls that take the
+                  with the reason if NVRTC or the model's shape rules it out), 2 = off, 3 = preferred (like 1, but a
+                  handle that cannot have it keeps the precompiled kernels silently; also asks reset() for the
+                  low-latency kernel on handles with few streams and maxBufferSize <= 128 -- the C++ shim's default).  Only calls that take the
                   persistent one-CTA-per-stream path use it; every other mode runs the precompiled kernels on the
                   same state */
   int32_t reserved[5];
@@ -93,7 +95,8 @@ typedef struct nam_b200_info
   double flops_per_frame; /* algorithmic FLOPs (2 x MACs) per frame per stream */
   int32_t kernel_variant; /* which CUDA specialisation serves this model (diagnostic) */
   int32_t jit_state; /* model-specialised kernel: 1 = active, 0 = not requested, -1 = requested but unavailable */
-  int32_t reserved[6];
+  int32_t jit_lat_state; /* the same for the low-latency kernel (few streams, calls of <= 128 frames; built by reset) */
+  int32_t reserved[5];
 } nam_b200_info;
 
 /* Fill with defaults: device -1, max_batch 1, fast_tanh 0, prewarm_on_reset 1. */
@@ -128,6 +131,30 @@ int nam_b200_process_f32(nam_b200_model* m, const float* in, float* out, int bat
  * No copies, no synchronisation. */
 int nam_b200_process_f32_device(nam_b200_model* m, const float* in_device, float* out_device, int batch, int n_frames,
                                 int64_t in_stride, int64_t out_stride, void* cuda_stream);
+
+/* Host-buffer contract of nam_b200_process_f32: any host memory is accepted; with PAGE-LOCKED buffers (cudaMallocHost,
+ * cudaHostRegister, or nam_b200_pin_host_buffer below) the call pipelines host->device copy, kernel and device->host copy
+ * of successive chunks of streams, with pageable buffers the driver stages the copies and that overlap is lost (same
+ * results, ~15-20 % slower end to end).  These helpers let a host without the CUDA runtime pin its buffers once. */
+int nam_b200_pin_host_buffer(void* ptr, int64_t bytes);
+int nam_b200_unpin_host_buffer(void* ptr);
+int nam_b200_host_buffer_is_pinned(const void* ptr); /* 1 pinned / device-accessible, 0 pageable, < 0 error */
+
+/* Several GPUs behind one handle (BASELINE.json config 5: the batch shards across GPUs, no collective on the data path:
+ * the streams are independent).  `opts->max_batch` = total streams, dealt out in contiguous blocks
+ * [max_batch * i / n, max_batch * (i + 1) / n) to devices[i]; `opts->device` is ignored.  process() runs one worker
+ * thread per GPU and returns when every shard's results are in `out`; errors name the device. */
+typedef struct nam_b200_multi nam_b200_multi;
+int nam_b200_multi_create_from_file(const char* nam_path, const nam_b200_options* opts, const int32_t* devices, int n_devices,
+                                    nam_b200_multi** out);
+int nam_b200_multi_create_from_json(const char* nam_json_text, const nam_b200_options* opts, const int32_t* devices,
+                                    int n_devices, nam_b200_multi** out);
+void nam_b200_multi_destroy(nam_b200_multi* mm);
+int nam_b200_multi_device_count(const nam_b200_multi* mm);
+int nam_b200_multi_shard(const nam_b200_multi* mm, int part, int32_t* device, int32_t* first_stream, int32_t* n_streams);
+int nam_b200_multi_reset(nam_b200_multi* mm, double sample_rate, int max_frames);
+int nam_b200_multi_process_f32(nam_b200_multi* mm, const float* in, float* out, int batch, int n_frames, int64_t in_stride,
+                               int64_t out_stride);
 
 /* nam::DSP::process for stream 0 of the handle: planar input[channel][frame], in_channels input arrays and
  * out_channels output arrays like the reference's NAM_SAMPLE** (NAM/dsp.h:97). */

@@ -53,7 +53,7 @@ def _stale() -> bool:
 def embed_spec_source() -> None:
     """wavenet_spec.cuh / lstm_spec.cuh -> csrc/*_src.inc, C++ raw string literals: the library carries the sources of the
     model-specialised kernels and hands them to NVRTC at model-load time (jit_spec.cpp)."""
-    for stem in ("wavenet_spec", "lstm_spec"):
+    for stem in ("wavenet_spec", "lstm_spec", "wavenet_lat"):
         _embed(stem)
 
 

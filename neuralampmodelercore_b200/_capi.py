@@ -48,7 +48,8 @@ class Info(C.Structure):
         ("flops_per_frame", C.c_double),
         ("kernel_variant", C.c_int32),
         ("jit_state", C.c_int32),
-        ("reserved", C.c_int32 * 6),
+        ("jit_lat_state", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -79,6 +80,16 @@ EXPORTED_SYMBOLS = [
     "nam_b200_submodel_json",
     "nam_b200_jit_prepare_json",
     "nam_b200_jit_note",
+    "nam_b200_pin_host_buffer",
+    "nam_b200_unpin_host_buffer",
+    "nam_b200_host_buffer_is_pinned",
+    "nam_b200_multi_create_from_file",
+    "nam_b200_multi_create_from_json",
+    "nam_b200_multi_destroy",
+    "nam_b200_multi_device_count",
+    "nam_b200_multi_shard",
+    "nam_b200_multi_reset",
+    "nam_b200_multi_process_f32",
 ]
 
 
@@ -135,6 +146,17 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.nam_b200_jit_prepare_json.restype = C.c_int
     lib.nam_b200_jit_note.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     lib.nam_b200_jit_note.restype = C.c_int64
+    lib.nam_b200_pin_host_buffer.argtypes = [C.c_void_p, C.c_int64]
+    lib.nam_b200_unpin_host_buffer.argtypes = [C.c_void_p]
+    lib.nam_b200_host_buffer_is_pinned.argtypes = [C.c_void_p]
+    lib.nam_b200_multi_create_from_json.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_void_p)]
+    lib.nam_b200_multi_create_from_file.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_void_p)]
+    lib.nam_b200_multi_destroy.argtypes = [C.c_void_p]
+    lib.nam_b200_multi_destroy.restype = None
+    lib.nam_b200_multi_device_count.argtypes = [C.c_void_p]
+    lib.nam_b200_multi_shard.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.nam_b200_multi_reset.argtypes = [C.c_void_p, C.c_double, C.c_int]
+    lib.nam_b200_multi_process_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64]
     lib.nam_b200_measure_fp32_tflops.argtypes = [C.c_int, C.c_int]
     lib.nam_b200_measure_fp32_tflops.restype = C.c_double
     for name in (

@@ -29,6 +29,9 @@ const char* const kSpecKernelSource =
 const char* const kLstmSpecKernelSource =
 #include "lstm_spec_src.inc"
   ;
+const char* const kLatKernelSource =
+#include "wavenet_lat_src.inc"
+  ;
 
 // ---- NVRTC through dlopen ------------------------------------------------------------------------------------------
 typedef struct _nvrtcProgram* nvrtcProgram;
@@ -182,7 +185,8 @@ struct CompiledKernel
 // header + `#include "<kernel_file>"` -> sm_100a cubin, through the disk cache.  `env_override`: development aid, an
 // environment variable that names a file to use instead of the embedded kernel source.
 CompiledKernel compile_or_fetch(const std::string& tag, const std::string& header, const char* kernel_file,
-                                const char* embedded_source, const char* env_override, const std::vector<std::string>& defines)
+                                const char* embedded_source, const char* env_override, const std::vector<std::string>& defines,
+                                const std::vector<std::pair<const char*, const char*>>& extra_headers = {})
 {
   CompiledKernel r;
   std::string kernel_source = embedded_source;
@@ -198,6 +202,8 @@ CompiledKernel compile_or_fetch(const std::string& tag, const std::string& heade
   uint64_t h = 1469598103934665603ull;
   h = fnv1a(h, header.data(), header.size());
   h = fnv1a(h, kernel_source.data(), kernel_source.size());
+  for (const auto& eh : extra_headers)
+    h = fnv1a(h, eh.second, std::strlen(eh.second));
   h = fnv1a(h, opts_text.data(), opts_text.size());
   char name[96];
   std::snprintf(name, sizeof name, "%s_%016llx.cubin", tag.c_str(), (unsigned long long)h);
@@ -216,10 +222,14 @@ CompiledKernel compile_or_fetch(const std::string& tag, const std::string& heade
   }
   const auto t0 = std::chrono::steady_clock::now();
   const std::string source = header + "\n#include \"" + kernel_file + "\"\n";
-  const char* hdr_src[] = {kernel_source.c_str()};
-  const char* hdr_name[] = {kernel_file};
+  std::vector<const char*> hdr_src = {kernel_source.c_str()}, hdr_name = {kernel_file};
+  for (const auto& eh : extra_headers)
+  {
+    hdr_name.push_back(eh.first);
+    hdr_src.push_back(eh.second);
+  }
   nvrtcProgram prog = nullptr;
-  int rc = n.CreateProgram(&prog, source.c_str(), (tag + "_model.cu").c_str(), 1, hdr_src, hdr_name);
+  int rc = n.CreateProgram(&prog, source.c_str(), (tag + "_model.cu").c_str(), (int)hdr_src.size(), hdr_src.data(), hdr_name.data());
   if (rc != 0)
   {
     r.why_not = std::string("nvrtcCreateProgram: ") + n.GetErrorString(rc);
@@ -320,9 +330,12 @@ std::string spec_header_source(const WaveNetPlan& plan)
     o << "  {" << L.kernel << ", " << L.dilation << ", " << L.act << ", " << L.w_off << ", " << L.ring_off << ", " << L.ring_mask
       << ", " << float_literal(L.ap0) << ", " << float_literal(L.ap1) << ", " << float_literal(L.ap2) << ", "
       << float_literal(L.ap3) << "},\n";
+  o << "};\n// channels (padded) of the array that owns layer li\n"
+       "__host__ __device__ constexpr int layer_channels(int li) { int c = A[0].C; for (int a = 0; a < NA; a++) if (li >= A[a].layer0 && li < "
+       "A[a].layer0 + A[a].n_layers) c = A[a].C; return c; }\n";
   // the weights as bit patterns (exact, locale-free); wavenet_spec.cuh reads them through spec::w(i), and after full
   // unrolling every index is a constant, so the loads fold into FFMA immediates
-  o << "};\n__device__ const unsigned Wb[" << plan.blob.size() << "] = {\n";
+  o << "__device__ const unsigned Wb[" << plan.blob.size() << "] = {\n";
   char buf[16];
   for (size_t i = 0; i < plan.blob.size(); i++)
   {
@@ -354,6 +367,62 @@ SpecBuild build_spec_kernel(const WaveNetPlan& plan, const SpecGeometry& g)
   r.cubin = ck.cubin;
   r.from_cache = ck.from_cache;
   r.compile_seconds = ck.compile_seconds;
+  return r;
+}
+
+// shared-memory bytes of wavenet_lat.cuh's Plan<F>: tile + exchange buffer + every (layer, tap) history window
+size_t lat_smem_bytes(const WaveNetPlan& plan, int frames)
+{
+  int pmax = 0;
+  for (int a = 0; a < plan.n_arrays; a++)
+    pmax = std::max(pmax, plan.cp[a] / 4);
+  size_t f4 = (size_t)2 * pmax * frames;
+  for (int a = 0; a < plan.n_arrays; a++)
+    for (int i = 0; i < plan.arrays[a].n_layers; i++)
+    {
+      const LayerDesc& L = plan.layers[plan.arrays[a].layer0 + i];
+      for (int k = 0; k + 1 < L.kernel; k++)
+        f4 += (size_t)(plan.cp[a] / 4) * std::min((L.kernel - 1 - k) * L.dilation, frames);
+    }
+  return f4 * 16;
+}
+
+SpecBuild build_lat_kernel(const WaveNetPlan& plan, int frame_warps)
+{
+  SpecBuild r;
+  r.geom.nt = 128 * frame_warps;
+  r.geom.s = 1;
+  r.geom.min_ctas = 1;
+  SpecGeometry tiny; // eligibility of the family (heads, finiteness); the throughput kernel's shared-memory rule does not apply
+  tiny.nt = 32;
+  tiny.min_ctas = 1;
+  std::string why;
+  if (!spec_eligible(plan, tiny, &why) && why.find("do not fit") == std::string::npos)
+  {
+    r.why_not = why;
+    return r;
+  }
+  if (plan.layers.size() > 64)
+  {
+    r.why_not = "more than 64 layers";
+    return r;
+  }
+  const size_t smem = lat_smem_bytes(plan, 32 * frame_warps);
+  if (smem > 200u * 1024u)
+  {
+    r.why_not = "history windows of a " + std::to_string(32 * frame_warps) + "-frame call do not fit in shared memory";
+    return r;
+  }
+  const CompiledKernel ck = compile_or_fetch("wavenet_lat", spec_header_source(plan), "wavenet_lat.cuh", kLatKernelSource,
+                                             "NAM_B200_LAT_SOURCE", {"-DNAMB200_LAT_FW=" + std::to_string(frame_warps)},
+                                             {{"wavenet_spec.cuh", kSpecKernelSource}});
+  r.ok = ck.ok;
+  r.why_not = ck.why_not;
+  r.cubin = ck.cubin;
+  r.from_cache = ck.from_cache;
+  r.compile_seconds = ck.compile_seconds;
+  r.staged_cols = (int)(smem / 16); // (reused: float4 columns of dynamic shared memory)
+  r.max_planes = 1;
   return r;
 }
 

@@ -46,6 +46,12 @@ std::string spec_header_source(const WaveNetPlan& plan);
 /// Cache directory: $NAM_B200_JIT_CACHE, else <directory of libnam_b200.so>/jit_cache.  Never throws.
 SpecBuild build_spec_kernel(const WaveNetPlan& plan, const SpecGeometry& g);
 
+/// The low-latency kernel (wavenet_lat.cuh: one CTA per stream, calls of up to 32 * frame_warps frames, output channels
+/// split over four warp groups, all history requested at kernel start).  SpecBuild::geom.nt = threads per CTA,
+/// lat_smem_bytes() = its dynamic shared memory.
+size_t lat_smem_bytes(const WaveNetPlan& plan, int frames);
+SpecBuild build_lat_kernel(const WaveNetPlan& plan, int frame_warps);
+
 /// The same for a small mono LSTM (lstm_spec.cuh: one thread per stream, weights as FFMA immediates); the cubin holds
 /// lstm_spec_kernel_exact and lstm_spec_kernel_fast (the fast-tanh switch is read at run time, lstm.cpp:48).
 bool lstm_spec_eligible(const ModelSpec& ms, std::string* why_not);

@@ -12,6 +12,8 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <set>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -50,6 +52,19 @@ struct CudaError : public std::runtime_error
     if (_e != cudaSuccess)                                                                                           \
       throw CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e));                                    \
   } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device); safe when several handles launch from
+// several host threads (the multi-device entry runs one worker thread per GPU)
+void ensure_max_dynamic_smem(const void* kern, int device, int bytes)
+{
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({kern, device}))
+    return;
+  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.insert({kern, device});
+}
 
 // =================================================================================================
 // LSTM kernel  (NAM/lstm.cpp:31-68 cell, :103-168 process)
@@ -369,6 +384,18 @@ struct nam_b200_model
   cudaLibrary_t spec_lib = nullptr;
   cudaKernel_t spec_kernel = nullptr;
   cudaKernel_t lstm_spec_kernels[2] = {nullptr, nullptr}; // lstm_spec.cuh: exact / fast activation regime
+  // low-latency kernel (wavenet_lat.cuh): few streams x short calls; built by reset() for the handle's maxBufferSize
+  cudaLibrary_t lat_lib = nullptr;
+  cudaKernel_t lat_kernel = nullptr;
+  int lat_frames = 0, lat_threads = 0; // calls of up to lat_frames frames
+  size_t lat_smem = 0;
+  int lat_state = 0; // like spec_state
+  std::string lat_note;
+  unsigned* h_flag = nullptr; // completion doorbell of the low-latency kernel: one word of mapped pinned memory
+  unsigned* h_flag_dev = nullptr;
+  unsigned flag_seq = 0;
+  bool flag_pending = false; // the launch just issued rings the doorbell
+  bool opts_timing_events = false; // $NAM_B200_TIMING=1: keep the per-call CUDA events (nam_b200_last_kernel_ms) on that path
   SpecGeometry spec_geom;
   size_t spec_smem = 0;
   int spec_ctas_per_sm = 0;
@@ -416,6 +443,8 @@ struct nam_b200_model
       cudaFree(d_glayers);
     if (spec_lib)
       cudaLibraryUnload(spec_lib);
+    if (lat_lib)
+      cudaLibraryUnload(lat_lib);
     if (d_tile_flags)
       cudaFree(d_tile_flags);
     if (d_hist)
@@ -430,6 +459,8 @@ struct nam_b200_model
       cudaFree(d_out);
     if (h_pin)
       cudaFreeHost(h_pin);
+    if (h_flag)
+      cudaFreeHost(h_flag);
     if (ev0)
       cudaEventDestroy(ev0);
     if (ev1)
@@ -472,12 +503,7 @@ template <int C0, int C1, int NT, int MINB, int LQ>
 void launch_wavenet_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem, cudaStream_t st)
 {
   auto kern = wavenet_fused_kernel<C0, C1, kWnS, NT, MINB, LQ>;
-  static bool configured[64] = {false};
-  if (!configured[m->device & 63])
-  {
-    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured[m->device & 63] = true;
-  }
+  ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), m->device, 227 * 1024);
   kern<<<grid, NT, smem, st>>>(kp);
   CUDA_CHECK(cudaGetLastError());
 }
@@ -513,12 +539,7 @@ template <int C0, int C1, int S, int NT, int MINB, int LQ>
 void launch_wavenet_ls_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem, cudaStream_t st)
 {
   auto kern = wavenet_fused_kernel<C0, C1, S, NT, MINB, LQ, true>;
-  static bool configured[64] = {false};
-  if (!configured[m->device & 63])
-  {
-    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured[m->device & 63] = true;
-  }
+  ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), m->device, 227 * 1024);
   // The tiles spin on each other's flags, so they must all be resident at once: a cooperative launch is
   // gang-scheduled (it starts only when the whole grid fits), which keeps two such launches from different handles
   // from starving each other.
@@ -614,12 +635,7 @@ template <int C0, int C1>
 void launch_wavenet_small_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem, cudaStream_t st)
 {
   auto kern = wavenet_fused_kernel<C0, C1, 1, kSmallNt, 3, kSmallLq, false>;
-  static bool configured[64] = {false};
-  if (!configured[m->device & 63])
-  {
-    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured[m->device & 63] = true;
-  }
+  ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), m->device, 227 * 1024);
   kern<<<grid, kSmallNt, smem, st>>>(kp);
   CUDA_CHECK(cudaGetLastError());
 }
@@ -821,21 +837,19 @@ struct SpecKernelParams
   long in_stride, out_stride;
   int batch, n_frames;
   uint32_t t_base;
+  float* scratch; // stream-pair variant (S = 2) only: per-CTA interleaved rings; the shipped geometry is S = 1
+  long scratch_stride;
 };
+
+int jit_mode(const nam_b200_model* m);
 
 // Decide whether this handle gets a specialised kernel, build / fetch it, load it.  jit option: 0 = auto (on for
 // throughput handles: max_batch >= 256, where one compilation pays for itself within the first calls), 1 = required
 // (creation fails with the reason if it cannot be had), 2 = off.  $NAM_B200_JIT=0/1 overrides "auto".
 void setup_spec_kernel(nam_b200_model* m)
 {
-  int mode = m->opts.jit;
-  if (mode == 0)
-  {
-    const char* e = std::getenv("NAM_B200_JIT");
-    if (e && *e)
-      mode = (e[0] == '0') ? 2 : 1;
-  }
-  const bool wanted = mode == 1 || (mode == 0 && m->opts.max_batch >= 256);
+  const int mode = jit_mode(m);
+  const bool wanted = mode == 1 || ((mode == 0 || mode == 3) && m->opts.max_batch >= 256);
   if (!wanted || m->opts.kernel_geometry != 0)
     return;
   SpecGeometry g;
@@ -882,9 +896,104 @@ void setup_spec_kernel(nam_b200_model* m)
   }
 }
 
+// the handle's JIT mode with the environment override applied: 1 required, 2 off, 3 preferred (try, fall back silently),
+// 0 automatic
+int jit_mode(const nam_b200_model* m)
+{
+  int mode = m->opts.jit;
+  if (mode == 0 || mode == 3)
+  {
+    const char* e = std::getenv("NAM_B200_JIT");
+    if (e && *e)
+      mode = (e[0] == '0') ? 2 : (mode == 3 ? 3 : 1);
+  }
+  return mode;
+}
+
+struct LatKernelParams // mirror of namb200_lat::LatParams
+{
+  float* state;
+  long state_stride;
+  const float* in;
+  float* out;
+  long in_stride, out_stride;
+  int batch, n_frames;
+  uint32_t t_base;
+  unsigned* done_flag;
+  unsigned seq;
+};
+
+// reset(): plugin-style handles (few streams, maxBufferSize <= 128) get the low-latency kernel for calls of up to
+// 64 / 128 frames.  Wanted when jit is "required" or "preferred" (the C++ shim's default), never by the automatic policy.
+void setup_lat_kernel(nam_b200_model* m)
+{
+  if (m->spec.arch != Arch::WaveNet || m->use_generic || m->wn_geometry > 1 || m->opts.kernel_geometry != 0)
+    return;
+  const int mode = jit_mode(m);
+  if (!(mode == 1 || mode == 3) || m->opts.max_batch > m->sm_count || m->max_frames > 128)
+    return;
+  const int fw = m->max_frames <= 64 ? 2 : 4;
+  if (m->lat_state == 1 && m->lat_frames == 32 * fw)
+    return;
+  if (m->lat_lib)
+    cudaLibraryUnload(m->lat_lib);
+  m->lat_lib = nullptr;
+  m->lat_kernel = nullptr;
+  m->lat_state = 0;
+  SpecBuild b = build_lat_kernel(m->plan, fw);
+  if (!b.ok)
+  {
+    m->lat_state = -1;
+    m->lat_note = b.why_not;
+    return; // the precompiled short-call geometries serve the handle
+  }
+  cudaError_t e = cudaLibraryLoadData(&m->lat_lib, b.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  if (e == cudaSuccess)
+    e = cudaLibraryGetKernel(&m->lat_kernel, m->lat_lib, "wavenet_lat_kernel");
+  m->lat_smem = lat_smem_bytes(m->plan, 32 * fw);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute((const void*)m->lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->lat_smem);
+  if (e != cudaSuccess)
+  {
+    cudaGetLastError();
+    if (m->lat_lib)
+      cudaLibraryUnload(m->lat_lib);
+    m->lat_lib = nullptr;
+    m->lat_kernel = nullptr;
+    m->lat_state = -1;
+    m->lat_note = std::string("loading the low-latency kernel failed: ") + cudaGetErrorString(e);
+    return;
+  }
+  if (!m->h_flag && cudaHostAlloc(&m->h_flag, 64, cudaHostAllocMapped) == cudaSuccess)
+  {
+    *m->h_flag = 0;
+    if (cudaHostGetDevicePointer(&m->h_flag_dev, m->h_flag, 0) != cudaSuccess)
+      m->h_flag_dev = nullptr;
+  }
+  cudaGetLastError();
+  m->lat_frames = 32 * fw;
+  m->lat_threads = b.geom.nt;
+  m->lat_state = 1;
+  m->lat_note = b.from_cache ? "cubin from cache" : "compiled in " + std::to_string(b.compile_seconds) + " s";
+}
+
+void launch_wavenet_lat(nam_b200_model* m, const WaveNetKernelParams& kp, cudaStream_t st)
+{
+  // single-stream calls ring the doorbell in mapped host memory (process_planar spins on it instead of synchronising)
+  unsigned* flag = (kp.batch == 1 && m->h_flag_dev != nullptr) ? m->h_flag_dev : nullptr;
+  if (flag)
+    m->flag_seq++;
+  LatKernelParams lp{kp.state, kp.state_stride, kp.in, kp.out, kp.in_stride, kp.out_stride, kp.batch, kp.n_frames, kp.t_base,
+                     flag, m->flag_seq};
+  m->flag_pending = flag != nullptr;
+  void* args[] = {&lp};
+  CUDA_CHECK(cudaLaunchKernel((const void*)m->lat_kernel, dim3(kp.batch), dim3(m->lat_threads), args, m->lat_smem, st));
+}
+
 void launch_wavenet_spec(nam_b200_model* m, const WaveNetKernelParams& kp, cudaStream_t st)
 {
-  SpecKernelParams sp{kp.state, kp.state_stride, kp.in, kp.out, kp.in_stride, kp.out_stride, kp.batch, kp.n_frames, kp.t_base};
+  SpecKernelParams sp{kp.state, kp.state_stride, kp.in,  kp.out, kp.in_stride, kp.out_stride,
+                      kp.batch, kp.n_frames,     kp.t_base, nullptr, 0};
   void* args[] = {&sp};
   int grid = std::min(kp.batch, m->spec_ctas_per_sm * m->sm_count);
   if (grid < 1)
@@ -917,12 +1026,7 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
     const int grid_g = std::min(batch, 16 * m->sm_count);
     if (wbytes <= 200 * 1024)
     {
-      static bool configured[64] = {false};
-      if (!configured[m->device & 63])
-      {
-        CUDA_CHECK(cudaFuncSetAttribute(wavenet_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured[m->device & 63] = true;
-      }
+      ensure_max_dynamic_smem(reinterpret_cast<const void*>(wavenet_generic_kernel<true>), m->device, 200 * 1024);
       wavenet_generic_kernel<true><<<grid_g, kGenTile, wbytes, st>>>(gp);
     }
     else
@@ -968,6 +1072,13 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
     if (grid_tc < 1)
       grid_tc = 1;
     launch_tc_dispatch(c0, c1, m, kp, grid_tc, smem_tc, st);
+    m->launches++;
+    return;
+  }
+  // few streams, short calls, on a handle that has the low-latency kernel (wavenet_lat.cuh): one CTA per stream
+  if (m->lat_state == 1 && n_frames <= m->lat_frames && batch <= m->sm_count)
+  {
+    launch_wavenet_lat(m, kp, st);
     m->launches++;
     return;
   }
@@ -1079,14 +1190,8 @@ struct LstmSpecKernelParams // mirror of namb200_lstm_spec::LstmSpecParams
 
 void setup_lstm_spec_kernel(nam_b200_model* m)
 {
-  int mode = m->opts.jit;
-  if (mode == 0)
-  {
-    const char* e = std::getenv("NAM_B200_JIT");
-    if (e && *e)
-      mode = (e[0] == '0') ? 2 : 1;
-  }
-  if (!(mode == 1 || (mode == 0 && m->opts.max_batch >= 256)))
+  const int mode = jit_mode(m);
+  if (!(mode == 1 || ((mode == 0 || mode == 3) && m->opts.max_batch >= 256)))
     return;
   SpecBuild b = build_lstm_spec_kernel(m->spec);
   if (!b.ok)
@@ -1187,12 +1292,7 @@ void launch_lstm(nam_b200_model* m, const float* d_in, float* d_out, int batch, 
   const size_t smem = (((m->n_weight_floats + 3) & ~(size_t)3) + (size_t)ls.num_layers * 2 * H * kLstmThreads
                        + (size_t)4 * H * kLstmThreads + (size_t)2 * kLstmThreads * (kLstmChunk + 1))
                       * sizeof(float);
-  static bool configured[64] = {false};
-  if (!configured[m->device & 63])
-  {
-    CUDA_CHECK(cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured[m->device & 63] = true;
-  }
+  ensure_max_dynamic_smem(reinterpret_cast<const void*>(lstm_kernel), m->device, 227 * 1024);
   if (smem > 227 * 1024)
     throw std::runtime_error("LSTM too large for the shared-memory resident kernel");
   const int grid = (batch + kLstmThreads - 1) / kLstmThreads;
@@ -1218,12 +1318,7 @@ void launch_linear(nam_b200_model* m, const float* d_in, float* d_out, int batch
   kp.batch = batch;
   kp.n_frames = n_frames;
   const size_t smem = (((size_t)li.receptive_field + 3) & ~(size_t)3) * 4 + ((size_t)li.receptive_field - 1 + kLinThreads) * 4;
-  static bool configured[64] = {false};
-  if (!configured[m->device & 63])
-  {
-    CUDA_CHECK(cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured[m->device & 63] = true;
-  }
+  ensure_max_dynamic_smem(reinterpret_cast<const void*>(linear_kernel), m->device, 227 * 1024);
   if (smem > 227 * 1024)
     throw std::runtime_error("Linear receptive field too long for the direct-form kernel");
   dim3 grid((n_frames + kLinThreads - 1) / kLinThreads, batch);
@@ -1273,12 +1368,7 @@ void launch_convnet(nam_b200_model* m, const float* d_in, float* d_out, int batc
   const int grid = std::min(batch, 16 * m->sm_count);
   if (wbytes <= 200 * 1024)
   {
-    static bool configured[64] = {false};
-    if (!configured[m->device & 63])
-    {
-      CUDA_CHECK(cudaFuncSetAttribute(convnet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured[m->device & 63] = true;
-    }
+    ensure_max_dynamic_smem(reinterpret_cast<const void*>(convnet_kernel<true>), m->device, 200 * 1024);
     convnet_kernel<true><<<grid, kGenTile, wbytes, st>>>(kp);
   }
   else
@@ -1408,6 +1498,8 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
     return fail(NAM_B200_ERR_INVALID_ARGUMENT, "max_batch must be >= 1");
   m->spec = std::move(spec);
   m->fast_tanh_runtime = m->opts.fast_tanh;
+  if (const char* e = std::getenv("NAM_B200_TIMING"))
+    m->opts_timing_events = (*e == '1');
 
   if (m->spec.arch == Arch::Container)
   {
@@ -1663,8 +1755,30 @@ int process_planar(nam_b200_model* m, const T* const* input, T* const* output, i
     {
       float* din = m->h_pin_dev;
       float* dout = m->h_pin_dev + (hout - hin);
-      CUDA_CHECK(cudaEventRecord(m->ev0, m->stream));
+      m->flag_pending = false;
+      const bool doorbell = m->lat_state == 1 && m->h_flag_dev != nullptr && n_frames <= m->lat_frames && !m->opts_timing_events;
+      if (!doorbell)
+        CUDA_CHECK(cudaEventRecord(m->ev0, m->stream));
       run_device(m, din, dout, 1, n_frames, (long)(ci * n), (long)(co * n), m->stream);
+      if (doorbell && m->flag_pending)
+      {
+        // the low-latency kernel served the call: wait for its doorbell (a word of host memory) -- no stream
+        // synchronisation, no event records on the per-block path
+        const unsigned want = m->flag_seq;
+        volatile unsigned* flag = m->h_flag;
+        long spins = 0;
+        while (*flag != want)
+          if (++spins > (1L << 26))
+          {
+            CUDA_CHECK(cudaStreamSynchronize(m->stream)); // surfaces a launch / execution error instead of hanging
+            break;
+          }
+        m->timing_valid = false;
+        for (size_t c = 0; c < co; c++)
+          for (size_t i = 0; i < n; i++)
+            output[c][i] = (T)hout[c * n + i];
+        return NAM_B200_OK;
+      }
       CUDA_CHECK(cudaEventRecord(m->ev1, m->stream));
     }
     else
@@ -1902,15 +2016,21 @@ int nam_b200_jit_prepare_json(const char* nam_json_text, int fast_tanh, char* ou
     if (ms.arch != Arch::WaveNet && ms.arch != Arch::LSTM)
       return fail(NAM_B200_ERR_UNSUPPORTED, "only WaveNets and LSTMs have model-specialised kernels");
     const SpecBuild b = ms.arch == Arch::LSTM ? build_lstm_spec_kernel(ms) : build_spec_kernel(plan_wavenet(ms), SpecGeometry{});
+    // WaveNets: also the low-latency kernel for 64-frame calls (the plugin protocol), so that a first Reset finds it cached
+    SpecBuild lat;
+    if (ms.arch == Arch::WaveNet)
+      lat = build_lat_kernel(plan_wavenet(ms), 2);
     std::string why;
     for (char c : b.why_not.substr(0, 600))
       why += (c == '"' || c == '\\') ? '\'' : (c == '\n' ? ' ' : c);
     char buf[1024];
     std::snprintf(buf, sizeof buf,
                   "{\"ok\": %s, \"from_cache\": %s, \"compile_seconds\": %.3f, \"cubin_bytes\": %zu, \"threads\": %d, "
-                  "\"frames_per_thread\": %d, \"smem_bytes\": %zu, \"why_not\": \"%s\"}",
+                  "\"frames_per_thread\": %d, \"smem_bytes\": %zu, \"why_not\": \"%s\", \"lat_ok\": %s, "
+                  "\"lat_compile_seconds\": %.3f, \"lat_cubin_bytes\": %zu}",
                   b.ok ? "true" : "false", b.from_cache ? "true" : "false", b.compile_seconds, b.cubin.size(), b.geom.nt,
-                  b.geom.s, b.ok ? b.smem_bytes() : (size_t)0, why.c_str());
+                  b.geom.s, b.ok ? b.smem_bytes() : (size_t)0, why.c_str(), lat.ok ? "true" : "false", lat.compile_seconds,
+                  lat.cubin.size());
     if (out && capacity > 0)
     {
       std::strncpy(out, buf, (size_t)capacity - 1);
@@ -1933,12 +2053,13 @@ int64_t nam_b200_jit_note(const nam_b200_model* m, char* out, int64_t capacity)
   m = active_model(m);
   if (!m)
     return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null model handle");
+  const std::string note = m->spec_note + (m->lat_note.empty() ? "" : (m->spec_note.empty() ? "" : "; ") + ("low-latency kernel: " + m->lat_note));
   if (out && capacity > 0)
   {
-    std::strncpy(out, m->spec_note.c_str(), (size_t)capacity - 1);
+    std::strncpy(out, note.c_str(), (size_t)capacity - 1);
     out[capacity - 1] = '\0';
   }
-  return (int64_t)m->spec_note.size();
+  return (int64_t)note.size();
 }
 
 int nam_b200_inspect_file(const char* nam_path, int fast_tanh, char* out, int64_t capacity)
@@ -2018,6 +2139,7 @@ int nam_b200_get_info(const nam_b200_model* m, nam_b200_info* info)
   r.flops_per_frame = m->flops_per_frame;
   r.kernel_variant = m->variant;
   r.jit_state = m->spec_state;
+  r.jit_lat_state = m->lat_state;
   const size_t n = std::min<size_t>(sizeof(r), (size_t)std::max(info->struct_size, 0));
   const int32_t user_size = info->struct_size;
   std::memcpy(info, &r, n);
@@ -2046,6 +2168,7 @@ int nam_b200_reset(nam_b200_model* m, double sample_rate, int max_frames)
     ensure_staging(m, (size_t)m->opts.max_batch * max_frames * ch);
     ensure_pinned(m, (size_t)2 * max_frames * ch);
     ensure_hist(m);
+    setup_lat_kernel(m);
     init_state(m);
     m->is_reset = true;
     CUDA_CHECK(cudaEventRecord(m->ev0, m->stream));
@@ -2154,6 +2277,168 @@ int nam_b200_process_f32(nam_b200_model* m, const float* in, float* out, int bat
     CUDA_CHECK(cudaStreamSynchronize(m->stream));
     m->timing_valid = true;
     return NAM_B200_OK;
+  });
+}
+
+// ---- host-memory helpers ---------------------------------------------------------------------------------------------
+// The host-buffer entries copy with cudaMemcpy2DAsync on side streams: with page-locked caller buffers the copies of
+// chunk c+1 / c-1 run under the kernel of chunk c; with pageable buffers the driver stages every copy through its own
+// bounce buffer and the overlap is lost (results are unaffected).  A host without the CUDA runtime pins through these.
+int nam_b200_pin_host_buffer(void* ptr, int64_t bytes)
+{
+  if (!ptr || bytes <= 0)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null buffer or non-positive size");
+  const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered)
+  {
+    cudaGetLastError();
+    return fail(NAM_B200_ERR_CUDA, std::string("cudaHostRegister failed: ") + cudaGetErrorString(e));
+  }
+  cudaGetLastError();
+  return NAM_B200_OK;
+}
+int nam_b200_unpin_host_buffer(void* ptr)
+{
+  if (!ptr)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null buffer");
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess)
+  {
+    cudaGetLastError();
+    return fail(NAM_B200_ERR_CUDA, std::string("cudaHostUnregister failed: ") + cudaGetErrorString(e));
+  }
+  return NAM_B200_OK;
+}
+/* 1 = page-locked (or device-accessible), 0 = pageable, < 0 = error */
+int nam_b200_host_buffer_is_pinned(const void* ptr)
+{
+  cudaPointerAttributes a{};
+  const cudaError_t e = cudaPointerGetAttributes(&a, ptr);
+  if (e != cudaSuccess)
+  {
+    cudaGetLastError();
+    return fail(NAM_B200_ERR_CUDA, std::string("cudaPointerGetAttributes failed: ") + cudaGetErrorString(e));
+  }
+  return a.type == cudaMemoryTypeUnregistered ? 0 : 1;
+}
+
+// ---- several GPUs behind one handle ------------------------------------------------------------------------------------
+// The batch shards across devices (streams are independent: SURVEY.md 8e, no collective on the data path): one complete
+// single-device handle per GPU, streams dealt out in contiguous blocks, one worker thread per GPU per call.
+extern "C++" {
+struct nam_b200_multi
+{
+  std::vector<std::unique_ptr<nam_b200_model>> parts;
+  std::vector<int> first; // first stream of part i; first.back() = total streams
+};
+
+namespace
+{
+template <typename F>
+int multi_for_each(nam_b200_multi* mm, F&& body) // body(part index) -> status; runs the parts concurrently
+{
+  const int n = (int)mm->parts.size();
+  std::vector<int> rc(n, NAM_B200_OK);
+  std::vector<std::string> msg(n);
+  std::vector<std::thread> workers;
+  for (int i = 0; i < n; i++)
+    workers.emplace_back([&, i]() {
+      rc[i] = body(i);
+      if (rc[i] != NAM_B200_OK)
+        msg[i] = g_last_error; // thread-local in the worker
+    });
+  for (auto& w : workers)
+    w.join();
+  for (int i = 0; i < n; i++)
+    if (rc[i] != NAM_B200_OK)
+      return fail(rc[i], "device " + std::to_string(mm->parts[i]->device) + ": " + msg[i]);
+  return NAM_B200_OK;
+}
+
+int multi_create(const char* text_or_path, bool is_file, const nam_b200_options* opts, const int32_t* devices, int n_devices,
+                 nam_b200_multi** out)
+{
+  if (!text_or_path || !out || n_devices < 1 || (n_devices > 0 && !devices))
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null argument or empty device list");
+  nam_b200_options o;
+  nam_b200_default_options(&o);
+  if (opts)
+    std::memcpy(&o, opts, std::min<size_t>(sizeof o, (size_t)std::max(opts->struct_size, 0)));
+  o.struct_size = sizeof o;
+  if (o.max_batch < n_devices)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "max_batch is smaller than the number of devices");
+  std::unique_ptr<nam_b200_multi> mm(new nam_b200_multi());
+  int s0 = 0;
+  for (int i = 0; i < n_devices; i++)
+  {
+    const int s1 = (int)((int64_t)o.max_batch * (i + 1) / n_devices); // sharding.shard_bounds' rule
+    nam_b200_options oi = o;
+    oi.device = devices[i];
+    oi.max_batch = s1 - s0;
+    nam_b200_model* h = nullptr;
+    const int rc = is_file ? nam_b200_create_from_file(text_or_path, &oi, &h) : nam_b200_create_from_json(text_or_path, &oi, &h);
+    if (rc != NAM_B200_OK)
+      return rc;
+    mm->parts.emplace_back(h);
+    mm->first.push_back(s0);
+    s0 = s1;
+  }
+  mm->first.push_back(s0);
+  *out = mm.release();
+  return NAM_B200_OK;
+}
+} // namespace
+} // extern "C++"
+
+int nam_b200_multi_create_from_file(const char* nam_path, const nam_b200_options* opts, const int32_t* devices, int n_devices,
+                                    nam_b200_multi** out)
+{
+  return multi_create(nam_path, true, opts, devices, n_devices, out);
+}
+int nam_b200_multi_create_from_json(const char* nam_json_text, const nam_b200_options* opts, const int32_t* devices,
+                                    int n_devices, nam_b200_multi** out)
+{
+  return multi_create(nam_json_text, false, opts, devices, n_devices, out);
+}
+void nam_b200_multi_destroy(nam_b200_multi* mm)
+{
+  delete mm;
+}
+int nam_b200_multi_device_count(const nam_b200_multi* mm)
+{
+  return mm ? (int)mm->parts.size() : 0;
+}
+int nam_b200_multi_shard(const nam_b200_multi* mm, int part, int32_t* device, int32_t* first_stream, int32_t* n_streams)
+{
+  if (!mm || part < 0 || part >= (int)mm->parts.size())
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "no such part");
+  if (device)
+    *device = mm->parts[part]->device;
+  if (first_stream)
+    *first_stream = mm->first[part];
+  if (n_streams)
+    *n_streams = mm->first[part + 1] - mm->first[part];
+  return NAM_B200_OK;
+}
+int nam_b200_multi_reset(nam_b200_multi* mm, double sample_rate, int max_frames)
+{
+  if (!mm)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null handle");
+  return multi_for_each(mm, [&](int i) { return nam_b200_reset(mm->parts[i].get(), sample_rate, max_frames); });
+}
+int nam_b200_multi_process_f32(nam_b200_multi* mm, const float* in, float* out, int batch, int n_frames, int64_t in_stride,
+                               int64_t out_stride)
+{
+  if (!mm || !in || !out)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null argument");
+  if (batch < 1 || batch > mm->first.back())
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "batch outside [1, max_batch]");
+  return multi_for_each(mm, [&](int i) {
+    const int s0 = mm->first[i], nb = std::min(mm->first[i + 1], batch) - s0;
+    if (nb <= 0)
+      return (int)NAM_B200_OK;
+    return nam_b200_process_f32(mm->parts[i].get(), in + (size_t)s0 * in_stride, out + (size_t)s0 * out_stride, nb, n_frames,
+                                in_stride, out_stride);
   });
 }
 

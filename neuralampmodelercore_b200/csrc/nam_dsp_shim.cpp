@@ -305,6 +305,9 @@ nam_b200_options make_options(int batch)
   o.fast_tanh = nam::activations::Activation::using_fast_tanh ? 1 : 0;
   // prewarm is driven by B200DSP::Reset (instance-level switch), not by the handle
   o.prewarm_on_reset = 0;
+  // compile the model when NVRTC is there (cubins are cached on disk): the plugin protocol -- one stream, 64-frame
+  // process() calls -- then runs on the low-latency kernel (wavenet_lat.cuh); $NAM_B200_JIT=0 turns it off
+  o.jit = 3;
   return o;
 }
 

@@ -63,6 +63,8 @@ struct SpecParams
   long in_stride, out_stride;
   int batch, n_frames;
   u32 t_base; // absolute frame index of in[:, 0] (mod 2^32)
+  float* scratch; // S = 2: [grid][scratch_stride] floats, a CTA's stream pair in the interleaved layout
+  long scratch_stride; // 2 * state_stride
 };
 
 // ---- scalar helpers (same arithmetic as wavenet_fused.cuh) ------------------------------------------------------
@@ -129,11 +131,18 @@ __device__ __forceinline__ float act_sigmoid(float x)
 }
 
 // ---- frame vectors -------------------------------------------------------------------------------------------------------
-// A thread owns S frames of the tile: {tid} for S = 1 (V = float), {tid, tid + NT} for S = 2 (V = a packed f32x2 pair,
-// low half = frame tid).  Everything a layer does is written once over V.  For S = 2 one instruction serves both
-// frames: `FFMA2 Racc, Rx.F32x2, <imm32>, Racc` -- the packed FMA takes the weight as a BROADCAST IMMEDIATE, so the
-// weight stream costs one issue slot per weight for two frames and the kernel is bound by the FMA pipe itself instead
-// of by instruction issue (profiles/r02a_*: S = 1 issues 16,800 instructions per warp-frame, 79 % of them FFMA).
+// S = 1: a thread owns frame `tid` of ONE stream, V = float.
+// S = 2: a thread owns frame `tid` of a PAIR of streams (2q, 2q + 1), V = a packed f32x2 pair (low half = the even
+// stream).  Everything a layer does is written once over V.  For S = 2 one instruction serves both streams:
+// `FFMA2 Racc, Rx.F32x2, <imm32>, Racc` -- the packed FMA takes the weight as a BROADCAST IMMEDIATE, so the weight stream
+// costs one issue slot and 16 instruction bytes per weight for two frames, and the kernel is bound by the FMA pipe itself
+// instead of by instruction issue / fetch (profiles/r02a_*: S = 1 issues 16,800 instructions per warp-frame, 79 % FFMA,
+// top stall no_instruction).  The pair must sit in an aligned register pair, so the activations of the two streams are
+// interleaved element-wise wherever they are stored: a column of a "sub-plane" is 16 bytes = (c A, c B, c' A, c' B) for
+// two channels c, c' -- one LDS.128 yields two ready pairs, conflict-free.  The rings of the library keep one stream
+// per ring ([C/4][R][4 floats]), so the kernel converts a pair's rings into a per-CTA scratch in the interleaved layout
+// when it picks the pair up, runs all tiles of the call on the scratch (bulk copies move interleaved columns), and
+// converts back at the end: other kernels never see the interleaved layout.
 template <int S>
 struct FrameVec;
 template <>
@@ -179,43 +188,32 @@ __device__ __forceinline__ void vsplat(u64& v, const float c)
 {
   v = dup2(c);
 }
-// the 4 channels of one plane at this thread's column(s), `p` = address of the frame-tid column
-template <int NT>
-__device__ __forceinline__ void vload4(const float4* p, float (&x)[4])
+// The 4 channels of plane `pl` at column offset `off` behind this thread's own column.  `col0` = the thread's column in
+// (sub-)plane 0, W = columns per (sub-)plane.  S = 1: one 16-byte column of a 4-channel plane.  S = 2: two 16-byte
+// columns of two 2-channel sub-planes, each (c A, c B, c' A, c' B).
+template <int W>
+__device__ __forceinline__ void load_plane(const float4* col0, const int pl, const int off, float (&x)[4])
 {
-  const float4 q = *p;
+  const float4 q = col0[pl * W - off];
   x[0] = q.x, x[1] = q.y, x[2] = q.z, x[3] = q.w;
 }
-// S = 2: the pair (frame tid, frame tid + NT) of a channel lives in two different columns.  Eight scalar loads put
-// every value straight into its half of a register pair; two 16-byte loads would need eight MOVs to re-pair them
-// (measured: 8,400 MOVs per tile pass, 1,610 instead of 1,760 Msamples/s).  `volatile` only keeps the compiler from
-// merging them back into vector loads; the shared-memory wavefronts are the same (8 per plane either way).
-template <int NT>
-__device__ __forceinline__ void vload4(const float4* p, u64 (&x)[4])
+template <int W>
+__device__ __forceinline__ void load_plane(const float4* col0, const int pl, const int off, u64 (&x)[4])
 {
-  const volatile float* a = reinterpret_cast<const volatile float*>(p);
-  const volatile float* b = reinterpret_cast<const volatile float*>(p + NT);
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-    x[i] = pack2(a[i], b[i]);
+  const float4 q0 = col0[(2 * pl) * W - off], q1 = col0[(2 * pl + 1) * W - off];
+  x[0] = pack2(q0.x, q0.y), x[1] = pack2(q0.z, q0.w), x[2] = pack2(q1.x, q1.y), x[3] = pack2(q1.z, q1.w);
 }
-template <int NT>
-__device__ __forceinline__ void vstore4(float4* p, const float (&x)[4])
+template <int W>
+__device__ __forceinline__ void store_plane(float4* col0, const int pl, const float (&x)[4])
 {
-  *p = make_float4(x[0], x[1], x[2], x[3]);
+  col0[pl * W] = make_float4(x[0], x[1], x[2], x[3]);
 }
-template <int NT>
-__device__ __forceinline__ void vstore4(float4* p, const u64 (&x)[4])
+template <int W>
+__device__ __forceinline__ void store_plane(float4* col0, const int pl, const u64 (&x)[4])
 {
-  volatile float* a = reinterpret_cast<volatile float*>(p);
-  volatile float* b = reinterpret_cast<volatile float*>(p + NT);
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-  {
-    float lo, hi;
-    unpack2(x[i], lo, hi);
-    a[i] = lo, b[i] = hi;
-  }
+  float4 q0, q1;
+  unpack2(x[0], q0.x, q0.y), unpack2(x[1], q0.z, q0.w), unpack2(x[2], q1.x, q1.y), unpack2(x[3], q1.z, q1.w);
+  col0[(2 * pl) * W] = q0, col0[(2 * pl + 1) * W] = q1;
 }
 
 // one element of layer LI's activation, channel i (activations.h:59-133)
@@ -415,9 +413,11 @@ __device__ __forceinline__ void request_layer_history(TileCtx& c, IntC<LI>)
 {
   constexpr spec::Layer Ld = spec::L[LI];
   constexpr int C = spec::A[AI].C;
-  constexpr int W = spec::LS + NT * S;
+  constexpr int W = spec::LS + NT;
+  // S = 2: C/2 sub-planes of 16-byte columns; the interleaved ring of a pair is twice the size of one stream's ring
   if (c.warp == 0)
-    hist_load<C / 4, (Ld.K - 1) * Ld.dil, Ld.ring_mask, W>(c.buf, c.state + Ld.ring_off, c.tabs0, c.bar, c.lane);
+    hist_load<(S == 1 ? C / 4 : C / 2), (Ld.K - 1) * Ld.dil, Ld.ring_mask, W>(c.buf, c.state + S * Ld.ring_off, c.tabs0, c.bar,
+                                                                              c.lane);
 }
 
 // One layer array for the S frames a thread owns (cf. namb200::array_forward), V = FrameVec<S>.
@@ -431,10 +431,10 @@ __device__ __forceinline__ void array_forward(TileCtx& c, const V (&hin)[spec::A
 {
   constexpr spec::Array A = spec::A[AI];
   constexpr int C = A.C, CIN = A.CIN, HOUT = A.HOUT, P = C / 4;
-  constexpr int T = NT * S;
-  constexpr int W = spec::LS + T;
+  constexpr int W = spec::LS + NT;
+  constexpr int HP = (S == 1) ? C / 4 : C / 2; // (sub-)planes the history copies move
   static_assert(A.head_kernel == 1, "convolutional heads are served by the generic fused kernel");
-  float4* const col0 = c.buf + spec::LS + threadIdx.x; // this thread's (first) column of plane 0
+  float4* const col0 = c.buf + spec::LS + threadIdx.x; // this thread's column of (sub-)plane 0
 
   // ---- rechannel (Conv1x1, no bias; model.cpp:492) -> this thread's columns of the tile
   {
@@ -451,7 +451,7 @@ __device__ __forceinline__ void array_forward(TileCtx& c, const V (&hin)[spec::A
     for (int pl = 0; pl < P; pl++)
     {
       const V q[4] = {h[4 * pl], h[4 * pl + 1], h[4 * pl + 2], h[4 * pl + 3]};
-      vstore4<NT>(col0 + pl * W, q);
+      store_plane<W>(col0, pl, q);
     }
   }
 
@@ -468,7 +468,7 @@ __device__ __forceinline__ void array_forward(TileCtx& c, const V (&hin)[spec::A
     mbar_wait(c.bar, c.phase); // .. and its history has landed in front of it
     c.phase ^= 1u;
     if (c.warp == 0) // newest columns -> ring (reads the tile until B1)
-      hist_store<P, L, Ld.ring_mask, W>(c.buf, c.state + Ld.ring_off, c.tabs0, c.tv, c.lane);
+      hist_store<HP, L, Ld.ring_mask, W>(c.buf, c.state + S * Ld.ring_off, c.tabs0, c.tv, c.lane);
 
     // ---- phase 1: z = b + M c + sum_k W_k h[t - (K-1-k) d];  a = act(z);  head += a
     V acc[C];
@@ -487,7 +487,7 @@ __device__ __forceinline__ void array_forward(TileCtx& c, const V (&hin)[spec::A
       for (int pl = 0; pl < P; pl++)
       {
         V x[4];
-        vload4<NT>(col0 + pl * W - off, x);
+        load_plane<W>(col0, pl, off, x);
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -508,7 +508,7 @@ __device__ __forceinline__ void array_forward(TileCtx& c, const V (&hin)[spec::A
       for (int o = 0; o < C; o++)
         head[o] = vadd(head[o], acc[o]); // model.cpp:530
     }
-    if (c.warp == 0 && c.lane < P)
+    if (c.warp == 0 && c.lane < HP)
       bulk_wait_all(); // my ring stores are done: the tile may be rewritten, the rings may be re-read
     __syncthreads(); // B1: every tap read of this layer's input is done
     // the next unit's history lands under this layer's 1x1 phase
@@ -523,7 +523,7 @@ __device__ __forceinline__ void array_forward(TileCtx& c, const V (&hin)[spec::A
     for (int pl = 0; pl < P; pl++)
     {
       V own[4];
-      vload4<NT>(col0 + pl * W, own);
+      load_plane<W>(col0, pl, 0, own);
 #pragma unroll
       for (int i = 0; i < 4; i++)
         hn[4 * pl + i] = vaddc(own[i], spec::w(w_pb + 4 * pl + i));
@@ -539,7 +539,7 @@ __device__ __forceinline__ void array_forward(TileCtx& c, const V (&hin)[spec::A
       for (int pl = 0; pl < P; pl++)
       {
         const V q[4] = {hn[4 * pl], hn[4 * pl + 1], hn[4 * pl + 2], hn[4 * pl + 3]};
-        vstore4<NT>(col0 + pl * W, q);
+        store_plane<W>(col0, pl, q);
       }
     }
     else
@@ -564,12 +564,63 @@ __device__ __forceinline__ void array_forward(TileCtx& c, const V (&hin)[spec::A
     headout[ho] = vaddc(headout[ho], spec::w(A.head_off + C * HOUT + ho)); // bias (zero when the head has none)
 }
 
+// ---- S = 2: one stream per ring <-> the CTA's interleaved scratch ----------------------------------------------------------
+// `ra`, `rb`: the two streams' ring storage ([C/4][R][4 floats] per layer, wavenet_fused.cuh); `sc`: the scratch, per layer
+// [C/2 sub-planes][R] columns of (c A, c B, c' A, c' B).  Whole rings are converted (R <= 2 x look-back).
+template <int NT>
+__device__ __forceinline__ void pair_rings_to_scratch(const float* ra, const float* rb, float* sc)
+{
+  static_for<0, spec::NL>([&](auto li_c) {
+    constexpr int LI = decltype(li_c)::value;
+    constexpr spec::Layer Ld = spec::L[LI];
+    constexpr int R = Ld.ring_mask + 1;
+    constexpr int C = spec::layer_channels(LI);
+    const float4* a4 = reinterpret_cast<const float4*>(ra + Ld.ring_off);
+    const float4* b4 = reinterpret_cast<const float4*>(rb + Ld.ring_off);
+    float4* s4 = reinterpret_cast<float4*>(sc + 2 * Ld.ring_off);
+    for (int idx = threadIdx.x; idx < (C / 4) * R; idx += NT)
+    {
+      const int pl = idx / R, col = idx - pl * R;
+      const float4 a = __ldcg(a4 + idx), b = __ldcg(b4 + idx);
+      __stcg(s4 + (2 * pl) * R + col, make_float4(a.x, b.x, a.y, b.y));
+      __stcg(s4 + (2 * pl + 1) * R + col, make_float4(a.z, b.z, a.w, b.w));
+    }
+  });
+}
+template <int NT>
+__device__ __forceinline__ void pair_scratch_to_rings(const float* sc, float* ra, float* rb, const bool live_b)
+{
+  static_for<0, spec::NL>([&](auto li_c) {
+    constexpr int LI = decltype(li_c)::value;
+    constexpr spec::Layer Ld = spec::L[LI];
+    constexpr int R = Ld.ring_mask + 1;
+    constexpr int C = spec::layer_channels(LI);
+    float4* a4 = reinterpret_cast<float4*>(ra + Ld.ring_off);
+    float4* b4 = reinterpret_cast<float4*>(rb + Ld.ring_off);
+    const float4* s4 = reinterpret_cast<const float4*>(sc + 2 * Ld.ring_off);
+    for (int idx = threadIdx.x; idx < (C / 4) * R; idx += NT)
+    {
+      const int pl = idx / R, col = idx - pl * R;
+      const float4 q0 = __ldcg(s4 + (2 * pl) * R + col), q1 = __ldcg(s4 + (2 * pl + 1) * R + col);
+      __stcg(a4 + idx, make_float4(q0.x, q0.z, q1.x, q1.z));
+      if (live_b)
+        __stcg(b4 + idx, make_float4(q0.y, q0.w, q1.y, q1.w));
+    }
+  });
+}
+// generic-proxy global accesses <-> the bulk (async-proxy) copies on the scratch
+__device__ __forceinline__ void fence_async_all()
+{
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
 template <int NT, int S, int MINB>
 __device__ __forceinline__ void wavenet_spec_body(const SpecParams& p)
 {
-  constexpr int T = NT * S;
+  constexpr int T = NT; // one frame per thread (of one stream, or of a pair of streams)
   static_assert(spec::NA == 1 || spec::NA == 2, "one or two layer arrays");
-  extern __shared__ float4 spec_smem[]; // [Pmax][W] float4
+  static_assert(S == 1 || S == 2, "one stream per thread, or a packed pair of streams");
+  extern __shared__ float4 spec_smem[]; // [(sub-)planes][W] float4
   __shared__ u64 bar;
   const int tid = threadIdx.x;
   TileCtx c;
@@ -586,12 +637,26 @@ __device__ __forceinline__ void wavenet_spec_body(const SpecParams& p)
   __syncthreads();
 
   typedef typename FrameVec<S>::type V;
-  static_assert(S == 1 || S == 2, "one frame per thread, or a packed pair");
-  for (int stream = blockIdx.x; stream < p.batch; stream += gridDim.x)
+  const int n_units = (S == 1) ? p.batch : (p.batch + 1) / 2; // streams, or pairs of streams
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x)
   {
-    c.state = p.state + (size_t)stream * p.state_stride;
-    const float* xin = p.in + (size_t)stream * p.in_stride;
-    float* yout = p.out + (size_t)stream * p.out_stride;
+    const int sa = S * unit, sb = min(sa + 1, p.batch - 1);
+    const bool live_b = (S == 2) && (sa + 1 < p.batch); // an odd batch leaves the last pair's second half idle
+    float* const state_a = p.state + (size_t)sa * p.state_stride;
+    float* const state_b = p.state + (size_t)sb * p.state_stride;
+    const float* xin_a = p.in + (size_t)sa * p.in_stride;
+    const float* xin_b = p.in + (size_t)sb * p.in_stride;
+    float* yout_a = p.out + (size_t)sa * p.out_stride;
+    float* yout_b = p.out + (size_t)sb * p.out_stride;
+    if constexpr (S == 1)
+      c.state = state_a;
+    else
+    {
+      c.state = p.scratch + (size_t)blockIdx.x * p.scratch_stride;
+      pair_rings_to_scratch<NT>(state_a, state_b, c.state);
+      fence_async_all(); // my scratch stores (generic proxy) -> the bulk loads below
+      __syncthreads();
+    }
     for (int t0 = 0; t0 < p.n_frames; t0 += T)
     {
       c.tv = min(T, p.n_frames - t0);
@@ -599,11 +664,11 @@ __device__ __forceinline__ void wavenet_spec_body(const SpecParams& p)
       request_layer_history<0, NT, S>(c, IntC<spec::A[0].layer0>{});
       V x[1];
       {
-        const float xa = (tid < c.tv) ? __ldg(xin + t0 + tid) : 0.0f;
+        const float xa = (tid < c.tv) ? __ldg(xin_a + t0 + tid) : 0.0f;
         if constexpr (S == 1)
           x[0] = xa;
         else
-          x[0] = pack2(xa, (tid + NT < c.tv) ? __ldg(xin + t0 + tid + NT) : 0.0f);
+          x[0] = pack2(xa, (live_b && tid < c.tv) ? __ldg(xin_b + t0 + tid) : 0.0f);
       }
       const V cond = x[0]; // no condition_dsp: condition == input (model.cpp:781)
       V y;
@@ -635,24 +700,36 @@ __device__ __forceinline__ void wavenet_spec_body(const SpecParams& p)
       if constexpr (S == 1)
       {
         if (tid < c.tv)
-          yout[t0 + tid] = spec::head_scale * y;
+          yout_a[t0 + tid] = spec::head_scale * y;
       }
       else
       {
         float ya, yb;
         unpack2(y, ya, yb);
         if (tid < c.tv)
-          yout[t0 + tid] = spec::head_scale * ya;
-        if (tid + NT < c.tv)
-          yout[t0 + tid + NT] = spec::head_scale * yb;
+        {
+          yout_a[t0 + tid] = spec::head_scale * ya;
+          if (live_b)
+            yout_b[t0 + tid] = spec::head_scale * yb;
+        }
       }
       // (no barrier here: the last layer's B1 already fenced every tap read before anything of the next tile is written)
+    }
+    if constexpr (S == 2)
+    {
+      // every bulk store of the call has completed (each issuing lane waited before the last B1); make them visible to
+      // the generic loads of the conversion, then hand the rings back in the library's layout
+      fence_async_all();
+      __syncthreads();
+      pair_scratch_to_rings<NT>(c.state, state_a, state_b, live_b);
+      __syncthreads(); // the scratch is rewritten for the next pair
     }
   }
 }
 
 } // namespace namb200_spec
 
+#ifndef NAMB200_SPEC_NO_KERNEL // (wavenet_lat.cuh includes this file for its helpers only)
 #ifndef NAMB200_SPEC_NT
 #define NAMB200_SPEC_NT 512
 #endif
@@ -668,3 +745,4 @@ extern "C" __global__ void __launch_bounds__(NAMB200_SPEC_NT, NAMB200_SPEC_MINB)
 {
   namb200_spec::wavenet_spec_body<NAMB200_SPEC_NT, NAMB200_SPEC_S, NAMB200_SPEC_MINB>(p);
 }
+#endif // NAMB200_SPEC_NO_KERNEL

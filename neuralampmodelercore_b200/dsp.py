@@ -174,6 +174,12 @@ class DSP:
         self._refresh_info()
         return int(self._info.jit_state)
 
+    @property
+    def jit_lat_state(self) -> int:
+        """The same for the low-latency kernel (few streams, short calls; built by Reset when jit is 1 or 3)."""
+        self._refresh_info()
+        return int(self._info.jit_lat_state)
+
     def jit_note(self) -> str:
         buf = C.create_string_buffer(4096)
         self._lib.nam_b200_jit_note(self._h, buf, len(buf))

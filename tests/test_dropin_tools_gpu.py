@@ -127,3 +127,19 @@ def test_reference_benchmodel_bufsize_runs_unchanged(tmp_path, bufsize):
     assert r.returncode == 0, r.stdout + r.stderr
     b, us = r.stdout.strip().splitlines()[-1].split(",")
     assert int(b) == bufsize and float(us) > 0.0
+
+
+def test_cpp_host_drives_several_gpus_through_the_c_abi(tmp_path):
+    """tools/nam_b200_multi_test.cpp: nam_b200_multi_* (one worker thread + one complete handle per GPU, the batch dealt out
+    in contiguous shards) reproduces a single-device handle bit for bit.  With one GPU visible the same device is listed
+    twice (two handles, two worker threads on one GPU); with two or more, devices 0 and 1."""
+    import torch
+
+    exe = ROOT / "build" / "nam_b200_multi_test"
+    if not exe.exists():
+        pytest.skip(f"{exe} not built")
+    devs = ["0", "1"] if torch.cuda.device_count() >= 2 else ["0", "0"]
+    r = subprocess.run([str(exe), str(_write_nam(tmp_path, "wavenet_a1_standard")), "600", "2048", *devs],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "bit-identical" in r.stdout, r.stdout

@@ -203,3 +203,72 @@ def test_lstm_spec_refuses_large_cells_loudly():
     d = nb.get_dsp(_random_lstm(16, 1), batch=256)  # default policy: falls back to the lane-group kernel
     assert d.jit_state == -1 and "too large" in d.jit_note()
     d.close()
+
+
+# ---- the low-latency kernel (csrc/wavenet_lat.cuh): few streams, short calls --------------------------------------------
+@pytest.mark.parametrize("fast", [False, True], ids=["exact_tanh", "fast_tanh"])
+def test_lat_kernel_plugin_protocol(fast):
+    """One stream, Reset(sr, 64), 64-frame process() calls (tools/benchmodel.cpp:116-133) on the low-latency kernel."""
+    nam = fx.load_model("wavenet_a1_standard")
+    x = fx.synthetic_batch(1, 64 * 40, seed=21)
+    ref = _oracle_batch(nam, x, fast)
+    d = nb.get_dsp(nam, batch=1, fast_tanh=fast, jit=3)
+    d.Reset(48000.0, 64)
+    assert d.jit_lat_state == 1, d.jit_note()
+    n0 = d.launch_count()
+    got = np.concatenate([d.process_batch(np.ascontiguousarray(x[:, p:p + 64])) for p in range(0, x.shape[1], 64)], axis=1)
+    assert d.launch_count() == n0 + 40
+    d.close()
+    err = float(np.max(np.abs(got - ref)))
+    assert err <= TOL, f"max-abs {err:.3e}"
+
+
+def test_lat_kernel_irregular_short_calls_several_streams_and_mixing():
+    """5 streams; call lengths 1..128 (a 128-frame handle: 4 frame warps), odd lengths, and a long call in between that the
+    precompiled kernels serve on the same rings."""
+    nam = fx.load_model("wavenet_a1_standard")
+    chunks = [64, 1, 17, 128, 63, 100, 2, 127, 64, 33]
+    N = sum(chunks)
+    x = fx.synthetic_batch(5, N, seed=4)
+    ref = _oracle_batch(nam, x, True)
+    d = nb.get_dsp(nam, batch=5, fast_tanh=True, jit=3)
+    d.Reset(48000.0, 128)
+    assert d.jit_lat_state == 1, d.jit_note()
+    out, pos = [], 0
+    for n in chunks:
+        out.append(d.process_batch(np.ascontiguousarray(x[:, pos:pos + n])))
+        pos += n
+    d.close()
+    err = float(np.max(np.abs(np.concatenate(out, axis=1) - ref)))
+    assert err <= TOL, f"max-abs {err:.3e}"
+    # the same handle type with a larger maxBufferSize has no low-latency kernel and still matches
+    d = nb.get_dsp(nam, batch=5, fast_tanh=True, jit=3)
+    d.Reset(48000.0, 512)
+    assert d.jit_lat_state == 0
+    got = np.concatenate([d.process_batch(np.ascontiguousarray(x[:, p:p + 512])) for p in range(0, N, 512)], axis=1)
+    d.close()
+    assert float(np.max(np.abs(got - ref))) <= TOL
+
+
+@pytest.mark.parametrize("case", [
+    dict(channels=(16, 8), kernel_size=3, dilations=[[1, 2, 4, 8, 16, 32, 64], [1, 3, 9, 27, 81, 200]], activation="Tanh"),
+    dict(channels=(8, 4), kernel_sizes=[[2, 3, 4, 5], [5, 1, 3]], dilations=[[1, 7, 13, 64], [2, 5, 128]], activation="ReLU"),
+    dict(channels=(4, 16), kernel_size=3, dilations=[[1, 2], [3, 100, 341]], activation={"type": "PReLU", "negative_slopes": [0.02 * (i + 1) for i in range(16)]}),
+    dict(channels=(12,), kernel_size=3, dilations=[[1, 2, 40]], activation="Sigmoid"),
+], ids=["a1_like", "kernels_1_to_5", "prelu_slices", "single_padded_array"])
+def test_lat_kernel_shape_family(case):
+    act = case.pop("activation")
+    if isinstance(act, dict) and act["type"] == "PReLU":
+        # per-array slope counts differ: use a shared slope list sized for the widest array only where it applies
+        act = {"type": "PReLU", "negative_slopes": [0.05]}
+    nam = fx.random_wavenet(seed=6, activation=act, **case)
+    x = fx.synthetic_batch(3, 64 * 12, seed=2)
+    ref = _oracle_batch(nam, x, False)
+    d = nb.get_dsp(nam, batch=3, jit=3)
+    d.Reset(48000.0, 64)
+    assert d.jit_lat_state == 1, d.jit_note()
+    got = np.concatenate([d.process_batch(np.ascontiguousarray(x[:, p:p + 64])) for p in range(0, x.shape[1], 64)], axis=1)
+    d.close()
+    scale = max(1.0, float(np.max(np.abs(ref))))
+    err = float(np.max(np.abs(got - ref)))
+    assert err <= TOL * scale, f"max-abs {err:.3e}"

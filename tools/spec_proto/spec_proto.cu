@@ -28,7 +28,7 @@ int main(int argc, char** argv)
   int pmax = 0;
   for (int a = 0; a < spec::NA; a++)
     pmax = spec::A[a].C / 4 > pmax ? spec::A[a].C / 4 : pmax;
-  const size_t smem = (size_t)pmax * (spec::LS + NT * S) * 16;
+  const size_t smem = (size_t)pmax * S * (spec::LS + NT) * 16; // S = 2: twice the (sub-)planes
   CK(cudaFuncSetAttribute(wavenet_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wavenet_spec_kernel, NT, smem));
@@ -46,7 +46,10 @@ int main(int argc, char** argv)
   for (size_t i = 0; i < h.size(); i++)
     h[i] = 0.3f * sinf(0.01f * (float)(i % 100003));
   CK(cudaMemcpy(in, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
-  namb200_spec::SpecParams p{state, spec::state_floats, in, out, n, n, batch, n, 0u};
+  float* scratch = nullptr;
+  if (S == 2)
+    CK(cudaMalloc(&scratch, (size_t)grid * 2 * spec::state_floats * 4));
+  namb200_spec::SpecParams p{state, spec::state_floats, in, out, n, n, batch, n, 0u, scratch, 2 * spec::state_floats};
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
