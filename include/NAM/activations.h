@@ -19,8 +19,10 @@ public:
   static void enable_fast_tanh();
   static void disable_fast_tanh();
   static bool using_fast_tanh;
-  /// The reference can swap Tanh/Sigmoid/SiLU for an interpolated lookup table.  The CUDA path has no LUT
-  /// mode (it would be slower than the arithmetic on a GPU): these throw std::runtime_error.
+  /// The reference can swap Tanh/Sigmoid/SiLU for an interpolated lookup table (NAM/activations.h:371-422), which CHANGES
+  /// the arithmetic.  The CUDA path has no LUT mode (a table lookup is slower than the arithmetic on a GPU, and silently
+  /// computing the exact function instead would not be the reference's output): enable_lut throws std::runtime_error,
+  /// disable_lut is a no-op (tests/test_host_logic.py::test_lut_switch_is_refused_loudly).
   static void enable_lut(std::string function_name, float min, float max, std::size_t n_points);
   static void disable_lut(std::string function_name);
 };

@@ -1,5 +1,8 @@
 #include "json_lite.h"
 
+#include <charconv>
+#include <cmath>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -9,6 +12,20 @@ namespace namb200
 {
 namespace json
 {
+
+// Shortest round-trip decimal of a double, locale-independent (std::to_chars); non-finite values as the tokens the parser
+// accepts (NaN, Infinity, -Infinity) so that a document survives dump() -> parse().
+std::string number_to_string(double v)
+{
+  if (std::isnan(v))
+    return "NaN";
+  if (std::isinf(v))
+    return v < 0 ? "-Infinity" : "Infinity";
+  char buf[64];
+  const auto res = std::to_chars(buf, buf + sizeof buf, v);
+  return std::string(buf, res.ptr);
+}
+
 
 namespace
 {
@@ -179,9 +196,21 @@ private:
     if (_i == start)
       fail("expected a value");
     const std::string tok(_s + start, _i - start);
-    char* end = nullptr;
-    const double d = std::strtod(tok.c_str(), &end);
-    if (end == tok.c_str() || *end != '\0')
+    // std::from_chars: locale-independent (strtod reads "0,5" in a decimal-comma locale, and a DAW host may well have
+    // called setlocale); nlohmann::json, the reference's parser, is locale-independent too
+    double d = 0.0;
+    const char* first = tok.c_str() + ((tok[0] == '+') ? 1 : 0);
+    const auto res = std::from_chars(first, tok.c_str() + tok.size(), d);
+    if (res.ec == std::errc::result_out_of_range && res.ptr == tok.c_str() + tok.size())
+    {
+      // beyond double's range: underflow to zero / overflow to infinity, like strtod and nlohmann::json
+      const size_t e = tok.find_first_of("eE");
+      const bool tiny = e != std::string::npos && e + 1 < tok.size() && tok[e + 1] == '-';
+      d = tiny ? 0.0 : INFINITY;
+      if (tok[0] == '-')
+        d = -d;
+    }
+    else if (res.ec != std::errc() || res.ptr != tok.c_str() + tok.size())
       fail("malformed number '" + tok + "'");
     Value v;
     v._type = Value::Type::Number;
@@ -339,9 +368,7 @@ void dump_value(const Value& v, std::string& out)
     case Value::Type::Bool: out += v.as_bool() ? "true" : "false"; break;
     case Value::Type::Number:
     {
-      char buf[40];
-      std::snprintf(buf, sizeof(buf), "%.17g", v.as_double());
-      out += buf;
+      out += number_to_string(v.as_double());
       break;
     }
     case Value::Type::String: dump_string(v.as_string(), out); break;

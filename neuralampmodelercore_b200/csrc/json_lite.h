@@ -17,6 +17,10 @@ namespace namb200
 namespace json
 {
 
+/// Shortest round-trip decimal, locale-independent; NaN / Infinity / -Infinity for non-finite values.
+std::string number_to_string(double v);
+
+
 class ParseError : public std::runtime_error
 {
 public:

@@ -365,6 +365,8 @@ struct nam_b200_model
   int64_t launches = 0;
   int max_frames = 0;
   bool is_reset = false;
+  bool streams_identical = true; // every stream holds the same state (true after init_state, false once audio was processed)
+  bool state_initialised = false; // init_state() has run at least once
   uint32_t t_base = 0;
   int fast_tanh_runtime = 0;
 
@@ -1390,6 +1392,7 @@ void run_device(nam_b200_model* m, const float* d_in, float* d_out, int batch, i
     default: throw std::runtime_error("no kernel for this architecture");
   }
   m->t_base += (uint32_t)n_frames;
+  m->streams_identical = false; // (prewarm() restores the flag: it feeds every stream the same zeros)
 }
 
 void ensure_staging(nam_b200_model* m, size_t floats)
@@ -1445,6 +1448,8 @@ void init_state(nam_b200_model* m)
   if (m->spec.arch == Arch::Linear && m->d_state_tmp)
     CUDA_CHECK(cudaMemsetAsync(m->d_state_tmp, 0, total * sizeof(float), m->stream));
   m->t_base = 0;
+  m->streams_identical = true;
+  m->state_initialised = true;
 }
 
 void broadcast_state(nam_b200_model* m)
@@ -1470,14 +1475,21 @@ void prewarm(nam_b200_model* m)
   const int bs = std::max(m->max_frames, 1);
   const size_t ci = (size_t)m->spec.in_channels, co = (size_t)m->spec.out_channels;
   ensure_staging(m, (size_t)m->opts.max_batch * bs * std::max(ci, co));
-  CUDA_CHECK(cudaMemsetAsync(m->d_in, 0, (size_t)bs * ci * sizeof(float), m->stream));
+  // DSP::prewarm continues from the instance's CURRENT state (dsp.cpp:67-101).  Straight after init_state every stream
+  // would compute the same thing: stream 0 runs, its state is broadcast.  Once the streams have seen different audio
+  // (a standalone nam_b200_prewarm, or a Reset of an LSTM, which keeps its running state) all of them are prewarmed.
+  const int nb = m->streams_identical ? 1 : m->opts.max_batch;
+  CUDA_CHECK(cudaMemsetAsync(m->d_in, 0, (size_t)nb * bs * ci * sizeof(float), m->stream));
+  const bool identical = m->streams_identical;
   int done = 0;
   while (done < ps)
   {
-    run_device(m, m->d_in, m->d_out, 1, bs, (long)(bs * ci), (long)(bs * co), m->stream);
+    run_device(m, m->d_in, m->d_out, nb, bs, (long)(bs * ci), (long)(bs * co), m->stream);
     done += bs;
   }
-  broadcast_state(m);
+  m->streams_identical = identical; // zeros into identical streams keep them identical
+  if (identical)
+    broadcast_state(m);
   if (m->spec.arch == Arch::Linear && m->d_state_tmp)
     CUDA_CHECK(cudaMemcpyAsync(m->d_state_tmp, m->d_state, (size_t)m->state_stride * m->opts.max_batch * sizeof(float),
                                cudaMemcpyDeviceToDevice, m->stream));
@@ -2169,7 +2181,11 @@ int nam_b200_reset(nam_b200_model* m, double sample_rate, int max_frames)
     ensure_pinned(m, (size_t)2 * max_frames * ch);
     ensure_hist(m);
     setup_lat_kernel(m);
-    init_state(m);
+    // DSP::Reset = SetMaxBufferSize + prewarm (dsp.cpp:130-140).  WaveNet / ConvNet / Linear clear their buffers in
+    // SetMaxBufferSize (RingBuffer::Reset, Buffer::_reset_input_buffer); the reference's LSTM overrides neither, so its
+    // hidden and cell state SURVIVE a Reset and only the prewarm runs on top of it: a second Reset keeps the state here too.
+    if (!(m->spec.arch == Arch::LSTM && m->state_initialised))
+      init_state(m);
     m->is_reset = true;
     CUDA_CHECK(cudaEventRecord(m->ev0, m->stream));
     if (m->opts.prewarm_on_reset)
@@ -2260,6 +2276,7 @@ int nam_b200_process_f32(nam_b200_model* m, const float* in, float* out, int bat
                                      (size_t)nb, cudaMemcpyDeviceToHost, m->copy_out));
       }
       m->t_base += (uint32_t)n_frames;
+      m->streams_identical = false;
       CUDA_CHECK(cudaEventRecord(m->ev1, m->stream));
       CUDA_CHECK(cudaStreamSynchronize(m->copy_out));
       CUDA_CHECK(cudaStreamSynchronize(m->stream));

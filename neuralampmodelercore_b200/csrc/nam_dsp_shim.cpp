@@ -47,9 +47,9 @@ void nam::activations::Activation::enable_lut(std::string function_name, float, 
 {
   throw std::runtime_error("LUT activations (" + function_name + ") are not available on the CUDA path");
 }
-void nam::activations::Activation::disable_lut(std::string function_name)
+void nam::activations::Activation::disable_lut(std::string)
 {
-  throw std::runtime_error("LUT activations (" + function_name + ") are not available on the CUDA path");
+  // enable_lut never succeeds here, so there is nothing to restore (the reference puts the original activation back)
 }
 
 // ---- ScopedPrewarmOnResetDefault / DSP base -------------------------------------------------------

@@ -574,6 +574,21 @@ void build_linear(ModelSpec& ms, const json::Value& config, const std::vector<fl
   LinearSpec& li = ms.linear;
   li.receptive_field = config.at("receptive_field").as_int("receptive_field");
   li.bias = config.at("bias").as_bool("bias");
+  // "implementation" (linear.cpp:280-293): auto / direct / fft pick HOW the reference evaluates the same FIR (direct form
+  // or partitioned FFT above 256 taps); the result is the same, and the CUDA path always runs direct form.  Unknown
+  // names are rejected like the reference does.
+  if (config.contains("implementation"))
+  {
+    std::string impl = config.at("implementation").as_string("implementation");
+    for (char& ch : impl)
+      ch = (char)std::tolower((unsigned char)ch);
+    static const char* known[] = {"auto", "direct", "legacy", "old", "fft", "partitioned_fft", "partitioned-fft"};
+    bool ok = false;
+    for (const char* k : known)
+      ok = ok || impl == k;
+    if (!ok)
+      throw std::runtime_error("Unsupported Linear implementation: " + config.at("implementation").as_string("implementation"));
+  }
   ms.in_channels = config.value_int("in_channels", 1);
   ms.out_channels = config.value_int("out_channels", 1);
   if (li.receptive_field <= 0)
@@ -778,9 +793,7 @@ std::vector<float> slice_wavenet_weights(const WaveNetSpec& wn, const std::vecto
 
 std::string json_number(double v)
 {
-  char buf[40];
-  std::snprintf(buf, sizeof(buf), "%.17g", v);
-  return buf;
+  return json::number_to_string(v); // locale-independent
 }
 
 // one layer-array config with its channel counts replaced and "slimmable" cleared (modify_params_for_channels,
@@ -944,9 +957,7 @@ void build_slimmable_wavenet(ModelSpec& ms, const json::Value& root, const json:
     doc += "\"config\": " + cfg + ", \"weights\": [";
     for (size_t i = 0; i < w.size(); i++)
     {
-      char buf[32];
-      std::snprintf(buf, sizeof(buf), "%s%.9g", i ? ", " : "", (double)w[i]);
-      doc += buf;
+      doc += (i ? ", " : "") + json::number_to_string((double)w[i]); // exact and locale-independent
     }
     doc += "]}";
     sm.model_json = std::move(doc);

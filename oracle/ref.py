@@ -53,6 +53,8 @@ def _load(variant: str) -> C.CDLL:
         lib.namref_run_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int]
         lib.namref_process_planar_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.namref_set_slimmable_size.argtypes = [C.c_void_p, C.c_double]
+        if hasattr(lib, "namref_prewarm"):
+            lib.namref_prewarm.argtypes = [C.c_void_p]
         for name in ("prewarm_samples", "in_channels", "out_channels"):
             getattr(lib, f"namref_{name}").argtypes = [C.c_void_p]
         lib.namref_expected_sample_rate.argtypes = [C.c_void_p]
@@ -108,6 +110,11 @@ class ReferenceModel:
 
     def reset(self, sample_rate: float, max_buffer_size: int) -> None:
         if self._lib.namref_reset(self._h, float(sample_rate), int(max_buffer_size)) != 0:
+            raise ReferenceError_(self._lib.namref_last_error().decode(errors="replace"))
+
+    def prewarm(self) -> None:
+        """DSP::prewarm() from the current state."""
+        if self._lib.namref_prewarm(self._h) != 0:
             raise ReferenceError_(self._lib.namref_last_error().decode(errors="replace"))
 
     def set_slimmable_size(self, value: float) -> None:

@@ -78,6 +78,21 @@ int namref_reset(void* p, double sample_rate, int max_buffer_size)
   }
 }
 
+// DSP::prewarm() on its own: continues from the instance's current state (NAM/dsp.cpp:67-101)
+int namref_prewarm(void* p)
+{
+  try
+  {
+    static_cast<Handle*>(p)->dsp->prewarm();
+    return 0;
+  }
+  catch (const std::exception& e)
+  {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 int namref_prewarm_samples(void* p)
 {
   return static_cast<Handle*>(p)->dsp->GetPrewarmSamples();

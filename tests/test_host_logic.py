@@ -207,3 +207,48 @@ def test_convnet_and_slimmable_wavenet_loaders():
     bad["config"]["layers"][0]["slimmable"]["method"] = "magic"
     with pytest.raises(RuntimeError, match="unsupported slimmable method"):
         nb.inspect(bad)
+
+
+def test_lut_switch_is_refused_loudly(tmp_path):
+    """NAM/activations.h:371-422 / activations.cpp:179-232: enable_lut swaps an activation for an interpolated table,
+    i.e. different arithmetic.  The CUDA path has no such mode: the drop-in header's enable_lut must throw (not silently
+    keep the exact function), disable_lut must be harmless.  Host-only: no kernel is launched."""
+    import subprocess
+
+    from neuralampmodelercore_b200 import _build
+
+    src = tmp_path / "lut.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <stdexcept>
+#include "NAM/activations.h"
+int main() {
+  nam::activations::Activation::disable_lut("Tanh");   // nothing to restore: must not throw
+  try { nam::activations::Activation::enable_lut("Tanh", -5.0f, 5.0f, 4096); }
+  catch (const std::runtime_error& e) { std::printf("refused: %s\n", e.what()); return 0; }
+  std::printf("enable_lut did not throw\n");
+  return 1;
+}
+''')
+    exe = tmp_path / "lut"
+    nb.build()
+    subprocess.run(["g++", "-std=c++17", f"-I{_build.INCLUDE}", "-o", str(exe), str(src), f"-L{_build.LIB_DIR}", "-lnam_b200",
+                    f"-Wl,-rpath,{_build.LIB_DIR}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "refused" in r.stdout and "Tanh" in r.stdout, r.stdout + r.stderr
+
+
+def test_linear_implementation_key_is_parsed_like_the_reference():
+    """NAM/linear.cpp:280-293,306-316: "implementation" chooses how the reference evaluates the FIR; the CUDA path runs
+    direct form for every value the reference accepts and rejects what it rejects."""
+    base = {"version": "0.5.4", "architecture": "Linear", "sample_rate": 48000,
+            "config": {"receptive_field": 300, "bias": True}, "weights": [0.001 * i for i in range(301)]}
+    for impl in ("auto", "direct", "FFT", "partitioned_fft", "legacy"):
+        nam = json.loads(json.dumps(base))
+        nam["config"]["implementation"] = impl
+        rep = nb.inspect(nam)
+        assert rep["architecture"] == "Linear" and rep["kernel"] == "linear", rep
+    nam = json.loads(json.dumps(base))
+    nam["config"]["implementation"] = "winograd"
+    with pytest.raises(Exception, match="Unsupported Linear implementation"):
+        nb.inspect(nam)

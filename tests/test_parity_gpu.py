@@ -247,6 +247,25 @@ def test_linear_direct():
     assert np.max(np.abs(got - ref)) <= TOL
 
 
+def test_linear_long_filter_with_fft_config_runs_direct_form():
+    """A Linear with more than 256 taps and "implementation": "fft" (NAM/linear.cpp:99-113,201-278): the reference would
+    evaluate it by partitioned FFT; the CUDA path's direct form gives the same filter output."""
+    rng = np.random.default_rng(12)
+    rf = 600
+    nam = {"version": "0.5.4", "architecture": "Linear", "sample_rate": 48000,
+           "config": {"receptive_field": rf, "bias": True, "implementation": "fft"},
+           "weights": [float(v) for v in rng.uniform(-0.05, 0.05, rf + 1)]}
+    x = fx.synthetic_batch(3, 3000, seed=5)
+    proto = oracle.OracleModel.from_dict(nam)
+    proto.reset(48000.0, 512)
+    ref = proto.run_batch(x, 512)
+    d = nb.get_dsp(nam, batch=3)
+    d.Reset(48000.0, 1024)
+    got = np.concatenate([d.process_batch(np.ascontiguousarray(x[:, p:p + 1024])) for p in range(0, 3000, 1024)], axis=1)
+    d.close()
+    assert float(np.max(np.abs(got - ref))) <= TOL
+
+
 def test_full_size_linearity_free_properties():
     """BASELINE-size check without the (slow) oracle: B=4096 streams x 4096 frames.
     Properties: (i) identical inputs -> bit-identical outputs across streams and across CTAs;

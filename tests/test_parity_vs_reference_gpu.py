@@ -73,3 +73,34 @@ def test_container_matches_the_reference():
         y = np.concatenate([d.process_batch(np.ascontiguousarray(x[None, p:p + 1000]))[0] for p in range(0, 3000, 1000)])
         d.close()
         assert float(np.max(np.abs(y - yr))) <= TOL, f"slim {slim}"
+
+
+def test_second_reset_and_standalone_prewarm_follow_the_reference():
+    """DSP::Reset = SetMaxBufferSize + prewarm (NAM/dsp.cpp:130-140).  The reference's LSTM overrides neither Reset nor
+    SetMaxBufferSize, so its hidden / cell state survives a Reset and only the prewarm runs on top of it; the WaveNet's
+    ring buffers are cleared.  Audio, Reset, audio again -- and a standalone prewarm() in the middle of a stream -- against the
+    reference build doing the same."""
+    x = fx.synthetic_batch(1, 3 * 1024, seed=17)[0]
+    for name in ("lstm", "wavenet"):
+        nam = fx.load_model(name)
+        r = ref.ReferenceModel.from_dict(nam, fast_tanh=False)
+        d = nb.get_dsp(nam, batch=3, fast_tanh=False)
+        r.reset(48000.0, 64)
+        d.Reset(48000.0, 64)
+        want, got = [], []
+        for part in range(3):
+            seg = x[part * 1024:(part + 1) * 1024]
+            want.append(r.run(seg, 64))
+            # three streams with different gains: they diverge, so the later prewarms must run on every stream
+            xb = np.ascontiguousarray(np.stack([seg, 0.5 * seg, -seg]))
+            got.append(np.concatenate([d.process_batch(np.ascontiguousarray(xb[:, p:p + 64])) for p in range(0, 1024, 64)], axis=1)[0])
+            if part == 0:
+                r.reset(48000.0, 64)
+                d.Reset(48000.0, 64)
+            elif part == 1:
+                r.prewarm()
+                d.prewarm()
+        r.close()
+        d.close()
+        err = float(np.max(np.abs(np.concatenate(got) - np.concatenate(want))))
+        assert err <= TOL, f"{name}: {err:.3e}"

@@ -266,3 +266,24 @@ def test_slimmable_wavenet_slicing(case):
         o.close()
         assert _rel(float(np.max(np.abs(yr - yo))), yr) <= TOL, f"{label}: ratio {val} -> sub-model {idx}"
     r0.close()
+
+
+@pytest.mark.parametrize("impl", ["direct", "fft", "auto"])
+def test_linear_fft_and_direct_form_are_the_same_filter(impl):
+    """NAM/linear.cpp:99-113,201-278: above 256 taps the reference's Linear switches ("auto") or can be told ("fft") to a
+    partitioned-FFT evaluation of the same FIR.  The product runs direct form at any length, so the two
+    must agree: the reference build with each implementation against the oracle's direct form."""
+    rng = np.random.default_rng(12)
+    rf = 600
+    nam = {"version": "0.5.4", "architecture": "Linear", "sample_rate": 48000,
+           "config": {"receptive_field": rf, "bias": True, "implementation": impl},
+           "weights": [float(v) for v in rng.uniform(-0.05, 0.05, rf + 1)]}
+    x = fx.synthetic_batch(1, 3000, seed=5)[0]
+    m = oracle.OracleModel.from_dict(nam)
+    m.reset(48000.0, 64)
+    want = m.run(x, 64)
+    r = ref.ReferenceModel.from_dict(nam)
+    r.reset(48000.0, 64)
+    got = r.run(x, 64)
+    r.close()
+    assert float(np.max(np.abs(got - want))) <= 2e-6
