@@ -209,6 +209,154 @@ __device__ __forceinline__ void lstm_spec_body(const LstmSpecParams& p)
   }
 }
 
+// ---- gate-split variant: FOUR lanes per stream, lane q = gate q (i, f, g, o) ----------------------------------------------
+// One thread per stream issues ~290 instructions per step from a single warp per scheduler (542 cycles measured for
+// lstm.nam); the step's dependent chain is only ~150.  Here lane q of a group of four computes gate q's H
+// pre-activations (its rows of W in registers: the rows differ per lane, so they cannot be immediates) and their
+// activation; the 4H activated values are exchanged by shuffles and every lane updates (c, h) of all units redundantly,
+// so nothing has to be broadcast back: ~115 instructions per lane per step, 8 streams per warp.
+template <bool FAST>
+__device__ __forceinline__ void lstm_gate_split_body(const LstmSpecParams& p)
+{
+  constexpr int H = spec::H, L = spec::L, I = spec::I;
+  static_assert(I == 1, "mono models");
+  constexpr int SPW = 8; // streams per warp
+  __shared__ float sin_[SPW][kTile + 1];
+  __shared__ float sout[SPW][kTile + 1];
+  const int lane = threadIdx.x;
+  const int q = lane & 3, grp = lane >> 2;
+  const int stream0 = blockIdx.x * SPW;
+  const int stream = stream0 + grp;
+  const bool live = stream < p.batch;
+  const unsigned base_lane = (unsigned)(lane & ~3);
+
+  // my gate's rows: W[q*H + u][0 .. I+H) and b[q*H + u].  Fast regime: the 0.5 z of the sigmoid gates is folded in.
+  const float sc = (FAST && q != 2) ? 0.5f : 1.0f;
+  float wx[L][H], wh[L][H][H], wb[L][H];
+#pragma unroll
+  for (int l = 0; l < L; l++)
+  {
+    const int Il = (l == 0) ? I : H, W = Il + H;
+    const int w0 = layer_offset(l), b0 = w0 + 4 * H * W;
+#pragma unroll
+    for (int u = 0; u < H; u++)
+    {
+      // (layer 0: one input column; deeper layers: H input columns, kept in wh2 below)
+      wx[l][u] = (l == 0) ? sc * spec::w(w0 + (q * H + u) * W) : 0.0f;
+#pragma unroll
+      for (int j = 0; j < H; j++)
+        wh[l][u][j] = sc * spec::w(w0 + (q * H + u) * W + Il + j);
+      wb[l][u] = sc * spec::w(b0 + q * H + u);
+    }
+  }
+  float wi[L > 1 ? L - 1 : 1][H][H]; // input part of layers 1.. (their input is the previous layer's h)
+#pragma unroll
+  for (int l = 1; l < L; l++)
+  {
+    const int W = 2 * H, w0 = layer_offset(l);
+#pragma unroll
+    for (int u = 0; u < H; u++)
+#pragma unroll
+      for (int j = 0; j < H; j++)
+        wi[l - 1][u][j] = sc * spec::w(w0 + (q * H + u) * W + j);
+  }
+  // post-activation map: tanh gate t -> t; sigmoid gates (fast regime) t -> 0.5 t + 0.5
+  const float ka = (FAST && q != 2) ? 0.5f : 1.0f, kb = (FAST && q != 2) ? 0.5f : 0.0f;
+
+  float h[L][H], c[L][H];
+#pragma unroll
+  for (int l = 0; l < L; l++)
+#pragma unroll
+    for (int u = 0; u < H; u++)
+    {
+      const float* st = p.state + (size_t)min(stream, p.batch - 1) * p.state_stride + l * 2 * H;
+      h[l][u] = st[u];
+      c[l][u] = st[H + u];
+    }
+
+  for (int t0 = 0; t0 < p.n_frames; t0 += kTile)
+  {
+    const int tc = min(kTile, p.n_frames - t0);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < SPW; r++)
+    {
+      const int s = stream0 + r;
+      sin_[r][lane] = (s < p.batch && t0 + lane < p.n_frames) ? __ldg(p.in + (size_t)s * p.in_stride + t0 + lane) : 0.0f;
+    }
+    __syncwarp();
+    for (int f = 0; f < tc; f++)
+    {
+      const float x = sin_[grp][f];
+#pragma unroll
+      for (int l = 0; l < L; l++)
+      {
+        // my gate's H pre-activations (lstm.cpp:36-40; input part first, then the recurrent part, then the bias)
+        float g[H];
+#pragma unroll
+        for (int u = 0; u < H; u++)
+        {
+          float a = 0.0f;
+          if (l == 0)
+            a = fmaf(wx[0][u], x, a);
+          else
+          {
+#pragma unroll
+            for (int j = 0; j < H; j++)
+              a = fmaf(wi[l > 0 ? l - 1 : 0][u][j], h[l > 0 ? l - 1 : 0][j], a);
+          }
+#pragma unroll
+          for (int j = 0; j < H; j++)
+            a = fmaf(wh[l][u][j], h[l][j], a);
+          a += wb[l][u];
+          if constexpr (FAST)
+            g[u] = fmaf(ka, fast_tanh(a), kb);
+          else
+            g[u] = (q == 2) ? tanhf(a) : sig<false>(a);
+        }
+        // everybody gets all four gates of every unit, then updates (c, h) of all units
+#pragma unroll
+        for (int u = 0; u < H; u++)
+        {
+          const float gi = __shfl_sync(0xffffffffu, g[u], base_lane + 0), gf = __shfl_sync(0xffffffffu, g[u], base_lane + 1);
+          const float gg = __shfl_sync(0xffffffffu, g[u], base_lane + 2), go = __shfl_sync(0xffffffffu, g[u], base_lane + 3);
+          const float cn = gf * c[l][u] + gi * gg; // lstm.cpp:50-53,61-63
+          c[l][u] = cn;
+          h[l][u] = go * tnh<FAST>(cn); // :55-57,65-66
+        }
+      }
+      // head (lstm.cpp:164-167)
+      constexpr int hw = layer_offset(L);
+      float y = 0.0f;
+#pragma unroll
+      for (int j = 0; j < H; j++)
+        y = fmaf(spec::w(hw + j), h[L - 1][j], y);
+      if (q == 0)
+        sout[grp][f] = y + spec::w(hw + H);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < SPW; r++)
+    {
+      const int s = stream0 + r;
+      if (s < p.batch && lane < tc)
+        p.out[(size_t)s * p.out_stride + t0 + lane] = sout[r][lane];
+    }
+  }
+  if (live && q == 0)
+  {
+#pragma unroll
+    for (int l = 0; l < L; l++)
+#pragma unroll
+      for (int u = 0; u < H; u++)
+      {
+        float* st = p.state + (size_t)stream * p.state_stride + l * 2 * H;
+        st[u] = h[l][u];
+        st[H + u] = c[l][u];
+      }
+  }
+}
+
 } // namespace namb200_lstm_spec
 
 extern "C" __global__ void __launch_bounds__(32) lstm_spec_kernel_exact(const __grid_constant__ namb200_lstm_spec::LstmSpecParams p)
@@ -218,4 +366,13 @@ extern "C" __global__ void __launch_bounds__(32) lstm_spec_kernel_exact(const __
 extern "C" __global__ void __launch_bounds__(32) lstm_spec_kernel_fast(const __grid_constant__ namb200_lstm_spec::LstmSpecParams p)
 {
   namb200_lstm_spec::lstm_spec_body<true>(p);
+}
+// gate-split variants: 8 streams per 32-thread CTA
+extern "C" __global__ void __launch_bounds__(32) lstm_spec_gates_kernel_exact(const __grid_constant__ namb200_lstm_spec::LstmSpecParams p)
+{
+  namb200_lstm_spec::lstm_gate_split_body<false>(p);
+}
+extern "C" __global__ void __launch_bounds__(32) lstm_spec_gates_kernel_fast(const __grid_constant__ namb200_lstm_spec::LstmSpecParams p)
+{
+  namb200_lstm_spec::lstm_gate_split_body<true>(p);
 }

@@ -386,6 +386,7 @@ struct nam_b200_model
   cudaLibrary_t spec_lib = nullptr;
   cudaKernel_t spec_kernel = nullptr;
   cudaKernel_t lstm_spec_kernels[2] = {nullptr, nullptr}; // lstm_spec.cuh: exact / fast activation regime
+  cudaKernel_t lstm_gate_kernels[2] = {nullptr, nullptr}; // its gate-split variant (four lanes per stream)
   // low-latency kernel (wavenet_lat.cuh): few streams x short calls; built by reset() for the handle's maxBufferSize
   cudaLibrary_t lat_lib = nullptr;
   cudaKernel_t lat_kernel = nullptr;
@@ -1111,7 +1112,11 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
   }
   const size_t smem = wavenet_smem_bytes(plan, geom);
   if (m->wn_ctas_per_sm <= 0)
-    m->wn_ctas_per_sm = m->opts.ctas_per_sm > 0 ? m->opts.ctas_per_sm : occupancy_wavenet_dispatch(c0, c1, geom, smem);
+  {
+    const int occ = occupancy_wavenet_dispatch(c0, c1, geom, smem);
+    // (a user value above the real occupancy would overstate co-residency for the spin-waiting tile-parallel launches)
+    m->wn_ctas_per_sm = m->opts.ctas_per_sm > 0 ? std::min(m->opts.ctas_per_sm, std::max(occ, 1)) : occ;
+  }
   const int per_sm = m->wn_ctas_per_sm;
   // Few streams, long calls, lock-step: one CTA per (stream, tile), all tiles advancing layer by layer together
   // (WaveNetKernelParams::hist).  All CTAs must be co-resident.
@@ -1213,6 +1218,8 @@ void setup_lstm_spec_kernel(nam_b200_model* m)
     check(cudaLibraryLoadData(&m->spec_lib, b.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0), "cudaLibraryLoadData");
     check(cudaLibraryGetKernel(&m->lstm_spec_kernels[0], m->spec_lib, "lstm_spec_kernel_exact"), "cudaLibraryGetKernel");
     check(cudaLibraryGetKernel(&m->lstm_spec_kernels[1], m->spec_lib, "lstm_spec_kernel_fast"), "cudaLibraryGetKernel");
+    check(cudaLibraryGetKernel(&m->lstm_gate_kernels[0], m->spec_lib, "lstm_spec_gates_kernel_exact"), "cudaLibraryGetKernel");
+    check(cudaLibraryGetKernel(&m->lstm_gate_kernels[1], m->spec_lib, "lstm_spec_gates_kernel_fast"), "cudaLibraryGetKernel");
     m->spec_state = 1;
     m->spec_note = b.from_cache ? "cubin from cache" : "compiled in " + std::to_string(b.compile_seconds) + " s";
   }
@@ -1233,11 +1240,20 @@ void launch_lstm(nam_b200_model* m, const float* d_in, float* d_out, int batch, 
 {
   if (m->spec_state == 1)
   {
-    // one thread per stream, one warp per CTA (lstm_spec.cuh)
     LstmSpecKernelParams sp{m->d_state, m->state_stride, d_in, d_out, in_stride, out_stride, batch, n_frames};
     void* args[] = {&sp};
-    CUDA_CHECK(cudaLaunchKernel((const void*)m->lstm_spec_kernels[m->fast_tanh_runtime ? 1 : 0], dim3((batch + 31) / 32), dim3(32),
-                                args, 0, st));
+    // The step rate is bound by one warp's instruction stream as long as every warp has a scheduler to itself: four
+    // lanes per stream (gate-split, 8 streams per warp: 155 ns per step for lstm.nam) while every warp still gets a
+    // scheduler of its own (4 x SMs), else one thread per stream (32 per warp, 284 ns per step; measured at 16,384
+    // streams: 57.7 against 46.7 Gsamples/s).  kernel_geometry 1 / 2 pins one of them.
+    const bool gates = m->spec.lstm.hidden >= 2
+                       && (m->opts.kernel_geometry == 1 || (m->opts.kernel_geometry != 2 && (batch + 7) / 8 <= 4 * m->sm_count));
+    if (gates)
+      CUDA_CHECK(cudaLaunchKernel((const void*)m->lstm_gate_kernels[m->fast_tanh_runtime ? 1 : 0], dim3((batch + 7) / 8), dim3(32),
+                                  args, 0, st));
+    else
+      CUDA_CHECK(cudaLaunchKernel((const void*)m->lstm_spec_kernels[m->fast_tanh_runtime ? 1 : 0], dim3((batch + 31) / 32),
+                                  dim3(32), args, 0, st));
     m->launches++;
     return;
   }
@@ -1323,6 +1339,8 @@ void launch_linear(nam_b200_model* m, const float* d_in, float* d_out, int batch
   ensure_max_dynamic_smem(reinterpret_cast<const void*>(linear_kernel), m->device, 227 * 1024);
   if (smem > 227 * 1024)
     throw std::runtime_error("Linear receptive field too long for the direct-form kernel");
+  if (batch > 65535)
+    throw std::runtime_error("Linear: more than 65535 streams per call (grid.y); split the batch");
   dim3 grid((n_frames + kLinThreads - 1) / kLinThreads, batch);
   linear_kernel<<<grid, kLinThreads, smem, st>>>(kp);
   CUDA_CHECK(cudaGetLastError());
@@ -1578,6 +1596,13 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
         {
           m->plan.eligible = false;
           m->plan.why_not = "multi-channel in / out";
+        }
+        if (m->plan.eligible && m->opts.kernel_geometry != 3
+            && wavenet_smem_bytes(m->plan, m->opts.kernel_geometry == 1 ? 0 : 1) > 227 * 1024)
+        {
+          // e.g. > ~50 layers of 16 channels: the general kernel keeps such weights in global memory
+          m->plan.eligible = false;
+          m->plan.why_not = "packed weights + tile exceed the 227 KB of shared memory of the fused kernel";
         }
         if (!m->plan.eligible || m->opts.kernel_geometry == 4)
         {

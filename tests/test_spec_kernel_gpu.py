@@ -168,7 +168,12 @@ def test_lstm_spec_example_model_both_regimes_and_runtime_switch():
     switch is read at run time like the reference (lstm.cpp:48): one handle, both kernels of the cubin."""
     nam = fx.load_model("lstm")
     x = fx.synthetic_batch(70, 1999, seed=9)
-    d = nb.get_dsp(nam, batch=70, fast_tanh=False, jit=1)
+    for geometry in (1, 2):
+        _lstm_example_both_regimes(nam, x, geometry)
+
+
+def _lstm_example_both_regimes(nam, x, geometry):
+    d = nb.get_dsp(nam, batch=70, fast_tanh=False, jit=1, kernel_geometry=geometry)
     assert d.jit_state == 1, d.jit_note()
     for fast in (False, True):
         proto = oracle.OracleModel.from_dict(nam, fast_tanh=fast)
@@ -182,14 +187,16 @@ def test_lstm_spec_example_model_both_regimes_and_runtime_switch():
     d.close()
 
 
+@pytest.mark.parametrize("geometry", [1, 2], ids=["gate_split", "thread_per_stream"])
 @pytest.mark.parametrize("H,nl", [(1, 1), (3, 1), (3, 3), (5, 2), (8, 1)])
-def test_lstm_spec_random_cells(H, nl):
+def test_lstm_spec_random_cells(H, nl, geometry):
+    """Both mappings of lstm_spec.cuh: four lanes per stream (lane = gate, kernel_geometry 1) and one thread per stream (2)."""
     nam = _random_lstm(H, nl)
     x = fx.synthetic_batch(37, 1000, seed=1)
     proto = oracle.OracleModel.from_dict(nam)
     proto.reset(48000.0, 256)
     ref = proto.run_batch(x, 256)
-    d = nb.get_dsp(nam, batch=37, jit=1)
+    d = nb.get_dsp(nam, batch=37, jit=1, kernel_geometry=geometry)
     assert d.jit_state == 1, d.jit_note()
     d.Reset(48000.0, 256)
     got = np.concatenate([d.process_batch(np.ascontiguousarray(x[:, p:p + c])) for p, c in ((0, 1), (1, 31), (32, 256), (288, 33), (321, 256), (577, 256), (833, 167))], axis=1)
