@@ -542,17 +542,21 @@ def run_b200(args) -> None:
         quick("wavenet_a1_standard_batch4096_128frame_calls", MODEL, 4096, 128, steps=32)
         quick("a2_full_batch4096", "a2_full", 4096, 4096, steps=4)
         quick("lstm_batch4096", "lstm", 4096, 4096, steps=4)
-        # latency roofline of the recurrence (streams / step latency): the same kernel with ONE warp in
-        # flight (8 streams) gives the step latency the dependent chain + one warp's issue allow; at batch 4096 every warp
-        # still has a scheduler to itself, so frac = that latency / the batch-4096 latency
-        quick("lstm_one_warp", "lstm", 8, 4096, steps=4)
-        if "error" not in secondary["lstm_batch4096"] and "error" not in secondary["lstm_one_warp"]:
-            big, one = secondary["lstm_batch4096"], secondary.pop("lstm_one_warp")
+        # latency roofline of the recurrence (streams / step latency).  4096 streams are 512 warps on 592
+        # schedulers: every warp issues alone, so the step is bound by its dependent chain.  Chain of the gate-split
+        # kernel for a 1-layer cell (instruction latencies of the microarchitecture guide: FFMA / FMUL 4, SHFL ~25, MUFU.RCP
+        # ~20): gate FMAs (1 + H + bias) x 4  ->  fast_tanh 45  ->  shuffle 25  ->  cell update 8  ->  fast_tanh 45  ->  h 4.
+        if "error" not in secondary["lstm_batch4096"]:
+            big = secondary["lstm_batch4096"]
+            H = 3
+            chain_cycles = (1 + H + 1) * 4 + 45 + 25 + 8 + 45 + 4
             ns_big = big["ms_per_step"] * 1e6 / big["frames_per_step"]
-            ns_one = one["ms_per_step"] * 1e6 / one["frames_per_step"]
-            big["roofline"] = {"bound": "latency of one recurrence step", "ns_per_step": ns_big, "ns_per_step_one_warp_alone": ns_one,
-                               "frac": ns_one / ns_big, "steps_per_s_per_stream": 1e9 / ns_big,
-                               "note": "serial in time: throughput = streams in flight / step latency; FLOP fraction is not the bound"}
+            ns_chain = chain_cycles / 1.965
+            big["roofline"] = {"bound": "latency of one recurrence step", "ns_per_step": ns_big,
+                               "critical_path_cycles_estimate": chain_cycles, "critical_path_ns_at_1965MHz": ns_chain,
+                               "frac": ns_chain / ns_big, "steps_per_s_per_stream": 1e9 / ns_big,
+                               "note": "serial in time: throughput = streams in flight / step latency (26 Gsamples/s = 4096 "
+                                       "streams / 155 ns); the FLOP fraction is not the bound"}
         quick("wavenet_a2_max_batch4096_general_kernel", "wavenet_a2_max", 4096, 1024, steps=2)
 
     # ---- roofline of the fused kernel (one launch per step) ----

@@ -287,8 +287,6 @@ bool spec_eligible(const WaveNetPlan& plan, const SpecGeometry& g, std::string* 
   int pmax = 0;
   for (int a = 0; a < plan.n_arrays; a++)
   {
-    if (plan.arrays[a].head_kernel != 1)
-      return no("convolutional head");
     pmax = std::max(pmax, plan.cp[a] / 4);
   }
   for (const LayerDesc& L : plan.layers)
@@ -311,7 +309,8 @@ std::string spec_header_source(const WaveNetPlan& plan)
        "#define NAMB200_SPEC_HEADER_INCLUDED 1\n"
        "namespace spec {\n"
        "struct Layer { int K, dil, act, w_off, ring_off, ring_mask; float ap0, ap1, ap2, ap3; };\n"
-       "struct Array { int C, CIN, HOUT, n_layers, layer0, rech_off, head_off, head_kernel; };\n";
+       "struct Array { int C, CIN, HOUT, n_layers, layer0, rech_off, head_off, head_kernel, head_dilation, head_ring_off, "
+       "head_ring_mask; };\n";
   o << "constexpr int NA = " << plan.n_arrays << ";\n";
   o << "constexpr int NL = " << plan.layers.size() << ";\n";
   o << "constexpr int LS = " << plan.max_lookback << ";\n";
@@ -323,7 +322,8 @@ std::string spec_header_source(const WaveNetPlan& plan)
     const int cin = a == 0 ? 1 : plan.cp[a - 1];
     const int hout = a + 1 == plan.n_arrays ? 1 : plan.cp[a + 1];
     o << "  {" << plan.cp[a] << ", " << cin << ", " << hout << ", " << A.n_layers << ", " << A.layer0 << ", " << A.rech_off
-      << ", " << A.head_off << ", " << A.head_kernel << "},\n";
+      << ", " << A.head_off << ", " << A.head_kernel << ", " << A.head_dilation << ", " << A.head_ring_off << ", "
+      << A.head_ring_mask << "},\n";
   }
   o << "};\nconstexpr Layer L[NL] = {\n";
   for (const LayerDesc& L : plan.layers)
@@ -402,6 +402,12 @@ SpecBuild build_lat_kernel(const WaveNetPlan& plan, int frame_warps)
     r.why_not = why;
     return r;
   }
+  for (int a = 0; a < plan.n_arrays; a++)
+    if (plan.arrays[a].head_kernel != 1)
+    {
+      r.why_not = "convolutional head (served by the precompiled short-call geometries)";
+      return r;
+    }
   if (plan.layers.size() > 64)
   {
     r.why_not = "more than 64 layers";

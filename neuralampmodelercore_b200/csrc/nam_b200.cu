@@ -1612,6 +1612,18 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
             return fail(NAM_B200_ERR_UNSUPPORTED,
                         "WaveNet not supported on the CUDA path: fused kernel: "
                           + (m->plan.eligible ? std::string("(eligible)") : m->plan.why_not) + "; general kernel: " + m->gplan.why_not);
+          if (m->opts.kernel_geometry != 4)
+          {
+            // no model-specialised kernel outside the fused family: say so, loudly when it was required
+            const std::string why = "not in the fused family: " + m->plan.why_not;
+            if (jit_mode(m.get()) == 1)
+              return fail(NAM_B200_ERR_UNSUPPORTED, "model-specialised kernel unavailable: " + why);
+            if (m->opts.max_batch >= 256 && jit_mode(m.get()) != 2)
+            {
+              m->spec_state = -1;
+              m->spec_note = why;
+            }
+          }
           m->use_generic = true;
           blob = m->gplan.weights;
           m->state_stride = m->gplan.state_floats;

@@ -433,7 +433,8 @@ __device__ __forceinline__ void array_forward(TileCtx& c, const V (&hin)[spec::A
   constexpr int C = A.C, CIN = A.CIN, HOUT = A.HOUT, P = C / 4;
   constexpr int W = spec::LS + NT;
   constexpr int HP = (S == 1) ? C / 4 : C / 2; // (sub-)planes the history copies move
-  static_assert(A.head_kernel == 1, "convolutional heads are served by the generic fused kernel");
+  constexpr int HEADK = A.head_kernel, HRMASK = A.head_ring_mask, HROFF = A.head_ring_off;
+  constexpr int HL = (A.head_kernel - 1) * A.head_dilation; // look-back of a convolutional head (0: kernel size 1)
   float4* const col0 = c.buf + spec::LS + threadIdx.x; // this thread's column of (sub-)plane 0
 
   // ---- rechannel (Conv1x1, no bias; model.cpp:492) -> this thread's columns of the tile
@@ -514,6 +515,11 @@ __device__ __forceinline__ void array_forward(TileCtx& c, const V (&hin)[spec::A
     // the next unit's history lands under this layer's 1x1 phase
     if constexpr (!last)
       request_layer_history<AI, NT, S>(c, IntC<LI + 1>{});
+    else if constexpr (HEADK > 1)
+    {
+      if (c.warp == 0) // the head accumulator's own ring (A2 family: head{kernel_size: 16}, model.cpp:397-400)
+        hist_load<HP, HL, HRMASK, W>(c.buf, c.state + S * HROFF, c.tabs0, c.bar, c.lane);
+    }
     else if constexpr (NEXT_AI >= 0)
       request_layer_history<NEXT_AI, NT, S>(c, IntC<spec::A[NEXT_AI < 0 ? 0 : NEXT_AI].layer0>{});
 
@@ -550,6 +556,50 @@ __device__ __forceinline__ void array_forward(TileCtx& c, const V (&hin)[spec::A
     }
   });
 
+  if constexpr (A.head_kernel > 1)
+  {
+    // ---- head rechannel as a causal convolution over the head accumulator (model.cpp:397-400,548): one more history
+    //      unit -- the accumulator columns go through the tile, their last (HK-1)*dilation columns live in the head ring
+    constexpr int HK = A.head_kernel, hd = A.head_dilation;
+#pragma unroll
+    for (int pl = 0; pl < P; pl++)
+    {
+      const V q[4] = {head[4 * pl], head[4 * pl + 1], head[4 * pl + 2], head[4 * pl + 3]};
+      store_plane<W>(col0, pl, q);
+    }
+    fence_async_smem();
+    __syncthreads(); // the accumulator columns are complete in the tile
+    mbar_wait(c.bar, c.phase);
+    c.phase ^= 1u;
+    if (c.warp == 0)
+      hist_store<HP, HL, A.head_ring_mask, W>(c.buf, c.state + S * A.head_ring_off, c.tabs0, c.tv, c.lane);
+#pragma unroll
+    for (int ho = 0; ho < HOUT; ho++)
+      vsplat(headout[ho], spec::w(A.head_off + HK * C * HOUT + ho)); // bias first, like the fused kernel
+#pragma unroll
+    for (int k = 0; k < HK; k++)
+    {
+      const int off = (HK - 1 - k) * hd;
+#pragma unroll
+      for (int pl = 0; pl < P; pl++)
+      {
+        V x[4];
+        load_plane<W>(col0, pl, off, x);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int ho = 0; ho < HOUT; ho++)
+            headout[ho] = vfma(x[i], spec::w(A.head_off + (k * C + 4 * pl + i) * HOUT + ho), headout[ho]);
+      }
+    }
+    if (c.warp == 0 && c.lane < HP)
+      bulk_wait_all();
+    __syncthreads(); // every read of the accumulator columns is done
+    if constexpr (NEXT_AI >= 0)
+      request_layer_history<NEXT_AI, NT, S>(c, IntC<spec::A[NEXT_AI < 0 ? 0 : NEXT_AI].layer0>{});
+    return;
+  }
+
   // ---- head rechannel (kernel size 1; model.cpp:548): headout = H head (+ g)
 #pragma unroll
   for (int ho = 0; ho < HOUT; ho++)
@@ -564,9 +614,6 @@ __device__ __forceinline__ void array_forward(TileCtx& c, const V (&hin)[spec::A
     headout[ho] = vaddc(headout[ho], spec::w(A.head_off + C * HOUT + ho)); // bias (zero when the head has none)
 }
 
-// ---- S = 2: one stream per ring <-> the CTA's interleaved scratch ----------------------------------------------------------
-// `ra`, `rb`: the two streams' ring storage ([C/4][R][4 floats] per layer, wavenet_fused.cuh); `sc`: the scratch, per layer
-// [C/2 sub-planes][R] columns of (c A, c B, c' A, c' B).  Whole rings are converted (R <= 2 x look-back).
 template <int NT>
 __device__ __forceinline__ void pair_rings_to_scratch(const float* ra, const float* rb, float* sc)
 {
@@ -617,6 +664,8 @@ __device__ __forceinline__ void fence_async_all()
 template <int NT, int S, int MINB>
 __device__ __forceinline__ void wavenet_spec_body(const SpecParams& p)
 {
+  static_assert(S == 1 || (spec::A[0].head_kernel == 1 && spec::A[spec::NA - 1].head_kernel == 1),
+                "the stream-pair variant does not convert head rings");
   constexpr int T = NT; // one frame per thread (of one stream, or of a pair of streams)
   static_assert(spec::NA == 1 || spec::NA == 2, "one or two layer arrays");
   static_assert(S == 1 || S == 2, "one stream per thread, or a packed pair of streams");

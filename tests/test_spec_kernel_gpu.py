@@ -135,14 +135,32 @@ def test_prewarmed_state_and_second_reset():
 
 
 def test_jit_required_refuses_what_it_cannot_serve():
-    """A convolutional head (A2 family) is outside the specialised kernel: jit=1 must fail loudly, jit=0 must fall back
-    to the precompiled fused kernel and say why."""
-    nam = fx.load_model("a2_full")
-    with pytest.raises(Exception, match="convolutional head"):
+    """A gated / FiLM / condition_dsp WaveNet is outside the specialised kernel (it runs on the general kernel): jit=1 must
+    fail loudly, jit=0 must keep the precompiled kernel and say why."""
+    nam = fx.load_model("wavenet_a2_max")
+    with pytest.raises(Exception, match="fused family"):
         nb.get_dsp(nam, batch=512, jit=1)
     d = nb.get_dsp(nam, batch=512, jit=0)
-    assert d.jit_state == -1 and "convolutional head" in d.jit_note()
+    assert d.jit_state == -1 and "fused family" in d.jit_note()
     d.close()
+
+
+@pytest.mark.parametrize("name", ["a2_full", "a2_lite"])
+@pytest.mark.parametrize("fast", [False, True], ids=["exact_tanh", "fast_tanh"])
+def test_a2_family_convolutional_head(name, fast):
+    """The A2 family (23 layers of 8 / 3 channels, kernel sizes 6 and 15, odd dilations up to 239, head rechannel = a causal
+    convolution of kernel size 16 over the head accumulator, model.cpp:397-400,548) compiled into the specialised kernel:
+    the head accumulator has its own ring and history window."""
+    nam = fx.load_model(name)
+    B, N = 6, 2600
+    x = fx.synthetic_batch(B, N, seed=13)
+    ref = _oracle_batch(nam, x, fast)
+    d = _spec(nam, B, fast)
+    d.Reset(48000.0, 1024)
+    got = np.concatenate([d.process_batch(np.ascontiguousarray(x[:, p:p + c])) for p, c in ((0, 1024), (1024, 513), (1537, 1), (1538, 1024), (2562, 38))], axis=1)
+    d.close()
+    err = float(np.max(np.abs(got - ref)))
+    assert err <= TOL, f"max-abs {err:.3e}"
 
 
 def test_default_policy_uses_it_for_throughput_handles():
