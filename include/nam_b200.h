@@ -195,6 +195,9 @@ int nam_b200_inspect_file(const char* nam_path, int fast_tanh, char* out, int64_
  * GPU -- NVRTC cross-compiles -- and describe the outcome as a small JSON object: ok, from_cache, compile_seconds,
  * cubin_bytes, threads, frames_per_thread, smem_bytes, why_not.  Used to pre-populate the cache at install time. */
 int nam_b200_jit_prepare_json(const char* nam_json_text, int fast_tanh, char* out, int64_t capacity);
+/* The same for the kernel geometry a handle of `max_batch` streams on a 148-SM device would get (the short-call entry point
+ * packs 6, 7 or 8 streams per CTA, whichever fills whole waves best at max_batch). */
+int nam_b200_jit_prepare_json_for_batch(const char* nam_json_text, int fast_tanh, int max_batch, char* out, int64_t capacity);
 /* Diagnostic: how this handle's specialised kernel was obtained, or why it has none.  Returns the text's length. */
 int64_t nam_b200_jit_note(const nam_b200_model* m, char* out, int64_t capacity);
 

@@ -79,6 +79,7 @@ EXPORTED_SYMBOLS = [
     "nam_b200_inspect_file",
     "nam_b200_submodel_json",
     "nam_b200_jit_prepare_json",
+    "nam_b200_jit_prepare_json_for_batch",
     "nam_b200_jit_note",
     "nam_b200_pin_host_buffer",
     "nam_b200_unpin_host_buffer",
@@ -144,6 +145,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.nam_b200_submodel_json.restype = C.c_int64
     lib.nam_b200_jit_prepare_json.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int64]
     lib.nam_b200_jit_prepare_json.restype = C.c_int
+    lib.nam_b200_jit_prepare_json_for_batch.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int64]
+    lib.nam_b200_jit_prepare_json_for_batch.restype = C.c_int
     lib.nam_b200_jit_note.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     lib.nam_b200_jit_note.restype = C.c_int64
     lib.nam_b200_pin_host_buffer.argtypes = [C.c_void_p, C.c_int64]

@@ -359,8 +359,18 @@ SpecBuild build_spec_kernel(const WaveNetPlan& plan, const SpecGeometry& g)
     r.max_planes = std::max(r.max_planes, plan.cp[a] / 4);
 
   const std::string header = spec_header_source(plan);
-  const std::vector<std::string> defs = {"-DNAMB200_SPEC_NT=" + std::to_string(g.nt), "-DNAMB200_SPEC_S=" + std::to_string(g.s),
-                                         "-DNAMB200_SPEC_MINB=" + std::to_string(g.min_ctas)};
+  std::vector<std::string> defs = {"-DNAMB200_SPEC_NT=" + std::to_string(g.nt), "-DNAMB200_SPEC_S=" + std::to_string(g.s),
+                                   "-DNAMB200_SPEC_MINB=" + std::to_string(g.min_ctas)};
+  // second entry point of the same cubin: the short-call variant (nt / 64 streams x 64 frames per CTA) for models
+  // without a convolutional head
+  r.has_short = g.s == 1 && g.nt % 64 == 0;
+  for (int a = 0; a < plan.n_arrays; a++)
+    r.has_short = r.has_short && plan.arrays[a].head_kernel == 1;
+  if (r.has_short)
+  {
+    defs.push_back("-DNAMB200_SPEC_SHORT_FQ=64");
+    defs.push_back("-DNAMB200_SPEC_SHORT_NT=" + std::to_string(64 * g.short_streams));
+  }
   const CompiledKernel ck = compile_or_fetch("wavenet_spec", header, "wavenet_spec.cuh", kSpecKernelSource, "NAM_B200_SPEC_SOURCE", defs);
   r.ok = ck.ok;
   r.why_not = ck.why_not;

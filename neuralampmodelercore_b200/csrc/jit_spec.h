@@ -20,6 +20,7 @@ struct SpecGeometry
   int nt = 512; // threads per CTA
   int s = 1; // frames per thread
   int min_ctas = 2; // __launch_bounds__ second argument
+  int short_streams = 8; // streams per CTA of the short-call entry point (64 frames each)
   int tile() const { return nt * s; }
 };
 
@@ -32,6 +33,7 @@ struct SpecBuild
   int staged_cols = 0; // spec::LS: columns of history staged in front of the tile (max look-back of the model)
   int max_planes = 0; // widest array, in planes of 4 channels
   bool from_cache = false;
+  bool has_short = false; // the cubin also holds wavenet_spec_short_kernel (geom.nt / 64 streams x 64 frames per CTA)
   double compile_seconds = 0.0;
   size_t smem_bytes() const { return (size_t)max_planes * (size_t)(staged_cols + geom.tile()) * 16; }
 };

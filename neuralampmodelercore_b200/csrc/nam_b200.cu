@@ -385,6 +385,9 @@ struct nam_b200_model
   // model-specialised kernel (wavenet_spec.cuh compiled for this model by NVRTC, jit_spec.cpp): the throughput path
   cudaLibrary_t spec_lib = nullptr;
   cudaKernel_t spec_kernel = nullptr;
+  cudaKernel_t spec_short_kernel = nullptr; // its short-call entry point (8 streams x 64 frames per CTA), may be absent
+  size_t spec_short_smem = 0;
+  int spec_short_ctas_per_sm = 0;
   cudaKernel_t lstm_spec_kernels[2] = {nullptr, nullptr}; // lstm_spec.cuh: exact / fast activation regime
   cudaKernel_t lstm_gate_kernels[2] = {nullptr, nullptr}; // its gate-split variant (four lanes per stream)
   // low-latency kernel (wavenet_lat.cuh): few streams x short calls; built by reset() for the handle's maxBufferSize
@@ -846,6 +849,26 @@ struct SpecKernelParams
 
 int jit_mode(const nam_b200_model* m);
 
+// Geometry of the specialised kernel for a handle of `max_batch` streams.  Streams per CTA of the short-call entry point:
+// the count that fills whole waves of 2 CTAs per SM best (4096 streams: 8 per CTA = 512 CTAs = 1.73 waves, 7 per CTA = 586 =
+// 1.98 waves).
+SpecGeometry spec_geometry_for(int max_batch, int sm_count)
+{
+  SpecGeometry g;
+  double best = -1.0;
+  for (int q : {8, 7, 6})
+  {
+    const double slots = (max_batch + q - 1) / q, resident = 2.0 * sm_count;
+    const double eff = slots / (std::ceil(slots / resident) * resident);
+    if (eff > best + 0.02)
+    {
+      best = eff;
+      g.short_streams = q;
+    }
+  }
+  return g;
+}
+
 // Decide whether this handle gets a specialised kernel, build / fetch it, load it.  jit option: 0 = auto (on for
 // throughput handles: max_batch >= 256, where one compilation pays for itself within the first calls), 1 = required
 // (creation fails with the reason if it cannot be had), 2 = off.  $NAM_B200_JIT=0/1 overrides "auto".
@@ -855,7 +878,7 @@ void setup_spec_kernel(nam_b200_model* m)
   const bool wanted = mode == 1 || ((mode == 0 || mode == 3) && m->opts.max_batch >= 256);
   if (!wanted || m->opts.kernel_geometry != 0)
     return;
-  SpecGeometry g;
+  const SpecGeometry g = spec_geometry_for(m->opts.max_batch, m->sm_count);
   SpecBuild b = build_spec_kernel(m->plan, g);
   if (!b.ok)
   {
@@ -883,6 +906,19 @@ void setup_spec_kernel(nam_b200_model* m)
     if (occ < 1)
       throw CudaError("the specialised kernel does not fit on an SM");
     m->spec_ctas_per_sm = occ;
+    if (b.has_short && cudaLibraryGetKernel(&m->spec_short_kernel, m->spec_lib, "wavenet_spec_short_kernel") == cudaSuccess)
+    {
+      m->spec_short_smem = (size_t)b.max_planes * 64 * b.geom.short_streams * 16;
+      int occ_s = 0;
+      if (cudaFuncSetAttribute((const void*)m->spec_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)m->spec_short_smem) != cudaSuccess
+          || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, (const void*)m->spec_short_kernel, 64 * b.geom.short_streams,
+                                                           m->spec_short_smem) != cudaSuccess
+          || occ_s < 1)
+        m->spec_short_kernel = nullptr;
+      m->spec_short_ctas_per_sm = occ_s;
+    }
+    cudaGetLastError();
     m->spec_state = 1;
     m->spec_note = b.from_cache ? "cubin from cache" : "compiled in " + std::to_string(b.compile_seconds) + " s";
   }
@@ -1082,6 +1118,20 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
   if (m->lat_state == 1 && n_frames <= m->lat_frames && batch <= m->sm_count)
   {
     launch_wavenet_lat(m, kp, st);
+    m->launches++;
+    return;
+  }
+  // short calls on many streams, specialised: nt / 64 streams x 64 frames per CTA (wavenet_spec_short_kernel)
+  if (m->spec_state == 1 && m->spec_short_kernel != nullptr && m->opts.kernel_geometry == 0 && n_frames <= 64
+      && batch >= 2 * m->spec_geom.short_streams)
+  {
+    SpecKernelParams sp{kp.state, kp.state_stride, kp.in,  kp.out, kp.in_stride, kp.out_stride,
+                        kp.batch, kp.n_frames,     kp.t_base, nullptr, 0};
+    void* args[] = {&sp};
+    const int q = m->spec_geom.short_streams;
+    const int grid_s = std::max(1, std::min((batch + q - 1) / q, m->spec_short_ctas_per_sm * m->sm_count));
+    CUDA_CHECK(cudaLaunchKernel((const void*)m->spec_short_kernel, dim3(grid_s), dim3(64 * q), args,
+                                m->spec_short_smem, st));
     m->launches++;
     return;
   }
@@ -2055,6 +2105,11 @@ int nam_b200_inspect_json(const char* nam_json_text, int fast_tanh, char* out, i
 
 int nam_b200_jit_prepare_json(const char* nam_json_text, int fast_tanh, char* out, int64_t capacity)
 {
+  return nam_b200_jit_prepare_json_for_batch(nam_json_text, fast_tanh, 1, out, capacity);
+}
+
+int nam_b200_jit_prepare_json_for_batch(const char* nam_json_text, int fast_tanh, int max_batch, char* out, int64_t capacity)
+{
   if (!nam_json_text)
     return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null argument");
   LoadOptions lo;
@@ -2064,7 +2119,7 @@ int nam_b200_jit_prepare_json(const char* nam_json_text, int fast_tanh, char* ou
     const ModelSpec ms = model_spec_from_text(nam_json_text, lo);
     if (ms.arch != Arch::WaveNet && ms.arch != Arch::LSTM)
       return fail(NAM_B200_ERR_UNSUPPORTED, "only WaveNets and LSTMs have model-specialised kernels");
-    const SpecBuild b = ms.arch == Arch::LSTM ? build_lstm_spec_kernel(ms) : build_spec_kernel(plan_wavenet(ms), SpecGeometry{});
+    const SpecBuild b = ms.arch == Arch::LSTM ? build_lstm_spec_kernel(ms) : build_spec_kernel(plan_wavenet(ms), spec_geometry_for(std::max(max_batch, 1), 148));
     // WaveNets: also the low-latency kernel for 64-frame calls (the plugin protocol), so that a first Reset finds it cached
     SpecBuild lat;
     if (ms.arch == Arch::WaveNet)

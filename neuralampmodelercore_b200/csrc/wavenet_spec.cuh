@@ -776,6 +776,172 @@ __device__ __forceinline__ void wavenet_spec_body(const SpecParams& p)
   }
 }
 
+// ==== short calls on many streams: Q streams x FQ frames per CTA ==========================================================
+// The reference's hosts call process() with 64-frame blocks.  With thousands of streams such a step is not latency-bound
+// per stream but occupancy-bound: every stream-call must pull ~61 KB of ring columns (a1_standard, 64 frames) through L2 /
+// HBM, and the precompiled short-call geometry (4 streams per 128-thread CTA, 55 KB of weights in shared memory per CTA)
+// runs 8 warps per SM -- profiles/r02i_short_call_*: long-scoreboard stalls, issue-active 32 %.  Here the weights are
+// immediates, so a CTA is NT / FQ streams side by side (8 x 64 frames at 512 threads), shared memory holds only the
+// tile (32 KB) and 32 warps per SM hide the ring loads.  History is NOT staged: a tap that reaches before the call reads
+// its ring column directly (16 bytes per thread, consecutive frames = consecutive addresses), one that stays inside the
+// call reads the tile.  Same rings as every other kernel.
+template <int AI, int NEXT_AI, int NT, int FQ>
+__device__ __forceinline__ void array_forward_short(float4* tile, float* state, const u32 tabs0, const int n, const int f,
+                                                    const bool live, const float (&hin)[spec::A[AI].CIN], const float cond,
+                                                    float (&head)[spec::A[AI].C], float (&hout)[spec::A[AI].C],
+                                                    float (&headout)[spec::A[AI].HOUT])
+{
+  constexpr spec::Array A = spec::A[AI];
+  constexpr int C = A.C, CIN = A.CIN, HOUT = A.HOUT, P = C / 4;
+  constexpr int W = NT; // tile columns per plane: Q streams x FQ frames, thread t owns column t
+  static_assert(A.head_kernel == 1, "convolutional heads take the precompiled short-call geometry");
+  float4* const col0 = tile + threadIdx.x;
+
+  {
+    float h[C];
+#pragma unroll
+    for (int o = 0; o < C; o++)
+      h[o] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < CIN; i++)
+#pragma unroll
+      for (int o = 0; o < C; o++)
+        h[o] = fmaf(spec::w(A.rech_off + i * C + o), hin[i], h[o]);
+#pragma unroll
+    for (int pl = 0; pl < P; pl++)
+      col0[pl * W] = make_float4(h[4 * pl], h[4 * pl + 1], h[4 * pl + 2], h[4 * pl + 3]);
+  }
+
+  static_for<0, A.n_layers>([&](auto li_c) {
+    constexpr int LI = A.layer0 + decltype(li_c)::value;
+    constexpr bool last = (decltype(li_c)::value + 1 == A.n_layers);
+    constexpr spec::Layer Ld = spec::L[LI];
+    constexpr int K = Ld.K, dil = Ld.dil, L = (K - 1) * dil, R = Ld.ring_mask + 1;
+    constexpr int w_conv = Ld.w_off, w_bias = w_conv + K * C * C, w_mix = w_bias + C, w_p = w_mix + C,
+                  w_pb = w_p + C * C;
+    const float4* const ring = reinterpret_cast<const float4*>(state + Ld.ring_off);
+
+    __syncthreads(); // B0: the layer input is complete in the tile
+    float acc[C];
+#pragma unroll
+    for (int o = 0; o < C; o++)
+      acc[o] = fmaf(spec::w(w_mix + o), cond, spec::w(w_bias + o));
+    static_for<0, K>([&](auto k_c) {
+      constexpr int k = decltype(k_c)::value;
+      constexpr int off = (K - 1 - k) * dil;
+      const bool from_ring = (off > 0) && (off >= FQ || f < off); // (warp-uniform for off >= FQ and for off a multiple of 32)
+      const u32 rcol = (tabs0 + (u32)f - (u32)off) & (u32)Ld.ring_mask;
+#pragma unroll
+      for (int pl = 0; pl < P; pl++)
+      {
+        float4 q;
+        if (from_ring)
+          q = __ldcg(ring + pl * R + rcol);
+        else
+          q = col0[pl * W - off];
+        const float x[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int o = 0; o < C; o++)
+            acc[o] = fmaf(spec::w(w_conv + (k * C + 4 * pl + i) * C + o), x[i], acc[o]);
+      }
+    });
+    apply_activation<LI, C>(acc);
+#pragma unroll
+    for (int q = 0; q < C / 2; q++) // model.cpp:530
+      unpack2(add2(pack2(head[2 * q], head[2 * q + 1]), pack2(acc[2 * q], acc[2 * q + 1])), head[2 * q], head[2 * q + 1]);
+    __syncthreads(); // B1: every tap read of the tile is done
+
+    float hn[C];
+#pragma unroll
+    for (int pl = 0; pl < P; pl++)
+    {
+      const float4 own = col0[pl * W];
+      // RingBuffer::Write: the call's last `look-back` columns of the layer input (ring loads of this layer are done:
+      // they fed the FMAs above, and the barrier ordered every thread's loads before anybody's stores)
+      if (live && f < n && f >= n - L)
+        __stcg(reinterpret_cast<float4*>(state + Ld.ring_off) + pl * R + ((tabs0 + (u32)f) & (u32)Ld.ring_mask), own);
+      hn[4 * pl] = own.x + spec::w(w_pb + 4 * pl);
+      hn[4 * pl + 1] = own.y + spec::w(w_pb + 4 * pl + 1);
+      hn[4 * pl + 2] = own.z + spec::w(w_pb + 4 * pl + 2);
+      hn[4 * pl + 3] = own.w + spec::w(w_pb + 4 * pl + 3);
+    }
+#pragma unroll
+    for (int i = 0; i < C; i++)
+#pragma unroll
+      for (int o = 0; o < C; o++)
+        hn[o] = fmaf(spec::w(w_p + i * C + o), acc[i], hn[o]);
+    if constexpr (!last)
+    {
+#pragma unroll
+      for (int pl = 0; pl < P; pl++)
+        col0[pl * W] = make_float4(hn[4 * pl], hn[4 * pl + 1], hn[4 * pl + 2], hn[4 * pl + 3]);
+    }
+    else
+    {
+#pragma unroll
+      for (int o = 0; o < C; o++)
+        hout[o] = hn[o];
+    }
+  });
+
+#pragma unroll
+  for (int ho = 0; ho < HOUT; ho++)
+    headout[ho] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < C; i++)
+#pragma unroll
+    for (int ho = 0; ho < HOUT; ho++)
+      headout[ho] = fmaf(spec::w(A.head_off + i * HOUT + ho), head[i], headout[ho]);
+#pragma unroll
+  for (int ho = 0; ho < HOUT; ho++)
+    headout[ho] += spec::w(A.head_off + C * HOUT + ho);
+}
+
+template <int NT, int FQ>
+__device__ __forceinline__ void wavenet_spec_short_body(const SpecParams& p)
+{
+  constexpr int Q = NT / FQ; // streams per CTA
+  static_assert(Q * FQ == NT && (FQ % 32) == 0, "whole warps per stream");
+  extern __shared__ float4 spec_smem[]; // [planes][NT]
+  const int tid = threadIdx.x;
+  const int f = tid % FQ, q = tid / FQ;
+  for (int slot = blockIdx.x; slot * Q < p.batch; slot += gridDim.x)
+  {
+    const int stream = slot * Q + q;
+    const bool live = stream < p.batch;
+    const int sc = min(stream, p.batch - 1);
+    float* state = p.state + (size_t)sc * p.state_stride;
+    const float xv = (live && f < p.n_frames) ? __ldg(p.in + (size_t)sc * p.in_stride + f) : 0.0f;
+    const float x[1] = {xv};
+    constexpr int C0 = spec::A[0].C;
+    float head0[C0], hout0[C0], ho0[spec::A[0].HOUT];
+#pragma unroll
+    for (int o = 0; o < C0; o++)
+      head0[o] = 0.0f;
+    float y;
+    array_forward_short<0, spec::NA - 1, NT, FQ>(spec_smem, state, p.t_base, p.n_frames, f, live, x, xv, head0, hout0, ho0);
+    if constexpr (spec::NA == 1)
+      y = ho0[0];
+    else
+    {
+      constexpr int AI1 = spec::NA - 1;
+      constexpr int C1 = spec::A[AI1].C;
+      float head1[C1], hout1[C1], ho1[spec::A[AI1].HOUT];
+#pragma unroll
+      for (int o = 0; o < C1; o++)
+        head1[o] = ho0[o];
+      __syncthreads(); // (the last layer's tap reads are fenced by its B1; this orders the rechannel's tile stores too)
+      array_forward_short<AI1, -1, NT, FQ>(spec_smem, state, p.t_base, p.n_frames, f, live, hout0, xv, head1, hout1, ho1);
+      y = ho1[0];
+    }
+    if (live && f < p.n_frames)
+      p.out[(size_t)sc * p.out_stride + f] = spec::head_scale * y;
+    __syncthreads(); // the next slot rewrites the tile
+  }
+}
+
 } // namespace namb200_spec
 
 #ifndef NAMB200_SPEC_NO_KERNEL // (wavenet_lat.cuh includes this file for its helpers only)
@@ -794,4 +960,15 @@ extern "C" __global__ void __launch_bounds__(NAMB200_SPEC_NT, NAMB200_SPEC_MINB)
 {
   namb200_spec::wavenet_spec_body<NAMB200_SPEC_NT, NAMB200_SPEC_S, NAMB200_SPEC_MINB>(p);
 }
+#ifdef NAMB200_SPEC_SHORT_FQ
+// short-call variant: NAMB200_SPEC_SHORT_NT / NAMB200_SPEC_SHORT_FQ streams per CTA, calls of up to NAMB200_SPEC_SHORT_FQ frames
+#ifndef NAMB200_SPEC_SHORT_NT
+#define NAMB200_SPEC_SHORT_NT NAMB200_SPEC_NT
+#endif
+extern "C" __global__ void __launch_bounds__(NAMB200_SPEC_SHORT_NT, 2)
+  wavenet_spec_short_kernel(const __grid_constant__ namb200_spec::SpecParams p)
+{
+  namb200_spec::wavenet_spec_short_body<NAMB200_SPEC_SHORT_NT, NAMB200_SPEC_SHORT_FQ>(p);
+}
+#endif
 #endif // NAMB200_SPEC_NO_KERNEL

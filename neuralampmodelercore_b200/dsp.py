@@ -353,7 +353,7 @@ def get_dsp(config, batch: int = 1, device: int = -1, prewarm: Optional[bool] = 
     return DSP(h.value, lib, int(batch))
 
 
-def jit_prepare(config, fast_tanh: Optional[bool] = None) -> dict:
+def jit_prepare(config, fast_tanh: Optional[bool] = None, batch: int = 1) -> dict:
     """Host-only: compile (or fetch from the cache) the model-specialised kernel of a WaveNet .nam (path, dict or JSON
     text).  Needs no GPU: NVRTC cross-compiles for sm_100a.  Returns the library's report as a dict."""
     import json
@@ -365,7 +365,7 @@ def jit_prepare(config, fast_tanh: Optional[bool] = None) -> dict:
         text = config if isinstance(config, str) else json.dumps(config)
     ft = int(_using_fast_tanh if fast_tanh is None else bool(fast_tanh))
     buf = C.create_string_buffer(2048)
-    rc = lib.nam_b200_jit_prepare_json(text.encode(), ft, buf, len(buf))
+    rc = lib.nam_b200_jit_prepare_json_for_batch(text.encode(), ft, int(batch), buf, len(buf))
     if rc != 0:
         _raise(rc, lib)
     return json.loads(buf.value.decode())

@@ -297,3 +297,23 @@ def test_lat_kernel_shape_family(case):
     scale = max(1.0, float(np.max(np.abs(ref))))
     err = float(np.max(np.abs(got - ref)))
     assert err <= TOL * scale, f"max-abs {err:.3e}"
+
+
+def test_short_call_variant_many_streams():
+    """64-frame process() calls on many streams (the reference's calling convention at scale): 8 streams x 64 frames per
+    CTA of the specialised kernel, ring columns read directly.  37 streams (the last CTA is partly empty), call lengths
+    64 / 17 / 1 / 33, a long call in between (throughput kernel, same rings)."""
+    nam = fx.load_model("wavenet_a1_standard")
+    chunks = [64] * 6 + [17, 64, 1, 64, 33, 700, 64, 64, 5]
+    N = sum(chunks)
+    x = fx.synthetic_batch(37, N, seed=31)
+    ref = _oracle_batch(nam, x, True)
+    d = _spec(nam, 37, True)
+    d.Reset(48000.0, 1024)
+    out, pos = [], 0
+    for n in chunks:
+        out.append(d.process_batch(np.ascontiguousarray(x[:, pos:pos + n])))
+        pos += n
+    d.close()
+    err = float(np.max(np.abs(np.concatenate(out, axis=1) - ref)))
+    assert err <= TOL, f"max-abs {err:.3e}"
