@@ -53,12 +53,13 @@ def _stale() -> bool:
 def embed_spec_source() -> None:
     """wavenet_spec.cuh / lstm_spec.cuh -> csrc/*_src.inc, C++ raw string literals: the library carries the sources of the
     model-specialised kernels and hands them to NVRTC at model-load time (jit_spec.cpp)."""
-    for stem in ("wavenet_spec", "lstm_spec", "wavenet_lat"):
+    for stem in ("wavenet_spec", "lstm_spec", "wavenet_lat", "wavenet_generic_spec"):
         _embed(stem)
+    _embed("generic_desc", ".h")
 
 
-def _embed(stem: str) -> Path:
-    src = (CSRC / f"{stem}.cuh").read_text()
+def _embed(stem: str, ext: str = ".cuh") -> Path:
+    src = (CSRC / f"{stem}{ext}").read_text()
     delim = "NAMB200SPEC"
     assert f"){delim}\"" not in src
     # a string literal may not exceed 64 KiB on some compilers: split into adjacent literals
@@ -66,7 +67,7 @@ def _embed(stem: str) -> Path:
     for i in range(0, len(src), chunk):
         parts.append(f'R"{delim}({src[i:i + chunk]}){delim}"')
     inc = CSRC / f"{stem}_src.inc"
-    text = f"// generated from {stem}.cuh by _build.py -- do not edit\n" + "\n".join(parts) + "\n"
+    text = f"// generated from {stem}{ext} by _build.py -- do not edit\n" + "\n".join(parts) + "\n"
     if not inc.exists() or inc.read_text() != text:
         inc.write_text(text)
     return inc

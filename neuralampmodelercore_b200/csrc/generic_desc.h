@@ -9,7 +9,11 @@
 // exact zeros to the sums); one CTA per stream, one thread per frame of a 128-frame tile, layer by layer.
 #pragma once
 
+#ifdef __CUDACC_RTC__ // (NVRTC: no system headers; the specialised general kernel includes this file)
+typedef unsigned int uint32_t;
+#else
 #include <stdint.h>
+#endif
 
 namespace namb200
 {

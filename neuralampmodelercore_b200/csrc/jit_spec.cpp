@@ -1,6 +1,7 @@
 // jit_spec.cpp -- see jit_spec.h.  NVRTC is reached through dlopen (no link-time dependency: the library still
 // loads, and serves every model through the precompiled kernels, on a host without libnvrtc).
 #include "jit_spec.h"
+#include "generic_pack.h"
 
 #include <dlfcn.h>
 #include <sys/stat.h>
@@ -31,6 +32,12 @@ const char* const kLstmSpecKernelSource =
   ;
 const char* const kLatKernelSource =
 #include "wavenet_lat_src.inc"
+  ;
+const char* const kGenericSpecKernelSource =
+#include "wavenet_generic_spec_src.inc"
+  ;
+const char* const kGenericDescSource =
+#include "generic_desc_src.inc"
   ;
 
 // ---- NVRTC through dlopen ------------------------------------------------------------------------------------------
@@ -439,6 +446,137 @@ SpecBuild build_lat_kernel(const WaveNetPlan& plan, int frame_warps)
   r.compile_seconds = ck.compile_seconds;
   r.staged_cols = (int)(smem / 16); // (reused: float4 columns of dynamic shared memory)
   r.max_planes = 1;
+  return r;
+}
+
+// ---- the general kernel, specialised (wavenet_generic_spec.cuh) -------------------------------------------------------
+namespace
+{
+std::string lit(const GMat& m)
+{
+  std::ostringstream o;
+  o << "{" << m.in << ", " << m.out << ", " << m.w_off << ", " << m.b_off << "}";
+  return o.str();
+}
+std::string lit(const GConv& v)
+{
+  std::ostringstream o;
+  o << "{" << v.in << ", " << v.out << ", " << v.kernel << ", " << v.dilation << ", " << v.w_off << ", " << v.b_off << ", "
+    << v.ring_off << ", " << v.ring_mask << "}";
+  return o.str();
+}
+std::string lit(const GAct& a)
+{
+  std::ostringstream o;
+  o << "{" << a.type << ", " << float_literal(a.p0) << ", " << float_literal(a.p1) << ", " << float_literal(a.p2) << ", "
+    << float_literal(a.p3) << ", " << a.slopes_off << ", " << a.n_slopes << "}";
+  return o.str();
+}
+std::string lit(const GFilm& f)
+{
+  std::ostringstream o;
+  o << "{" << f.active << ", " << f.shift << ", " << f.dim << ", " << lit(f.css) << "}";
+  return o.str();
+}
+std::string lit(const GLayer& L)
+{
+  std::ostringstream o;
+  o << "{" << L.channels << ", " << L.bottleneck << ", " << L.zrows << ", " << L.gating << ", " << L.has_l1x1 << ", " << L.has_h1x1
+    << ",\n   " << lit(L.conv) << ", " << lit(L.mixin) << ", " << lit(L.l1x1) << ", " << lit(L.h1x1) << ",\n   " << lit(L.act) << ", "
+    << lit(L.sec) << ",\n   {";
+  for (int i = 0; i < kGenFilmSites; i++)
+    o << (i ? ", " : "") << lit(L.film[i]);
+  o << "}}";
+  return o.str();
+}
+std::string lit(const GArray& A)
+{
+  std::ostringstream o;
+  o << "{" << A.input_size << ", " << A.channels << ", " << A.head_out_size << ", " << A.head_size << ", " << A.layer0 << ", "
+    << A.n_layers << ", " << lit(A.rechannel) << ", " << lit(A.head) << "}";
+  return o.str();
+}
+std::string lit(const GNet& N)
+{
+  std::ostringstream o;
+  o << "{" << N.in_channels << ", " << N.out_channels << ", " << N.n_arrays << ", " << N.with_head << ", " << N.n_head_convs << ", "
+    << float_literal(N.head_scale) << ", " << lit(N.head_act) << ",\n  {";
+  for (int i = 0; i < kGenMaxArrays; i++)
+    o << (i ? ",\n   " : "") << lit(N.arrays[i]);
+  o << "},\n  {";
+  for (int i = 0; i < kGenMaxHeadConvs; i++)
+    o << (i ? ", " : "") << lit(N.head_convs[i]);
+  o << "}}";
+  return o.str();
+}
+bool finite_desc(const GenericPlan& gp)
+{
+  for (float v : gp.weights)
+    if (!std::isfinite(v))
+      return false;
+  for (const GLayer& L : gp.layers)
+    for (float v : {L.act.p0, L.act.p1, L.act.p2, L.act.p3, L.sec.p0, L.sec.p1, L.sec.p2, L.sec.p3})
+      if (!std::isfinite(v))
+        return false;
+  return std::isfinite(gp.net.head_scale) && std::isfinite(gp.cond.head_scale);
+}
+} // namespace
+
+std::string generic_spec_header_source(const GenericPlan& gp)
+{
+  std::ostringstream o;
+  o << "// generated by jit_spec.cpp: one WaveNet with the reference's full option set, as compile-time data\n"
+       "#define NAMB200_GSPEC_HEADER_INCLUDED 1\n#include \"generic_desc.h\"\nnamespace gspec {\nusing namespace namb200;\n";
+  o << "constexpr int has_cond = " << (gp.has_cond ? 1 : 0) << ";\n";
+  o << "__device__ constexpr GNet net = " << lit(gp.net) << ";\n";
+  o << "__device__ constexpr GNet cond = " << lit(gp.has_cond ? gp.cond : GNet{}) << ";\n";
+  o << "__device__ constexpr GLayer layers[" << std::max<size_t>(gp.layers.size(), 1) << "] = {\n";
+  for (const GLayer& L : gp.layers)
+    o << "  " << lit(L) << ",\n";
+  if (gp.layers.empty())
+    o << "  {}\n";
+  o << "};\n__device__ const unsigned Wb[" << std::max<size_t>(gp.weights.size(), 1) << "] = {\n";
+  char buf[16];
+  for (size_t i = 0; i < gp.weights.size(); i++)
+  {
+    uint32_t u;
+    std::memcpy(&u, &gp.weights[i], 4);
+    std::snprintf(buf, sizeof buf, "0x%08Xu,", u);
+    o << buf << ((i % 8 == 7) ? "\n" : " ");
+  }
+  if (gp.weights.empty())
+    o << "0u";
+  o << "};\n__device__ __forceinline__ float w(const int i) { return __uint_as_float(Wb[i]); }\n}  // namespace gspec\n";
+  return o.str();
+}
+
+SpecBuild build_generic_spec_kernel(const GenericPlan& gp)
+{
+  SpecBuild r;
+  r.geom.nt = kGenTile;
+  if (!gp.eligible)
+  {
+    r.why_not = "not served by the general kernel: " + gp.why_not;
+    return r;
+  }
+  if (!finite_desc(gp))
+  {
+    r.why_not = "non-finite weight or activation parameter";
+    return r;
+  }
+  if (gp.weights.size() > 40000)
+  {
+    r.why_not = "too many weights to unroll (" + std::to_string(gp.weights.size()) + ")";
+    return r;
+  }
+  const CompiledKernel ck = compile_or_fetch("wavenet_generic_spec", generic_spec_header_source(gp), "wavenet_generic_spec.cuh",
+                                             kGenericSpecKernelSource, "NAM_B200_GSPEC_SOURCE", {},
+                                             {{"generic_desc.h", kGenericDescSource}});
+  r.ok = ck.ok;
+  r.why_not = ck.why_not;
+  r.cubin = ck.cubin;
+  r.from_cache = ck.from_cache;
+  r.compile_seconds = ck.compile_seconds;
   return r;
 }
 

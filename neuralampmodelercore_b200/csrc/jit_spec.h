@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "generic_pack.h"
 #include "wavenet_pack.h"
 
 namespace namb200
@@ -53,6 +54,11 @@ SpecBuild build_spec_kernel(const WaveNetPlan& plan, const SpecGeometry& g);
 /// lat_smem_bytes() = its dynamic shared memory.
 size_t lat_smem_bytes(const WaveNetPlan& plan, int frames);
 SpecBuild build_lat_kernel(const WaveNetPlan& plan, int frame_warps);
+
+/// The general kernel (every WaveNet option of the reference) compiled for one model: wavenet_generic_spec.cuh with the
+/// descriptors of generic_desc.h and the weights as constant data.  Entry point: wavenet_generic_spec_kernel, 128 threads.
+std::string generic_spec_header_source(const GenericPlan& gp);
+SpecBuild build_generic_spec_kernel(const GenericPlan& gp);
 
 /// The same for a small mono LSTM (lstm_spec.cuh: one thread per stream, weights as FFMA immediates); the cubin holds
 /// lstm_spec_kernel_exact and lstm_spec_kernel_fast (the fast-tanh switch is read at run time, lstm.cpp:48).

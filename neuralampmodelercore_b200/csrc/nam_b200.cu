@@ -388,6 +388,7 @@ struct nam_b200_model
   cudaKernel_t spec_short_kernel = nullptr; // its short-call entry point (8 streams x 64 frames per CTA), may be absent
   size_t spec_short_smem = 0;
   int spec_short_ctas_per_sm = 0;
+  cudaKernel_t gen_spec_kernel = nullptr; // wavenet_generic_spec.cuh: the general kernel compiled for this model
   cudaKernel_t lstm_spec_kernels[2] = {nullptr, nullptr}; // lstm_spec.cuh: exact / fast activation regime
   cudaKernel_t lstm_gate_kernels[2] = {nullptr, nullptr}; // its gate-split variant (four lanes per stream)
   // low-latency kernel (wavenet_lat.cuh): few streams x short calls; built by reset() for the handle's maxBufferSize
@@ -849,6 +850,18 @@ struct SpecKernelParams
 
 int jit_mode(const nam_b200_model* m);
 
+struct GenSpecKernelParams // mirror of namb200_gspec::GParams
+{
+  float* state;
+  long state_stride;
+  const float* in;
+  float* out;
+  long in_stride, out_stride;
+  int batch, n_frames;
+  unsigned t_base;
+};
+
+
 // Geometry of the specialised kernel for a handle of `max_batch` streams.  Streams per CTA of the short-call entry point:
 // the count that fills whole waves of 2 CTAs per SM best (4096 streams: 8 per CTA = 512 CTAs = 1.73 waves, 7 per CTA = 586 =
 // 1.98 waves).
@@ -1043,6 +1056,16 @@ void launch_wavenet_spec(nam_b200_model* m, const WaveNetKernelParams& kp, cudaS
 void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batch, int n_frames, long in_stride,
                     long out_stride, cudaStream_t st, int stream0 = 0)
 {
+  if (m->use_generic && m->gen_spec_kernel != nullptr && m->opts.kernel_geometry == 0)
+  {
+    GenSpecKernelParams sp{m->d_state + (size_t)stream0 * (size_t)m->state_stride, m->state_stride, d_in, d_out, in_stride, out_stride,
+                           batch, n_frames, m->t_base};
+    void* args[] = {&sp};
+    CUDA_CHECK(cudaLaunchKernel((const void*)m->gen_spec_kernel, dim3(std::max(1, std::min(batch, 16 * m->sm_count))), dim3(kGenTile),
+                                args, 0, st));
+    m->launches++;
+    return;
+  }
   if (m->use_generic)
   {
     GenericKernelParams gp{};
@@ -1283,6 +1306,37 @@ void setup_lstm_spec_kernel(nam_b200_model* m)
     if (mode == 1)
       throw;
   }
+}
+
+// ---- the general kernel compiled for this model (wavenet_generic_spec.cuh): same policy as the fused family's -------------
+void setup_generic_spec_kernel(nam_b200_model* m)
+{
+  const int mode = jit_mode(m);
+  if (!(mode == 1 || ((mode == 0 || mode == 3) && m->opts.max_batch >= 256)) || m->opts.kernel_geometry == 4)
+    return;
+  SpecBuild b = build_generic_spec_kernel(m->gplan);
+  auto give_up = [&](const std::string& why) {
+    if (m->spec_lib)
+      cudaLibraryUnload(m->spec_lib);
+    m->spec_lib = nullptr;
+    m->gen_spec_kernel = nullptr;
+    m->spec_state = -1;
+    m->spec_note = why;
+    if (mode == 1)
+      throw std::runtime_error("model-specialised kernel unavailable: " + why);
+  };
+  if (!b.ok)
+    return give_up(b.why_not);
+  cudaError_t e = cudaLibraryLoadData(&m->spec_lib, b.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  if (e == cudaSuccess)
+    e = cudaLibraryGetKernel(&m->gen_spec_kernel, m->spec_lib, "wavenet_generic_spec_kernel");
+  if (e != cudaSuccess)
+  {
+    cudaGetLastError();
+    return give_up(std::string("loading the specialised general kernel failed: ") + cudaGetErrorString(e));
+  }
+  m->spec_state = 1;
+  m->spec_note = std::string("general kernel, ") + (b.from_cache ? "cubin from cache" : "compiled in " + std::to_string(b.compile_seconds) + " s");
 }
 
 void launch_lstm(nam_b200_model* m, const float* d_in, float* d_out, int batch, int n_frames, long in_stride,
@@ -1662,19 +1716,8 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
             return fail(NAM_B200_ERR_UNSUPPORTED,
                         "WaveNet not supported on the CUDA path: fused kernel: "
                           + (m->plan.eligible ? std::string("(eligible)") : m->plan.why_not) + "; general kernel: " + m->gplan.why_not);
-          if (m->opts.kernel_geometry != 4)
-          {
-            // no model-specialised kernel outside the fused family: say so, loudly when it was required
-            const std::string why = "not in the fused family: " + m->plan.why_not;
-            if (jit_mode(m.get()) == 1)
-              return fail(NAM_B200_ERR_UNSUPPORTED, "model-specialised kernel unavailable: " + why);
-            if (m->opts.max_batch >= 256 && jit_mode(m.get()) != 2)
-            {
-              m->spec_state = -1;
-              m->spec_note = why;
-            }
-          }
           m->use_generic = true;
+          setup_generic_spec_kernel(m.get()); // throws when jit = 1 and the specialised general kernel cannot be had
           blob = m->gplan.weights;
           m->state_stride = m->gplan.state_floats;
           m->flops_per_frame = 2.0 * m->gplan.macs_per_frame;
@@ -2119,10 +2162,20 @@ int nam_b200_jit_prepare_json_for_batch(const char* nam_json_text, int fast_tanh
     const ModelSpec ms = model_spec_from_text(nam_json_text, lo);
     if (ms.arch != Arch::WaveNet && ms.arch != Arch::LSTM)
       return fail(NAM_B200_ERR_UNSUPPORTED, "only WaveNets and LSTMs have model-specialised kernels");
-    const SpecBuild b = ms.arch == Arch::LSTM ? build_lstm_spec_kernel(ms) : build_spec_kernel(plan_wavenet(ms), spec_geometry_for(std::max(max_batch, 1), 148));
+    SpecBuild b;
+    bool fused_family = false;
+    if (ms.arch == Arch::LSTM)
+      b = build_lstm_spec_kernel(ms);
+    else
+    {
+      const WaveNetPlan wp = plan_wavenet(ms);
+      fused_family = wp.eligible && ms.in_channels == 1 && ms.out_channels == 1;
+      b = fused_family ? build_spec_kernel(wp, spec_geometry_for(std::max(max_batch, 1), 148))
+                       : build_generic_spec_kernel(plan_generic(ms)); // every other WaveNet: the general kernel, compiled
+    }
     // WaveNets: also the low-latency kernel for 64-frame calls (the plugin protocol), so that a first Reset finds it cached
     SpecBuild lat;
-    if (ms.arch == Arch::WaveNet)
+    if (ms.arch == Arch::WaveNet && fused_family)
       lat = build_lat_kernel(plan_wavenet(ms), 2);
     std::string why;
     for (char c : b.why_not.substr(0, 600))

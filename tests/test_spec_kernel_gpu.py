@@ -134,15 +134,24 @@ def test_prewarmed_state_and_second_reset():
     d.close()
 
 
-def test_jit_required_refuses_what_it_cannot_serve():
-    """A gated / FiLM / condition_dsp WaveNet is outside the specialised kernel (it runs on the general kernel): jit=1 must
-    fail loudly, jit=0 must keep the precompiled kernel and say why."""
-    nam = fx.load_model("wavenet_a2_max")
-    with pytest.raises(Exception, match="fused family"):
-        nb.get_dsp(nam, batch=512, jit=1)
-    d = nb.get_dsp(nam, batch=512, jit=0)
-    assert d.jit_state == -1 and "fused family" in d.jit_note()
+@pytest.mark.parametrize("name", ["wavenet_a2_max", "wavenet_condition_dsp"])
+@pytest.mark.parametrize("fast", [False, True], ids=["exact_tanh", "fast_tanh"])
+def test_general_kernel_compiled_per_model(name, fast):
+    """WaveNets outside the fused family (gated / blended activations, FiLM, groups, head1x1, condition_dsp, post-stack head)
+    run on the general kernel; with jit it is compiled for the model (wavenet_generic_spec.cuh: the descriptors and weights as
+    constant data, the whole network unrolled)."""
+    nam = fx.load_model(name)
+    B, N = 70, 1500
+    x = fx.synthetic_batch(B, N, seed=19)
+    ref = _oracle_batch(nam, x, fast)
+    d = nb.get_dsp(nam, batch=B, fast_tanh=fast, jit=1)
+    assert d.jit_state == 1 and "general kernel" in d.jit_note(), d.jit_note()
+    d.Reset(48000.0, 600)
+    got = np.concatenate([d.process_batch(np.ascontiguousarray(x[:, p:p + c])) for p, c in ((0, 600), (600, 1), (601, 299), (900, 600))], axis=1)
     d.close()
+    scale = max(1.0, float(np.max(np.abs(ref))))
+    err = float(np.max(np.abs(got - ref)))
+    assert err <= TOL * scale, f"max-abs {err:.3e} (|y| up to {scale:.1f})"
 
 
 @pytest.mark.parametrize("name", ["a2_full", "a2_lite"])
