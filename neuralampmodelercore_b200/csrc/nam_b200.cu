@@ -19,6 +19,7 @@
 
 #include "nam_model_spec.h"
 #include "wavenet_fused.cuh"
+#include "wavenet_lat2.cuh"
 #include "wavenet_pack.h"
 #include "wavenet_tc.cuh"
 #include "generic_pack.h"
@@ -637,6 +638,59 @@ int occupancy_wavenet_ls_dispatch(int c0, int c1, int geom, size_t smem)
 // ---- few streams, short calls (the plugin protocol: one stream, 64-frame process() calls) ----------------------------
 // Such a call is pure latency: ~22 layer steps, each as long as ONE warp needs for its frames' instructions.  A CTA
 // of 128 threads x 1 frame (tile 128) halves the instructions per warp against the 2-frame geometries.
+// ---- low-latency kernel (wavenet_lat2.cuh): one CTA per stream, calls of up to 64 / 128 frames --------------------------
+size_t lat2_smem_bytes(const WaveNetPlan& plan, int F)
+{
+  int pmax = 0;
+  for (int a = 0; a < plan.n_arrays; a++)
+    pmax = std::max(pmax, plan.cp[a] / 4);
+  size_t f4 = (plan.blob.size() + 3) / 4 + (size_t)2 * pmax * F;
+  for (int a = 0; a < plan.n_arrays; a++)
+    for (int i = 0; i < plan.arrays[a].n_layers; i++)
+    {
+      const LayerDesc& L = plan.layers[plan.arrays[a].layer0 + i];
+      for (int k = 0; k + 1 < L.kernel; k++)
+        f4 += (size_t)(plan.cp[a] / 4) * lat2_window_cols((L.kernel - 1 - k) * L.dilation, F);
+    }
+  return f4 * 16 + kMaxLayers * sizeof(int);
+}
+bool lat2_serves(const WaveNetPlan& plan, int F)
+{
+  for (int a = 0; a < plan.n_arrays; a++)
+    if (plan.arrays[a].head_kernel != 1)
+      return false;
+  return plan.n_arrays <= 2 && lat2_smem_bytes(plan, F) <= 200 * 1024;
+}
+template <int C0, int C1>
+void launch_wavenet_lat2_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int fw, size_t smem, cudaStream_t st)
+{
+  if (fw == 2)
+  {
+    auto kern = wavenet_lat2_kernel<C0, C1, 2>;
+    ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), m->device, 200 * 1024); // (+ 520 B of static mbarriers)
+    kern<<<kp.batch, 256, smem, st>>>(kp);
+  }
+  else
+  {
+    auto kern = wavenet_lat2_kernel<C0, C1, 4>;
+    ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), m->device, 200 * 1024);
+    kern<<<kp.batch, 512, smem, st>>>(kp);
+  }
+  CUDA_CHECK(cudaGetLastError());
+}
+#define WN_LAT2_CASE(C0, C1) \
+  case (C0) * 100 + (C1): return launch_wavenet_lat2_variant<C0, C1>(m, kp, fw, smem, st);
+void launch_wavenet_lat2_dispatch(int c0, int c1, nam_b200_model* m, const WaveNetKernelParams& kp, int fw, size_t smem,
+                                  cudaStream_t st)
+{
+  switch (c0 * 100 + c1)
+  {
+    WN_LAT2_CASE(4, 0) WN_LAT2_CASE(8, 0) WN_LAT2_CASE(16, 0) WN_LAT2_CASE(4, 4) WN_LAT2_CASE(4, 8) WN_LAT2_CASE(4, 16)
+    WN_LAT2_CASE(8, 4) WN_LAT2_CASE(8, 8) WN_LAT2_CASE(8, 16) WN_LAT2_CASE(16, 4) WN_LAT2_CASE(16, 8) WN_LAT2_CASE(16, 16)
+    default: throw std::runtime_error("no low-latency WaveNet kernel for channel pair " + std::to_string(c0) + "/" + std::to_string(c1));
+  }
+}
+
 constexpr int kSmallNt = 128, kSmallLq = 7;
 template <int C0, int C1>
 void launch_wavenet_small_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem, cudaStream_t st)
@@ -1137,12 +1191,36 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
     m->launches++;
     return;
   }
-  // few streams, short calls, on a handle that has the low-latency kernel (wavenet_lat.cuh): one CTA per stream
-  if (m->lat_state == 1 && n_frames <= m->lat_frames && batch <= m->sm_count)
+  // few streams, short calls: the precompiled low-latency kernel (wavenet_lat2.cuh): one CTA per stream, the weight blob and
+  // every history window of the call brought in by bulk copies at kernel start ($NAM_B200_LAT_KERNEL=jit: prefer the
+  // model-specialised wavenet_lat.cuh where the handle has it, =off: neither)
   {
-    launch_wavenet_lat(m, kp, st);
-    m->launches++;
-    return;
+    const char* lat_env = std::getenv("NAM_B200_LAT_KERNEL"); // (read per call: tests switch it)
+    // 0: the model-specialised kernel where the handle has it (20.5 us per 64-frame call of a1_standard), else the
+    // precompiled one (29 us; the 128 x 1 geometry it replaces: 41.6); "precompiled" / "jit" / "off" pin the choice
+    const int lat_pref = !lat_env ? 0 : (std::strcmp(lat_env, "jit") == 0 ? 1 : (std::strcmp(lat_env, "off") == 0 ? 2 : (std::strcmp(lat_env, "precompiled") == 0 ? 3 : 0)));
+    const int fw = n_frames <= 64 ? 2 : 4;
+    const bool jit_lat_ok = lat_pref != 2 && lat_pref != 3 && m->lat_state == 1 && n_frames <= m->lat_frames && batch <= m->sm_count;
+    if (!jit_lat_ok && lat_pref != 1 && lat_pref != 2 && m->opts.kernel_geometry == 0 && n_frames <= 128 && batch <= m->sm_count
+        && lat2_serves(plan, 32 * fw))
+    {
+      if (batch == 1 && m->h_flag_dev != nullptr)
+      {
+        kp.done_flag = m->h_flag_dev;
+        kp.done_seq = ++m->flag_seq;
+        m->flag_pending = true;
+      }
+      launch_wavenet_lat2_dispatch(c0, c1, m, kp, fw, lat2_smem_bytes(plan, 32 * fw), st);
+      m->launches++;
+      return;
+    }
+    if (jit_lat_ok)
+    {
+      // the model-specialised variant (wavenet_lat.cuh)
+      launch_wavenet_lat(m, kp, st);
+      m->launches++;
+      return;
+    }
   }
   // short calls on many streams, specialised: nt / 64 streams x 64 frames per CTA (wavenet_spec_short_kernel)
   if (m->spec_state == 1 && m->spec_short_kernel != nullptr && m->opts.kernel_geometry == 0 && n_frames <= 64
@@ -1898,7 +1976,7 @@ int process_planar(nam_b200_model* m, const T* const* input, T* const* output, i
       float* din = m->h_pin_dev;
       float* dout = m->h_pin_dev + (hout - hin);
       m->flag_pending = false;
-      const bool doorbell = m->lat_state == 1 && m->h_flag_dev != nullptr && n_frames <= m->lat_frames && !m->opts_timing_events;
+      const bool doorbell = m->h_flag_dev != nullptr && n_frames <= 128 && !m->opts_timing_events;
       if (!doorbell)
         CUDA_CHECK(cudaEventRecord(m->ev0, m->stream));
       run_device(m, din, dout, 1, n_frames, (long)(ci * n), (long)(co * n), m->stream);
@@ -2326,6 +2404,15 @@ int nam_b200_reset(nam_b200_model* m, double sample_rate, int max_frames)
     ensure_pinned(m, (size_t)2 * max_frames * ch);
     ensure_hist(m);
     setup_lat_kernel(m);
+    if (m->spec.arch == Arch::WaveNet && !m->h_flag && m->opts.max_batch <= m->sm_count && max_frames <= 128
+        && cudaHostAlloc(&m->h_flag, 64, cudaHostAllocMapped) == cudaSuccess)
+    {
+      // completion doorbell of the low-latency kernels: DSP::process spins on this word instead of synchronising
+      *m->h_flag = 0;
+      if (cudaHostGetDevicePointer(&m->h_flag_dev, m->h_flag, 0) != cudaSuccess)
+        m->h_flag_dev = nullptr;
+    }
+    cudaGetLastError();
     // DSP::Reset = SetMaxBufferSize + prewarm (dsp.cpp:130-140).  WaveNet / ConvNet / Linear clear their buffers in
     // SetMaxBufferSize (RingBuffer::Reset, Buffer::_reset_input_buffer); the reference's LSTM overrides neither, so its
     // hidden and cell state SURVIVE a Reset and only the prewarm runs on top of it: a second Reset keeps the state here too.

@@ -85,6 +85,10 @@ struct WaveNetKernelParams
   const float* tc_blob;
   int tc_off[kMaxLayers]; // float offset of layer i's image in tc_blob
   int tc_floats[kMaxLayers]; // its size (multiple of 4)
+  // low-latency kernel (wavenet_lat2.cuh): completion doorbell, a word of mapped host memory that receives done_seq once the
+  // call's outputs are visible to the host (nullptr: none)
+  unsigned* done_flag;
+  unsigned done_seq;
 };
 
 // Layout of one layer's tensor-core image (floats), CP = padded channels (8 or 16), KS = CP/8 K-steps:

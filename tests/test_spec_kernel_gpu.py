@@ -241,8 +241,10 @@ def test_lstm_spec_refuses_large_cells_loudly():
 
 # ---- the low-latency kernel (csrc/wavenet_lat.cuh): few streams, short calls --------------------------------------------
 @pytest.mark.parametrize("fast", [False, True], ids=["exact_tanh", "fast_tanh"])
-def test_lat_kernel_plugin_protocol(fast):
-    """One stream, Reset(sr, 64), 64-frame process() calls (tools/benchmodel.cpp:116-133) on the low-latency kernel."""
+def test_lat_kernel_plugin_protocol(fast, monkeypatch):
+    """One stream, Reset(sr, 64), 64-frame process() calls (tools/benchmodel.cpp:116-133) on the model-specialised
+    low-latency kernel (NAM_B200_LAT_KERNEL=jit: by default the precompiled wavenet_lat2.cuh takes these calls)."""
+    monkeypatch.setenv("NAM_B200_LAT_KERNEL", "jit")
     nam = fx.load_model("wavenet_a1_standard")
     x = fx.synthetic_batch(1, 64 * 40, seed=21)
     ref = _oracle_batch(nam, x, fast)
@@ -257,9 +259,11 @@ def test_lat_kernel_plugin_protocol(fast):
     assert err <= TOL, f"max-abs {err:.3e}"
 
 
-def test_lat_kernel_irregular_short_calls_several_streams_and_mixing():
-    """5 streams; call lengths 1..128 (a 128-frame handle: 4 frame warps), odd lengths, and a long call in between that the
+@pytest.mark.parametrize("which", ["jit", "precompiled"])
+def test_lat_kernel_irregular_short_calls_several_streams_and_mixing(which, monkeypatch):
+    """Both low-latency kernels (wavenet_lat.cuh compiled per model / wavenet_lat2.cuh precompiled).  5 streams; call lengths 1..128 (a 128-frame handle: 4 frame warps), odd lengths, and a long call in between that the
     precompiled kernels serve on the same rings."""
+    monkeypatch.setenv("NAM_B200_LAT_KERNEL", which)
     nam = fx.load_model("wavenet_a1_standard")
     chunks = [64, 1, 17, 128, 63, 100, 2, 127, 64, 33]
     N = sum(chunks)
@@ -290,7 +294,10 @@ def test_lat_kernel_irregular_short_calls_several_streams_and_mixing():
     dict(channels=(4, 16), kernel_size=3, dilations=[[1, 2], [3, 100, 341]], activation={"type": "PReLU", "negative_slopes": [0.02 * (i + 1) for i in range(16)]}),
     dict(channels=(12,), kernel_size=3, dilations=[[1, 2, 40]], activation="Sigmoid"),
 ], ids=["a1_like", "kernels_1_to_5", "prelu_slices", "single_padded_array"])
-def test_lat_kernel_shape_family(case):
+@pytest.mark.parametrize("which", ["jit", "precompiled"])
+def test_lat_kernel_shape_family(case, which, monkeypatch):
+    monkeypatch.setenv("NAM_B200_LAT_KERNEL", which)
+    case = dict(case)
     act = case.pop("activation")
     if isinstance(act, dict) and act["type"] == "PReLU":
         # per-array slope counts differ: use a shared slope list sized for the widest array only where it applies
