@@ -587,7 +587,7 @@ def run_b200(args) -> None:
                    "note": "kernel uses the FP32 FMA pipe, not tensor cores (1e-5 parity forbids TF32/BF16 operands)"},
     }
     # DRAM bytes of one launch from the committed ncu --set full capture of this command's default shape
-    prof = ROOT / "profiles" / "r01_traffic.json"
+    prof = ROOT / "profiles" / ("r02_traffic.json" if jit_state == 1 else "r01_traffic.json")
     if prof.exists() and args.model == MODEL and (B, n) == (4096, 4096) and args.geometry == 0 and fast:
         try:
             t = json.loads(prof.read_text())
