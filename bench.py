@@ -459,6 +459,9 @@ def run_b200(args) -> None:
                 dist.all_gather_into_tensor(gathered[b].view(-1), y2[b].view(-1))
                 done[b].record(side)
 
+        # The collective finds its SMs in the last, partly filled round of the persistent kernel (4096 streams over 296 CTAs =
+        # 13.8 rounds: 24 SMs idle for the last ~0.7 ms of a step).  Reserving SMs for it outright (nam_b200_set_reserved_sms)
+        # was measured and costs a whole extra round (4 SMs: 288 CTAs -> 15 rounds, +8 %), so none are reserved here.
         for i in range(max(args.warmup, NB)):
             step_with_gather(i)
         barrier()
@@ -487,8 +490,10 @@ def run_b200(args) -> None:
                   "busbw_GBs": y_dev.numel() * 4 * (world - 1) / (gms * 1e-3) / 1e9,
                   "step_ms_with_gather_overlapped": with_ms, "step_ms_without": total_ms_max / args.steps,
                   "hidden_fraction": max(0.0, 1.0 - (with_ms - total_ms_max / args.steps) / gms) if gms > 0 else None,
+                  "reserved_sms": 0,
                   "what": "ncclAllGather (torch.distributed all_gather_into_tensor) of each rank's outputs on a side "
-                          "stream, overlapped with the next step's kernel; every rank ends up with all N x batch streams"}
+                          "stream, overlapped with the next steps' kernels (three output buffers; it runs on the SMs the last, "
+                          "partly filled round of the persistent kernel leaves idle); every rank ends up with all N x batch streams"}
         # the gathered block really holds every rank's outputs
         torch.cuda.synchronize()
         assert torch.equal(gathered[(args.steps - 1) % NB][rank], y2[(args.steps - 1) % NB])

@@ -161,6 +161,13 @@ int nam_b200_multi_process_f32(nam_b200_multi* mm, const float* in, float* out, 
 int nam_b200_process_f64_planar(nam_b200_model* m, const double* const* input, double* const* output, int n_frames);
 int nam_b200_process_f32_planar(nam_b200_model* m, const float* const* input, float* const* output, int n_frames);
 
+/* The persistent WaveNet throughput kernels occupy every SM for a whole call, so a concurrent kernel on another stream (an NCCL
+ * collective gathering the previous call's outputs, say) only starts when they drain.  Leaving `n_sms` SMs free (0 = none,
+ * the default) lets such work overlap the call.  The price is
+ * quantised: the streams are walked in rounds of (CTAs per SM) x (SMs left), so check that the batch does not need one more
+ * round (4096 streams, 2 CTAs per SM: 14 rounds on 147 or 148 SMs, 15 on 146 or fewer). */
+int nam_b200_set_reserved_sms(nam_b200_model* m, int n_sms);
+
 /* LSTM reads the fast-tanh switch at run time (NAM/lstm.cpp:48); WaveNet captured it at load. */
 int nam_b200_set_fast_tanh(nam_b200_model* m, int enabled);
 

@@ -68,6 +68,7 @@ EXPORTED_SYMBOLS = [
     "nam_b200_process_f64_planar",
     "nam_b200_process_f32_planar",
     "nam_b200_set_fast_tanh",
+    "nam_b200_set_reserved_sms",
     "nam_b200_set_slimmable_size",
     "nam_b200_slimmable_breakpoints",
     "nam_b200_synchronize",
@@ -129,6 +130,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.nam_b200_process_f64_planar.argtypes = [vp, C.POINTER(f64p), C.POINTER(f64p), C.c_int]
     lib.nam_b200_process_f32_planar.argtypes = [vp, C.POINTER(f32p), C.POINTER(f32p), C.c_int]
     lib.nam_b200_set_fast_tanh.argtypes = [vp, C.c_int]
+    lib.nam_b200_set_reserved_sms.argtypes = [vp, C.c_int]
     lib.nam_b200_set_slimmable_size.argtypes = [vp, C.c_double]
     lib.nam_b200_slimmable_breakpoints.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
     lib.nam_b200_synchronize.argtypes = [vp]
@@ -173,6 +175,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         "nam_b200_process_f64_planar",
         "nam_b200_process_f32_planar",
         "nam_b200_set_fast_tanh",
+        "nam_b200_set_reserved_sms",
         "nam_b200_set_slimmable_size",
         "nam_b200_slimmable_breakpoints",
         "nam_b200_synchronize",

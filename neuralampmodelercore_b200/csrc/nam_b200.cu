@@ -366,6 +366,7 @@ struct nam_b200_model
   int64_t launches = 0;
   int max_frames = 0;
   bool is_reset = false;
+  int reserved_sms = 0; // SMs the persistent throughput kernels leave free (nam_b200_set_reserved_sms)
   bool streams_identical = true; // every stream holds the same state (true after init_state, false once audio was processed)
   bool state_initialised = false; // init_state() has run at least once
   uint32_t t_base = 0;
@@ -1101,7 +1102,7 @@ void launch_wavenet_spec(nam_b200_model* m, const WaveNetKernelParams& kp, cudaS
   SpecKernelParams sp{kp.state, kp.state_stride, kp.in,  kp.out, kp.in_stride, kp.out_stride,
                       kp.batch, kp.n_frames,     kp.t_base, nullptr, 0};
   void* args[] = {&sp};
-  int grid = std::min(kp.batch, m->spec_ctas_per_sm * m->sm_count);
+  int grid = std::min(kp.batch, m->spec_ctas_per_sm * std::max(1, m->sm_count - m->reserved_sms));
   if (grid < 1)
     grid = 1;
   CUDA_CHECK(cudaLaunchKernel((const void*)m->spec_kernel, dim3(grid), dim3(m->spec_geom.nt), args, m->spec_smem, st));
@@ -1328,7 +1329,7 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
     m->launches++;
     return;
   }
-  int grid = std::min(batch, per_sm * m->sm_count);
+  int grid = std::min(batch, per_sm * std::max(1, m->sm_count - m->reserved_sms));
   if (grid < 1)
     grid = 1;
   launch_wavenet_dispatch(c0, c1, geom, m, kp, grid, smem, st);
@@ -2699,6 +2700,16 @@ int nam_b200_process_f32_planar(nam_b200_model* m, const float* const* input, fl
 int nam_b200_process_f64_planar(nam_b200_model* m, const double* const* input, double* const* output, int n_frames)
 {
   return process_planar<double>(m, input, output, n_frames);
+}
+
+int nam_b200_set_reserved_sms(nam_b200_model* m, int n_sms)
+{
+  if (!m || n_sms < 0)
+    return fail(NAM_B200_ERR_INVALID_ARGUMENT, "null model handle or negative count");
+  m->reserved_sms = n_sms;
+  for (auto& sub : m->subs)
+    sub->reserved_sms = n_sms;
+  return NAM_B200_OK;
 }
 
 int nam_b200_set_fast_tanh(nam_b200_model* m, int enabled)

@@ -208,6 +208,12 @@ class DSP:
         if rc != 0:
             _raise(rc, self._lib)
 
+    def set_reserved_sms(self, n_sms: int) -> None:
+        """Leave n_sms SMs free for concurrent kernels (e.g. an NCCL collective) during the persistent WaveNet kernels."""
+        rc = self._lib.nam_b200_set_reserved_sms(self._h, int(n_sms))
+        if rc != 0:
+            _raise(rc, self._lib)
+
     def set_fast_tanh(self, enabled: bool) -> None:
         """LSTM reads the switch at run time (NAM/lstm.cpp:48)."""
         self._lib.nam_b200_set_fast_tanh(self._h, int(bool(enabled)))

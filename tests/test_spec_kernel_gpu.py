@@ -333,3 +333,23 @@ def test_short_call_variant_many_streams():
     d.close()
     err = float(np.max(np.abs(np.concatenate(out, axis=1) - ref)))
     assert err <= TOL, f"max-abs {err:.3e}"
+
+
+def test_reserved_sms_change_the_grid_not_the_result():
+    """nam_b200_set_reserved_sms: the persistent kernels walk the streams with fewer CTAs; same outputs bit for bit, and the
+    setting can change between calls on live rings."""
+    nam = fx.load_model("wavenet_a1_standard")
+    B, N = 700, 1024  # more streams than CTAs, so the stride of the persistent loop really changes
+    x = fx.synthetic_batch(B, 2 * N, seed=23)
+    d = _spec(nam, B, True)
+    d.Reset(48000.0, N)
+    a = np.concatenate([d.process_batch(x[:, :N]), d.process_batch(x[:, N:])], axis=1)
+    d.Reset(48000.0, N)
+    d.set_reserved_sms(8)
+    b0 = d.process_batch(x[:, :N])
+    d.set_reserved_sms(147)
+    b1 = d.process_batch(x[:, N:])
+    assert np.array_equal(a, np.concatenate([b0, b1], axis=1))
+    with pytest.raises(Exception):
+        d.set_reserved_sms(-1)
+    d.close()
