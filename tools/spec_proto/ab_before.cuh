@@ -785,110 +785,9 @@ __device__ __forceinline__ void wavenet_spec_body(const SpecParams& p)
 // tile (32 KB) and 32 warps per SM hide the ring loads.  History is NOT staged: a tap that reaches before the call reads
 // its ring column directly (16 bytes per thread, consecutive frames = consecutive addresses), one that stays inside the
 // call reads the tile.  Same rings as every other kernel.
-//
-// Two things decide this kernel (profiles/r02t_*: a launch is only two passes through ~260 KB of straight-line code, and
-// the 0.5 GB of ring traffic between two launches had pushed that code out of L2, so one pass in two fetched its
-// instructions from HBM -- `no_instruction` 7.3 cycles per issued instruction against 2.1 in the long-call kernel):
-//  * ring loads / stores carry an L2 evict-first policy, so the code (and nothing else is reused) stays L2-resident;
-//  * each warp prefetches the NEXT layer's ring windows into L2 (one `prefetch.global.L2` per lane) while it computes
-//    this one, so the tap loads meet L2 latency instead of HBM latency.
-#ifndef NAMB200_SHORT_HINT
-#define NAMB200_SHORT_HINT 1
-#endif
-#ifndef NAMB200_SHORT_PREFETCH
-#define NAMB200_SHORT_PREFETCH 0
-#endif
-
-__device__ __forceinline__ unsigned long long l2_evict_first_policy()
-{
-  unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-
-__device__ __forceinline__ float4 ring_load(const float4* a, const unsigned long long pol)
-{
-#if NAMB200_SHORT_HINT
-  float4 v;
-  asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(a), "l"(pol));
-  return v;
-#else
-  return __ldcg(a);
-#endif
-}
-
-__device__ __forceinline__ void ring_store(float4* a, const float4 v, const unsigned long long pol)
-{
-#if NAMB200_SHORT_HINT
-  asm volatile("st.global.cg.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
-               "l"(pol)
-               : "memory");
-#else
-  __stcg(a, v);
-#endif
-}
-
-// L2 prefetch of the ring windows layer LJ will read for this warp's 32 frames: (K - 1) history taps x P planes x 4 lines
-// of 8 columns; one line per lane (two rounds when there are more).  Lines are taken from the 8-column-aligned start, which
-// is exact whenever call start and dilation are multiples of 8 (the usual case); otherwise the last partial line is left out.
-template <int LJ, int FQ>
-__device__ __forceinline__ void prefetch_ring_windows(const float* state, const unsigned long long pol, const u32 tabs0, const int f)
-{
-#if NAMB200_SHORT_PREFETCH == 2
-  // bulk form: one lane per (tap, plane), up to 512 contiguous bytes (two pieces where the window wraps), evict-first like
-  // the loads that follow
-  constexpr spec::Layer Ld = spec::L[LJ];
-  constexpr int K = Ld.K, dil = Ld.dil, R = Ld.ring_mask + 1;
-  constexpr int C = spec::layer_channels(LJ), P = C / 4;
-  if constexpr (K > 1 && R >= 32)
-  {
-    const int lane = f & 31, fw = f & ~31;
-    const int tap = lane / P, pl = lane % P;
-    const int off = (K - 1 - tap) * dil;
-    if (lane < (K - 1) * P && fw < off)
-    {
-      const float4* const ring = reinterpret_cast<const float4*>(state + Ld.ring_off) + pl * R;
-      const int n_cols = min(32, off - fw);
-      const int s0 = (int)((tabs0 + (u32)fw - (u32)off) & (u32)Ld.ring_mask);
-      const int first = min(n_cols, R - s0);
-      asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(ring + s0), "r"(first * 16), "l"(pol)
-                   : "memory");
-      if (first < n_cols)
-        asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(ring), "r"((n_cols - first) * 16),
-                     "l"(pol)
-                     : "memory");
-    }
-  }
-#elif NAMB200_SHORT_PREFETCH == 1
-  constexpr spec::Layer Ld = spec::L[LJ];
-  constexpr int K = Ld.K, dil = Ld.dil, R = Ld.ring_mask + 1;
-  constexpr int C = spec::layer_channels(LJ), P = C / 4;
-  if constexpr (K > 1 && R >= 32)
-  {
-    constexpr int TOTAL = (K - 1) * P * 4;
-    const int lane = f & 31, fw = f & ~31;
-    const float4* const ring = reinterpret_cast<const float4*>(state + Ld.ring_off);
-#pragma unroll
-    for (int base = 0; base < TOTAL; base += 32)
-    {
-      const int idx = base + lane;
-      const int tap = idx / (P * 4), pl = (idx >> 2) % P, qtr = idx & 3;
-      const int off = (K - 1 - tap) * dil;
-      if (idx < TOTAL && fw < off)
-      {
-        const u32 col = ((tabs0 + (u32)(fw + 8 * qtr) - (u32)off) & (u32)Ld.ring_mask) & ~7u;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ring + pl * R + col));
-      }
-    }
-  }
-#endif
-}
-
 template <int AI, int NEXT_AI, int NT, int FQ>
-__device__ __forceinline__ void array_forward_short(float4* tile, float* state, const unsigned long long pol, const u32 tabs0,
-                                                    const int n, const int f, const bool live, const float (&hin)[spec::A[AI].CIN], const float cond,
+__device__ __forceinline__ void array_forward_short(float4* tile, float* state, const u32 tabs0, const int n, const int f,
+                                                    const bool live, const float (&hin)[spec::A[AI].CIN], const float cond,
                                                     float (&head)[spec::A[AI].C], float (&hout)[spec::A[AI].C],
                                                     float (&headout)[spec::A[AI].HOUT])
 {
@@ -898,8 +797,6 @@ __device__ __forceinline__ void array_forward_short(float4* tile, float* state, 
   static_assert(A.head_kernel == 1, "convolutional heads take the precompiled short-call geometry");
   float4* const col0 = tile + threadIdx.x;
 
-  if constexpr (AI == 0)
-    prefetch_ring_windows<A.layer0, FQ>(state, pol, tabs0, f);
   {
     float h[C];
 #pragma unroll
@@ -925,10 +822,6 @@ __device__ __forceinline__ void array_forward_short(float4* tile, float* state, 
     const float4* const ring = reinterpret_cast<const float4*>(state + Ld.ring_off);
 
     __syncthreads(); // B0: the layer input is complete in the tile
-    if constexpr (!last)
-      prefetch_ring_windows<LI + 1, FQ>(state, pol, tabs0, f);
-    else if constexpr (NEXT_AI >= 0)
-      prefetch_ring_windows<spec::A[NEXT_AI >= 0 ? NEXT_AI : 0].layer0, FQ>(state, pol, tabs0, f);
     float acc[C];
 #pragma unroll
     for (int o = 0; o < C; o++)
@@ -943,7 +836,7 @@ __device__ __forceinline__ void array_forward_short(float4* tile, float* state, 
       {
         float4 q;
         if (from_ring)
-          q = ring_load(ring + pl * R + rcol, pol);
+          q = __ldcg(ring + pl * R + rcol);
         else
           q = col0[pl * W - off];
         const float x[4] = {q.x, q.y, q.z, q.w};
@@ -968,7 +861,7 @@ __device__ __forceinline__ void array_forward_short(float4* tile, float* state, 
       // RingBuffer::Write: the call's last `look-back` columns of the layer input (ring loads of this layer are done:
       // they fed the FMAs above, and the barrier ordered every thread's loads before anybody's stores)
       if (live && f < n && f >= n - L)
-        ring_store(reinterpret_cast<float4*>(state + Ld.ring_off) + pl * R + ((tabs0 + (u32)f) & (u32)Ld.ring_mask), own, pol);
+        __stcg(reinterpret_cast<float4*>(state + Ld.ring_off) + pl * R + ((tabs0 + (u32)f) & (u32)Ld.ring_mask), own);
       hn[4 * pl] = own.x + spec::w(w_pb + 4 * pl);
       hn[4 * pl + 1] = own.y + spec::w(w_pb + 4 * pl + 1);
       hn[4 * pl + 2] = own.z + spec::w(w_pb + 4 * pl + 2);
@@ -1014,7 +907,6 @@ __device__ __forceinline__ void wavenet_spec_short_body(const SpecParams& p)
   extern __shared__ float4 spec_smem[]; // [planes][NT]
   const int tid = threadIdx.x;
   const int f = tid % FQ, q = tid / FQ;
-  const unsigned long long pol = l2_evict_first_policy();
   for (int slot = blockIdx.x; slot * Q < p.batch; slot += gridDim.x)
   {
     const int stream = slot * Q + q;
@@ -1029,7 +921,7 @@ __device__ __forceinline__ void wavenet_spec_short_body(const SpecParams& p)
     for (int o = 0; o < C0; o++)
       head0[o] = 0.0f;
     float y;
-    array_forward_short<0, spec::NA - 1, NT, FQ>(spec_smem, state, pol, p.t_base, p.n_frames, f, live, x, xv, head0, hout0, ho0);
+    array_forward_short<0, spec::NA - 1, NT, FQ>(spec_smem, state, p.t_base, p.n_frames, f, live, x, xv, head0, hout0, ho0);
     if constexpr (spec::NA == 1)
       y = ho0[0];
     else
@@ -1041,7 +933,7 @@ __device__ __forceinline__ void wavenet_spec_short_body(const SpecParams& p)
       for (int o = 0; o < C1; o++)
         head1[o] = ho0[o];
       __syncthreads(); // (the last layer's tap reads are fenced by its B1; this orders the rechannel's tile stores too)
-      array_forward_short<AI1, -1, NT, FQ>(spec_smem, state, pol, p.t_base, p.n_frames, f, live, hout0, xv, head1, hout1, ho1);
+      array_forward_short<AI1, -1, NT, FQ>(spec_smem, state, p.t_base, p.n_frames, f, live, hout0, xv, head1, hout1, ho1);
       y = ho1[0];
     }
     if (live && f < p.n_frames)

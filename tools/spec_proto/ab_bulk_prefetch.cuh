@@ -796,7 +796,7 @@ __device__ __forceinline__ void wavenet_spec_body(const SpecParams& p)
 #define NAMB200_SHORT_HINT 1
 #endif
 #ifndef NAMB200_SHORT_PREFETCH
-#define NAMB200_SHORT_PREFETCH 0
+#define NAMB200_SHORT_PREFETCH 2
 #endif
 
 __device__ __forceinline__ unsigned long long l2_evict_first_policy()

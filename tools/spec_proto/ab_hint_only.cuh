@@ -834,34 +834,9 @@ __device__ __forceinline__ void ring_store(float4* a, const float4 v, const unsi
 // of 8 columns; one line per lane (two rounds when there are more).  Lines are taken from the 8-column-aligned start, which
 // is exact whenever call start and dilation are multiples of 8 (the usual case); otherwise the last partial line is left out.
 template <int LJ, int FQ>
-__device__ __forceinline__ void prefetch_ring_windows(const float* state, const unsigned long long pol, const u32 tabs0, const int f)
+__device__ __forceinline__ void prefetch_ring_windows(const float* state, const u32 tabs0, const int f)
 {
-#if NAMB200_SHORT_PREFETCH == 2
-  // bulk form: one lane per (tap, plane), up to 512 contiguous bytes (two pieces where the window wraps), evict-first like
-  // the loads that follow
-  constexpr spec::Layer Ld = spec::L[LJ];
-  constexpr int K = Ld.K, dil = Ld.dil, R = Ld.ring_mask + 1;
-  constexpr int C = spec::layer_channels(LJ), P = C / 4;
-  if constexpr (K > 1 && R >= 32)
-  {
-    const int lane = f & 31, fw = f & ~31;
-    const int tap = lane / P, pl = lane % P;
-    const int off = (K - 1 - tap) * dil;
-    if (lane < (K - 1) * P && fw < off)
-    {
-      const float4* const ring = reinterpret_cast<const float4*>(state + Ld.ring_off) + pl * R;
-      const int n_cols = min(32, off - fw);
-      const int s0 = (int)((tabs0 + (u32)fw - (u32)off) & (u32)Ld.ring_mask);
-      const int first = min(n_cols, R - s0);
-      asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(ring + s0), "r"(first * 16), "l"(pol)
-                   : "memory");
-      if (first < n_cols)
-        asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(ring), "r"((n_cols - first) * 16),
-                     "l"(pol)
-                     : "memory");
-    }
-  }
-#elif NAMB200_SHORT_PREFETCH == 1
+#if NAMB200_SHORT_PREFETCH
   constexpr spec::Layer Ld = spec::L[LJ];
   constexpr int K = Ld.K, dil = Ld.dil, R = Ld.ring_mask + 1;
   constexpr int C = spec::layer_channels(LJ), P = C / 4;
@@ -899,7 +874,7 @@ __device__ __forceinline__ void array_forward_short(float4* tile, float* state, 
   float4* const col0 = tile + threadIdx.x;
 
   if constexpr (AI == 0)
-    prefetch_ring_windows<A.layer0, FQ>(state, pol, tabs0, f);
+    prefetch_ring_windows<A.layer0, FQ>(state, tabs0, f);
   {
     float h[C];
 #pragma unroll
@@ -926,9 +901,9 @@ __device__ __forceinline__ void array_forward_short(float4* tile, float* state, 
 
     __syncthreads(); // B0: the layer input is complete in the tile
     if constexpr (!last)
-      prefetch_ring_windows<LI + 1, FQ>(state, pol, tabs0, f);
+      prefetch_ring_windows<LI + 1, FQ>(state, tabs0, f);
     else if constexpr (NEXT_AI >= 0)
-      prefetch_ring_windows<spec::A[NEXT_AI >= 0 ? NEXT_AI : 0].layer0, FQ>(state, pol, tabs0, f);
+      prefetch_ring_windows<spec::A[NEXT_AI >= 0 ? NEXT_AI : 0].layer0, FQ>(state, tabs0, f);
     float acc[C];
 #pragma unroll
     for (int o = 0; o < C; o++)
