@@ -377,6 +377,8 @@ SpecBuild build_spec_kernel(const WaveNetPlan& plan, const SpecGeometry& g)
   {
     defs.push_back("-DNAMB200_SPEC_SHORT_FQ=64");
     defs.push_back("-DNAMB200_SPEC_SHORT_NT=" + std::to_string(64 * g.short_streams));
+    defs.push_back("-DNAMB200_SPEC_SHORT128_NT=" + std::to_string(128 * g.short128_streams));
+    defs.push_back("-DNAMB200_SPEC_SHORT256_NT=" + std::to_string(256 * g.short256_streams));
   }
   const CompiledKernel ck = compile_or_fetch("wavenet_spec", header, "wavenet_spec.cuh", kSpecKernelSource, "NAM_B200_SPEC_SOURCE", defs);
   r.ok = ck.ok;

@@ -22,6 +22,7 @@ struct SpecGeometry
   int s = 1; // frames per thread
   int min_ctas = 2; // __launch_bounds__ second argument
   int short_streams = 8; // streams per CTA of the short-call entry point (64 frames each)
+  int short128_streams = 4, short256_streams = 2; // ... of the entry points for calls of up to 128 / 256 frames
   int tile() const { return nt * s; }
 };
 
@@ -34,7 +35,7 @@ struct SpecBuild
   int staged_cols = 0; // spec::LS: columns of history staged in front of the tile (max look-back of the model)
   int max_planes = 0; // widest array, in planes of 4 channels
   bool from_cache = false;
-  bool has_short = false; // the cubin also holds wavenet_spec_short_kernel (geom.nt / 64 streams x 64 frames per CTA)
+  bool has_short = false; // the cubin also holds wavenet_spec_short{,128,256}_kernel (several streams x 64 / 128 / 256 frames per CTA)
   double compile_seconds = 0.0;
   size_t smem_bytes() const { return (size_t)max_planes * (size_t)(staged_cols + geom.tile()) * 16; }
 };

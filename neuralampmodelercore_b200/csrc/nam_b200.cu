@@ -387,9 +387,12 @@ struct nam_b200_model
   // model-specialised kernel (wavenet_spec.cuh compiled for this model by NVRTC, jit_spec.cpp): the throughput path
   cudaLibrary_t spec_lib = nullptr;
   cudaKernel_t spec_kernel = nullptr;
-  cudaKernel_t spec_short_kernel = nullptr; // its short-call entry point (8 streams x 64 frames per CTA), may be absent
-  size_t spec_short_smem = 0;
-  int spec_short_ctas_per_sm = 0;
+  struct SpecShort // its short-call entry points (q streams x fq frames per CTA; fq = 64, 128, 256), may be absent
+  {
+    cudaKernel_t kernel = nullptr;
+    size_t smem = 0;
+    int ctas_per_sm = 0, fq = 0, q = 0;
+  } spec_short[3];
   cudaKernel_t gen_spec_kernel = nullptr; // wavenet_generic_spec.cuh: the general kernel compiled for this model
   cudaKernel_t lstm_spec_kernels[2] = {nullptr, nullptr}; // lstm_spec.cuh: exact / fast activation regime
   cudaKernel_t lstm_gate_kernels[2] = {nullptr, nullptr}; // its gate-split variant (four lanes per stream)
@@ -924,16 +927,22 @@ SpecGeometry spec_geometry_for(int max_batch, int sm_count)
 {
   SpecGeometry g;
   double best = -1.0;
-  for (int q : {8, 7, 6})
-  {
-    const double slots = (max_batch + q - 1) / q, resident = 2.0 * sm_count;
-    const double eff = slots / (std::ceil(slots / resident) * resident);
-    if (eff > best + 0.02)
+  auto pick = [&](std::initializer_list<int> candidates, int& streams) {
+    best = -1.0;
+    for (int q : candidates)
     {
-      best = eff;
-      g.short_streams = q;
+      const double slots = (max_batch + q - 1) / q, resident = 2.0 * sm_count;
+      const double eff = slots / (std::ceil(slots / resident) * resident);
+      if (eff > best + 0.02)
+      {
+        best = eff;
+        streams = q;
+      }
     }
-  }
+  };
+  pick({8, 7, 6}, g.short_streams);
+  pick({4, 3}, g.short128_streams);
+  g.short256_streams = 2;
   return g;
 }
 
@@ -974,17 +983,28 @@ void setup_spec_kernel(nam_b200_model* m)
     if (occ < 1)
       throw CudaError("the specialised kernel does not fit on an SM");
     m->spec_ctas_per_sm = occ;
-    if (b.has_short && cudaLibraryGetKernel(&m->spec_short_kernel, m->spec_lib, "wavenet_spec_short_kernel") == cudaSuccess)
+    if (b.has_short)
     {
-      m->spec_short_smem = (size_t)b.max_planes * 64 * b.geom.short_streams * 16;
-      int occ_s = 0;
-      if (cudaFuncSetAttribute((const void*)m->spec_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)m->spec_short_smem) != cudaSuccess
-          || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, (const void*)m->spec_short_kernel, 64 * b.geom.short_streams,
-                                                           m->spec_short_smem) != cudaSuccess
-          || occ_s < 1)
-        m->spec_short_kernel = nullptr;
-      m->spec_short_ctas_per_sm = occ_s;
+      const char* const names[3] = {"wavenet_spec_short_kernel", "wavenet_spec_short128_kernel", "wavenet_spec_short256_kernel"};
+      const int fqs[3] = {64, 128, 256}, qs[3] = {b.geom.short_streams, b.geom.short128_streams, b.geom.short256_streams};
+      for (int v = 0; v < 3; v++)
+      {
+        nam_b200_model::SpecShort& sv = m->spec_short[v];
+        sv = nam_b200_model::SpecShort{};
+        if (cudaLibraryGetKernel(&sv.kernel, m->spec_lib, names[v]) != cudaSuccess)
+        {
+          sv.kernel = nullptr;
+          continue;
+        }
+        sv.fq = fqs[v];
+        sv.q = qs[v];
+        sv.smem = (size_t)b.max_planes * sv.fq * sv.q * 16;
+        if (cudaFuncSetAttribute((const void*)sv.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sv.smem) != cudaSuccess
+            || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sv.ctas_per_sm, (const void*)sv.kernel, sv.fq * sv.q, sv.smem)
+                 != cudaSuccess
+            || sv.ctas_per_sm < 1)
+          sv.kernel = nullptr;
+      }
     }
     cudaGetLastError();
     m->spec_state = 1;
@@ -1223,20 +1243,24 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
       return;
     }
   }
-  // short calls on many streams, specialised: nt / 64 streams x 64 frames per CTA (wavenet_spec_short_kernel)
-  if (m->spec_state == 1 && m->spec_short_kernel != nullptr && m->opts.kernel_geometry == 0 && n_frames <= 64
-      && batch >= 2 * m->spec_geom.short_streams)
-  {
-    SpecKernelParams sp{kp.state, kp.state_stride, kp.in,  kp.out, kp.in_stride, kp.out_stride,
-                        kp.batch, kp.n_frames,     kp.t_base, nullptr, 0};
-    void* args[] = {&sp};
-    const int q = m->spec_geom.short_streams;
-    const int grid_s = std::max(1, std::min((batch + q - 1) / q, m->spec_short_ctas_per_sm * m->sm_count));
-    CUDA_CHECK(cudaLaunchKernel((const void*)m->spec_short_kernel, dim3(grid_s), dim3(64 * q), args,
-                                m->spec_short_smem, st));
-    m->launches++;
-    return;
-  }
+  // short calls on many streams, specialised: q streams x 64 / 128 / 256 frames per CTA (wavenet_spec_short*_kernel)
+  if (m->spec_state == 1 && m->opts.kernel_geometry == 0 && n_frames <= 256)
+    for (const nam_b200_model::SpecShort& sv : m->spec_short)
+    {
+      if (n_frames > sv.fq)
+        continue;
+      if (sv.kernel == nullptr || batch < 2 * sv.q)
+        break; // the smallest variant that holds the call, or none
+      {
+        SpecKernelParams sp{kp.state, kp.state_stride, kp.in,  kp.out, kp.in_stride, kp.out_stride,
+                            kp.batch, kp.n_frames,     kp.t_base, nullptr, 0};
+        void* args[] = {&sp};
+        const int grid_s = std::max(1, std::min((batch + sv.q - 1) / sv.q, sv.ctas_per_sm * m->sm_count));
+        CUDA_CHECK(cudaLaunchKernel((const void*)sv.kernel, dim3(grid_s), dim3(sv.fq * sv.q), args, sv.smem, st));
+        m->launches++;
+        return;
+      }
+    }
   // short calls on more than a handful of streams: several streams per tile (same rings, same arithmetic)
   for (int sg = 0; sg < 2; sg++)
   {

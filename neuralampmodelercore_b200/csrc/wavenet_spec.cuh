@@ -1079,4 +1079,19 @@ extern "C" __global__ void __launch_bounds__(NAMB200_SPEC_SHORT_NT, 2)
   namb200_spec::wavenet_spec_short_body<NAMB200_SPEC_SHORT_NT, NAMB200_SPEC_SHORT_FQ>(p);
 }
 #endif
+// the same for calls of up to 128 / 256 frames (hosts with larger audio buffers): NT / 128 and NT / 256 streams per CTA
+#ifdef NAMB200_SPEC_SHORT128_NT
+extern "C" __global__ void __launch_bounds__(NAMB200_SPEC_SHORT128_NT, 2)
+  wavenet_spec_short128_kernel(const __grid_constant__ namb200_spec::SpecParams p)
+{
+  namb200_spec::wavenet_spec_short_body<NAMB200_SPEC_SHORT128_NT, 128>(p);
+}
+#endif
+#ifdef NAMB200_SPEC_SHORT256_NT
+extern "C" __global__ void __launch_bounds__(NAMB200_SPEC_SHORT256_NT, 2)
+  wavenet_spec_short256_kernel(const __grid_constant__ namb200_spec::SpecParams p)
+{
+  namb200_spec::wavenet_spec_short_body<NAMB200_SPEC_SHORT256_NT, 256>(p);
+}
+#endif
 #endif // NAMB200_SPEC_NO_KERNEL

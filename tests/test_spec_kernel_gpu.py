@@ -335,6 +335,30 @@ def test_short_call_variant_many_streams():
     assert err <= TOL, f"max-abs {err:.3e}"
 
 
+@pytest.mark.parametrize("name", ["wavenet_a1_standard", "wavenet"])
+def test_short_call_variants_for_128_and_256_frame_calls(name):
+    """Calls of 65..128 and 129..256 frames take the 128- / 256-frame entry points (3-4 / 2 streams per CTA); mixed with 64-frame
+    and long calls on the same rings, odd lengths, a stream count that leaves the last CTA partly empty; one launch per call."""
+    nam = fx.load_model(name)
+    chunks = [128, 128, 100, 65, 256, 256, 129, 200, 64, 128, 1000, 256, 77, 128, 3]
+    N = sum(chunks)
+    B = 23
+    x = fx.synthetic_batch(B, N, seed=41)
+    ref = _oracle_batch(nam, x, True)
+    d = _spec(nam, B, True)
+    d.Reset(48000.0, 1024)
+    out, pos = [], 0
+    n0 = d.launch_count()
+    for n in chunks:
+        out.append(d.process_batch(np.ascontiguousarray(x[:, pos:pos + n])))
+        pos += n
+    assert d.launch_count() == n0 + len(chunks)
+    d.close()
+    scale = max(1.0, float(np.max(np.abs(ref))))
+    err = float(np.max(np.abs(np.concatenate(out, axis=1) - ref)))
+    assert err <= TOL * scale, f"max-abs {err:.3e}"
+
+
 def test_reserved_sms_change_the_grid_not_the_result():
     """nam_b200_set_reserved_sms: the persistent kernels walk the streams with fewer CTAs; same outputs bit for bit, and the
     setting can change between calls on live rings."""
