@@ -409,7 +409,18 @@ size_t lat_smem_bytes(const WaveNetPlan& plan, int frames)
 SpecBuild build_lat_kernel(const WaveNetPlan& plan, int frame_warps)
 {
   SpecBuild r;
-  r.geom.nt = 128 * frame_warps;
+  // 8 channel groups when every array's (padded) width divides by 8: twice the instruction streams of half the length
+  // (wavenet_lat.cuh); $NAM_B200_LAT_GROUPS=4 keeps the 4-group form (A/B)
+  int groups = 8;
+  for (int a = 0; a < plan.n_arrays; a++)
+    if (plan.cp[a] % 8 != 0)
+      groups = 4;
+  if (const char* e = std::getenv("NAM_B200_LAT_GROUPS"))
+    if (std::atoi(e) == 4)
+      groups = 4;
+  if (32 * groups * frame_warps > 1024)
+    groups = 4;
+  r.geom.nt = 32 * groups * frame_warps;
   r.geom.s = 1;
   r.geom.min_ctas = 1;
   SpecGeometry tiny; // eligibility of the family (heads, finiteness); the throughput kernel's shared-memory rule does not apply
@@ -439,7 +450,8 @@ SpecBuild build_lat_kernel(const WaveNetPlan& plan, int frame_warps)
     return r;
   }
   const CompiledKernel ck = compile_or_fetch("wavenet_lat", spec_header_source(plan), "wavenet_lat.cuh", kLatKernelSource,
-                                             "NAM_B200_LAT_SOURCE", {"-DNAMB200_LAT_FW=" + std::to_string(frame_warps)},
+                                             "NAM_B200_LAT_SOURCE",
+                                             {"-DNAMB200_LAT_FW=" + std::to_string(frame_warps), "-DNAMB200_LAT_GROUPS=" + std::to_string(groups)},
                                              {{"wavenet_spec.cuh", kSpecKernelSource}});
   r.ok = ck.ok;
   r.why_not = ck.why_not;

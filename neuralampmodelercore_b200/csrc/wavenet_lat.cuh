@@ -19,7 +19,7 @@
 //   * no shared-memory weights to load at kernel start (55 KB per call for the precompiled kernel).
 // Same rings, same arithmetic order per output as wavenet_fused.cuh / wavenet_spec.cuh, so calls can be mixed.
 //
-// Geometry: one CTA per stream, FW frame warps (frames per call <= 32 FW), 4 channel groups: 128 FW threads.
+// Geometry: one CTA per stream, FW frame warps (frames per call <= 32 FW), 4 or 8 channel groups: 128 FW / 256 FW threads.
 #pragma once
 
 #ifndef NAMB200_SPEC_HEADER_INCLUDED
@@ -33,7 +33,14 @@ namespace namb200_lat
 {
 using namespace namb200_spec;
 
-constexpr int kGroups = 4; // channel groups
+#ifndef NAMB200_LAT_GROUPS
+#define NAMB200_LAT_GROUPS 4
+#endif
+// Channel groups.  Each group is its own instruction stream, and streaming straight-line code from L2 is what bounds this
+// kernel: one SM fetches ~10.6 B / cycle for 4 distinct streams but ~17.5 B / cycle for 8 (tools/ifetch_probe,
+// profiles/r02x_ifetch_probe.jsonl), so 8 groups of half-size streams finish sooner than 4.
+constexpr int kGroups = NAMB200_LAT_GROUPS;
+static_assert(kGroups == 4 || kGroups == 8, "4 or 8 channel groups");
 
 struct LatParams
 {
@@ -120,7 +127,7 @@ __device__ __forceinline__ void store_slice(float4* planes, const int F, const i
   else if constexpr (CO == 2)
     reinterpret_cast<float2*>(planes + (g >> 1) * F + f)[g & 1] = make_float2(v[0], v[1]);
   else
-    reinterpret_cast<float*>(planes + 0 * F + f)[g] = v[0];
+    reinterpret_cast<float*>(planes + (g >> 2) * F + f)[g & 3] = v[0];
 }
 template <int CO>
 __device__ __forceinline__ void load_slice(const float4* planes, const int F, const int g, const int f, float (&v)[CO])
@@ -136,7 +143,7 @@ __device__ __forceinline__ void load_slice(const float4* planes, const int F, co
     v[0] = q.x, v[1] = q.y;
   }
   else
-    v[0] = reinterpret_cast<const float*>(planes + 0 * F + f)[g];
+    v[0] = reinterpret_cast<const float*>(planes + (g >> 2) * F + f)[g & 3];
 }
 // all C channels of frame f
 template <int C>
@@ -401,14 +408,11 @@ __device__ __forceinline__ void wavenet_lat_body(const LatParams& p)
   const float x = (c.f < c.n) ? p.in[(size_t)stream * p.in_stride + c.f] : 0.0f;
   float* yout = p.out + (size_t)stream * p.out_stride;
   // each channel group runs its own copy of the network: its weights are its own immediates
-  if (g == 0)
-    network_lat<0, F, NTH>(c, p, x, yout, 0);
-  else if (g == 1)
-    network_lat<1, F, NTH>(c, p, x, yout, 0);
-  else if (g == 2)
-    network_lat<2, F, NTH>(c, p, x, yout, 0);
-  else
-    network_lat<3, F, NTH>(c, p, x, yout, 0);
+  static_for<0, kGroups>([&](auto g_c) {
+    constexpr int G = decltype(g_c)::value;
+    if (g == G)
+      network_lat<G, F, NTH>(c, p, x, yout, 0);
+  });
   if (p.done_flag != nullptr)
   {
     __threadfence_system(); // my outputs (mapped host memory) before the doorbell
@@ -427,7 +431,7 @@ __device__ __forceinline__ void wavenet_lat_body(const LatParams& p)
 #define NAMB200_LAT_FW 2
 #endif
 
-extern "C" __global__ void __launch_bounds__(128 * NAMB200_LAT_FW, 1)
+extern "C" __global__ void __launch_bounds__(32 * NAMB200_LAT_GROUPS * NAMB200_LAT_FW, 1)
   wavenet_lat_kernel(const __grid_constant__ namb200_lat::LatParams p)
 {
   namb200_lat::wavenet_lat_body<NAMB200_LAT_FW>(p);
