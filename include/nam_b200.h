@@ -161,6 +161,11 @@ int nam_b200_multi_process_f32(nam_b200_multi* mm, const float* in, float* out, 
 int nam_b200_process_f64_planar(nam_b200_model* m, const double* const* input, double* const* output, int n_frames);
 int nam_b200_process_f32_planar(nam_b200_model* m, const float* const* input, float* const* output, int n_frames);
 
+/* 1 when the library was built with the tcgen05 / TMEM WaveNet kernel (options.kernel_geometry = 3; a build option,
+ * NAM_B200_BUILD_TC=1: validated to the same 1e-5 but slower than the FP32 kernels on the reference's model families), else 0:
+ * creating a handle with kernel_geometry = 3 then fails with NAM_B200_ERR_UNSUPPORTED. */
+int nam_b200_has_tensor_core_kernel(void);
+
 /* The persistent WaveNet throughput kernels occupy every SM for a whole call, so a concurrent kernel on another stream (an NCCL
  * collective gathering the previous call's outputs, say) only starts when they drain.  Leaving `n_sms` SMs free (0 = none,
  * the default) lets such work overlap the call.  The price is

@@ -16,6 +16,7 @@ from .dsp import (  # noqa: F401
     inspect,
     jit_prepare,
     measure_fp32_tflops,
+    has_tensor_core_kernel,
     submodels,
     using_fast_tanh,
 )
@@ -32,6 +33,7 @@ __all__ = [
     "disable_fast_tanh",
     "using_fast_tanh",
     "measure_fp32_tflops",
+    "has_tensor_core_kernel",
     "NamFileValidationError",
     "UnsupportedModelError",
     "CudaUnavailableError",

@@ -17,7 +17,18 @@ LIB_PATH = LIB_DIR / "libnam_b200.so"
 INCLUDE = PKG.parent / "include"
 
 SOURCES = ["nam_b200.cu", "nam_model_spec.cpp", "json_lite.cpp", "wavenet_pack.cpp", "generic_pack.cpp", "nam_dsp_shim.cpp",
-           "jit_spec.cpp"]
+           "jit_spec.cpp", "wavenet_tc_launch.cu"]
+
+
+def with_tc() -> bool:
+    """Build option: NAM_B200_BUILD_TC=1 compiles the tensor-core WaveNet kernel (wavenet_tc.cuh) into the library; the default
+    build carries stubs (validated, slower than the FP32 kernels on the reference's model families)."""
+    return os.environ.get("NAM_B200_BUILD_TC", "0").strip().lower() in ("1", "true", "yes", "on")
+
+
+def _obj_name(src: Path) -> str:
+    # the option is part of the object's name, so switching it recompiles / relinks the right one
+    return src.name + (".tc1.o" if src.name == "wavenet_tc_launch.cu" and with_tc() else ".o")
 
 NVCC_FLAGS = [
     "-gencode",
@@ -42,8 +53,15 @@ def sources() -> list[Path]:
     return [CSRC / s for s in SOURCES if (CSRC / s).exists()]
 
 
+def _options_stamp() -> str:
+    return f"tc={int(with_tc())}\n"
+
+
 def _stale() -> bool:
     if not LIB_PATH.exists():
+        return True
+    stamp = LIB_DIR / "build_options.txt"
+    if not stamp.exists() or stamp.read_text() != _options_stamp():
         return True
     t = LIB_PATH.stat().st_mtime
     deps = list(CSRC.glob("*")) + list(INCLUDE.rglob("*.h"))
@@ -75,6 +93,8 @@ def _embed(stem: str, ext: str = ".cuh") -> Path:
 
 def _compile_object(src: Path, obj: Path, verbose: bool) -> str:
     cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f != "-shared"], f"-I{INCLUDE}", "-c", "-o", str(obj), str(src)]
+    if src.name == "wavenet_tc_launch.cu" and with_tc():
+        cmd.insert(1, "-DNAM_B200_WITH_TC=1")
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
@@ -110,7 +130,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     jobs = []
     for src in sources():
-        obj = obj_dir / (src.name + ".o")
+        obj = obj_dir / _obj_name(src)
         deps = [src, *closure(src, set())]
         if force or not obj.exists() or any(d.stat().st_mtime > obj.stat().st_mtime for d in deps):
             jobs.append((src, obj))
@@ -118,11 +138,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         logs = list(ex.map(lambda j: _compile_object(j[0], j[1], verbose), jobs))
     tmp = LIB_DIR / "libnam_b200.so.tmp"
     cmd = [_nvcc(), "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp),
-           *[str(obj_dir / (s.name + ".o")) for s in sources()], "-ldl"]
+           *[str(obj_dir / _obj_name(s)) for s in sources()], "-ldl"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     os.replace(tmp, LIB_PATH)
+    (LIB_DIR / "build_options.txt").write_text(_options_stamp())
     if verbose:
         print("\n".join(logs))
     return LIB_PATH

@@ -69,6 +69,7 @@ EXPORTED_SYMBOLS = [
     "nam_b200_process_f32_planar",
     "nam_b200_set_fast_tanh",
     "nam_b200_set_reserved_sms",
+    "nam_b200_has_tensor_core_kernel",
     "nam_b200_set_slimmable_size",
     "nam_b200_slimmable_breakpoints",
     "nam_b200_synchronize",
@@ -164,6 +165,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.nam_b200_multi_process_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64]
     lib.nam_b200_measure_fp32_tflops.argtypes = [C.c_int, C.c_int]
     lib.nam_b200_measure_fp32_tflops.restype = C.c_double
+    lib.nam_b200_has_tensor_core_kernel.argtypes = []
+    lib.nam_b200_has_tensor_core_kernel.restype = C.c_int
     for name in (
         "nam_b200_create_from_file",
         "nam_b200_create_from_json",

@@ -21,7 +21,7 @@
 #include "wavenet_fused.cuh"
 #include "wavenet_lat2.cuh"
 #include "wavenet_pack.h"
-#include "wavenet_tc.cuh"
+#include "wavenet_tc_launch.h"
 #include "generic_pack.h"
 #include "wavenet_generic.cuh"
 #include "jit_spec.h"
@@ -837,59 +837,6 @@ size_t wavenet_smem_bytes(const WaveNetPlan& plan, int geom)
 }
 
 // ---- tensor-core variant dispatch ---------------------------------------------------------------
-size_t tc_smem_bytes(const WaveNetPlan& plan)
-{
-  const int cmax = std::max(plan.cp[0], plan.cp[1]);
-  const size_t pm = cmax / 4;
-  const size_t wimg4 = (size_t)(plan.tc_max_image_floats + 3) / 4;
-  return (2 * wimg4 + 2 * pm * kTcTW + 4 * pm * kTcM) * 16;
-}
-
-template <int C0, int C1>
-void launch_tc_variant(nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem, cudaStream_t st)
-{
-  auto kern = wavenet_tc_kernel<C0, C1>;
-  // the kernel also has a few bytes of static shared memory (mbarriers), so ask for what is needed, not the maximum
-  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  kern<<<grid, kTcThreads, smem, st>>>(kp, (int)((m->plan.tc_max_image_floats + 3) / 4), (int)m->plan.layers.size());
-  CUDA_CHECK(cudaGetLastError());
-}
-
-template <int C0, int C1>
-int occupancy_tc_variant(size_t smem)
-{
-  auto kern = wavenet_tc_kernel<C0, C1>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  // shared memory decides (227 KB per SM, 1 KB reserved per CTA); registers allow 3 (launch bounds)
-  const int by_smem = (int)((227 * 1024) / (smem + 1024 + 64));
-  return std::max(1, std::min(3, by_smem));
-}
-
-#define TC_DISPATCH(FN, ...)                                                                                         \
-  switch (c0 * 100 + c1)                                                                                             \
-  {                                                                                                                  \
-    case 800: return FN<8, 0>(__VA_ARGS__);                                                                          \
-    case 1600: return FN<16, 0>(__VA_ARGS__);                                                                        \
-    case 808: return FN<8, 8>(__VA_ARGS__);                                                                          \
-    case 816: return FN<8, 16>(__VA_ARGS__);                                                                         \
-    case 1608: return FN<16, 8>(__VA_ARGS__);                                                                        \
-    case 1616: return FN<16, 16>(__VA_ARGS__);                                                                       \
-    default: throw std::runtime_error("no tensor-core WaveNet kernel for channel pair " + std::to_string(c0) + "/"   \
-                                      + std::to_string(c1));                                                         \
-  }
-
-void launch_tc_dispatch(int c0, int c1, nam_b200_model* m, const WaveNetKernelParams& kp, int grid, size_t smem,
-                        cudaStream_t st)
-{
-  TC_DISPATCH(launch_tc_variant, m, kp, grid, smem, st)
-}
-int occupancy_tc_dispatch(int c0, int c1, size_t smem)
-{
-  TC_DISPATCH(occupancy_tc_variant, smem)
-}
-
 // `stream0`: index of the handle's stream that d_in / d_out row 0 belongs to (chunked host calls)
 // ---- model-specialised kernel (wavenet_spec.cuh, compiled per model by jit_spec.cpp) ----------------------------------
 // Mirror of namb200_spec::SpecParams (wavenet_spec.cuh): the kernel's single by-value parameter.
@@ -1204,11 +1151,11 @@ void launch_wavenet(nam_b200_model* m, const float* d_in, float* d_out, int batc
     }
     const size_t smem_tc = tc_smem_bytes(plan);
     if (m->wn_ctas_per_sm <= 0)
-      m->wn_ctas_per_sm = m->opts.ctas_per_sm > 0 ? m->opts.ctas_per_sm : occupancy_tc_dispatch(c0, c1, smem_tc);
+      m->wn_ctas_per_sm = m->opts.ctas_per_sm > 0 ? m->opts.ctas_per_sm : tc_occupancy(c0, c1, smem_tc);
     int grid_tc = std::min(batch, m->wn_ctas_per_sm * m->sm_count);
     if (grid_tc < 1)
       grid_tc = 1;
-    launch_tc_dispatch(c0, c1, m, kp, grid_tc, smem_tc, st);
+    tc_launch(c0, c1, kp, (int)((plan.tc_max_image_floats + 3) / 4), (int)plan.layers.size(), grid_tc, smem_tc, st);
     m->launches++;
     return;
   }
@@ -1837,6 +1784,10 @@ int create_common(ModelSpec&& spec, const nam_b200_options* user_opts, nam_b200_
         // option: 0 default, 1 = FFMA 128-thread, 2 = FFMA 256-thread, 3 = tensor-core (tcgen05)
         if (m->opts.kernel_geometry == 3)
         {
+          if (!tc_built())
+            return fail(NAM_B200_ERR_UNSUPPORTED,
+                        "tensor-core kernel: this library was built without it (rebuild with NAM_B200_BUILD_TC=1; it is slower "
+                        "than the FP32 kernels on 8/16-channel models, DESIGN.md section 2.2)");
           if (!m->plan.tc_eligible)
             return fail(NAM_B200_ERR_UNSUPPORTED, "tensor-core kernel not available for this model: " + m->plan.tc_why_not);
           m->wn_geometry = 2;
@@ -2724,6 +2675,11 @@ int nam_b200_process_f32_planar(nam_b200_model* m, const float* const* input, fl
 int nam_b200_process_f64_planar(nam_b200_model* m, const double* const* input, double* const* output, int n_frames)
 {
   return process_planar<double>(m, input, output, n_frames);
+}
+
+int nam_b200_has_tensor_core_kernel(void)
+{
+  return tc_built() ? 1 : 0;
 }
 
 int nam_b200_set_reserved_sms(nam_b200_model* m, int n_sms)

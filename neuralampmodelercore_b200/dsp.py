@@ -419,6 +419,11 @@ def submodels(config) -> list:
     return out
 
 
+def has_tensor_core_kernel() -> bool:
+    """Was libnam_b200.so built with the tcgen05 / TMEM WaveNet kernel (NAM_B200_BUILD_TC=1; kernel_geometry=3)?"""
+    return bool(_capi.load().nam_b200_has_tensor_core_kernel())
+
+
 def measure_fp32_tflops(device: int = -1, packed: bool = True) -> float:
     """Measured FP32 FMA throughput of the device (the compute roofline of the fused kernel)."""
     return float(_capi.load().nam_b200_measure_fp32_tflops(int(device), int(packed)))

@@ -377,3 +377,13 @@ def test_reserved_sms_change_the_grid_not_the_result():
     with pytest.raises(Exception):
         d.set_reserved_sms(-1)
     d.close()
+
+
+def test_tensor_core_kernel_is_a_build_option_and_refused_loudly_without_it():
+    nam = fx.load_model("wavenet_a1_standard")
+    if nb.has_tensor_core_kernel():
+        d = nb.get_dsp(nam, batch=2, kernel_geometry=3)
+        d.close()
+        return
+    with pytest.raises(Exception, match="built without"):
+        nb.get_dsp(nam, batch=2, kernel_geometry=3)
