@@ -489,7 +489,7 @@ def run_b200(args) -> None:
         gather = {"ms_per_step": gms, "bytes_per_rank": int(y_dev.numel() * 4),
                   "busbw_GBs": y_dev.numel() * 4 * (world - 1) / (gms * 1e-3) / 1e9,
                   "step_ms_with_gather_overlapped": with_ms, "step_ms_without": total_ms_max / args.steps,
-                  "hidden_fraction": max(0.0, 1.0 - (with_ms - total_ms_max / args.steps) / gms) if gms > 0 else None,
+                  "hidden_fraction": min(1.0, max(0.0, 1.0 - (with_ms - total_ms_max / args.steps) / gms)) if gms > 0 else None,
                   "reserved_sms": 0,
                   "what": "ncclAllGather (torch.distributed all_gather_into_tensor) of each rank's outputs on a side "
                           "stream, overlapped with the next steps' kernels (three output buffers; it runs on the SMs the last, "
