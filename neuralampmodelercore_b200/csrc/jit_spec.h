@@ -31,6 +31,7 @@ struct SpecBuild
   bool ok = false;
   std::string why_not; // !ok: the reason (not eligible / NVRTC missing / compile error + log)
   std::vector<char> cubin;
+  std::vector<char> cubin_extra; // second program of the model (128- / 256-frame short-call entry points), may be empty
   SpecGeometry geom;
   int staged_cols = 0; // spec::LS: columns of history staged in front of the tile (max look-back of the model)
   int max_planes = 0; // widest array, in planes of 4 channels

@@ -386,6 +386,7 @@ struct nam_b200_model
   float* d_tc_blob = nullptr; // per-layer B-operand images of the tensor-core kernel
   // model-specialised kernel (wavenet_spec.cuh compiled for this model by NVRTC, jit_spec.cpp): the throughput path
   cudaLibrary_t spec_lib = nullptr;
+  cudaLibrary_t spec_lib_extra = nullptr; // second program of the model: the 128- / 256-frame short-call entry points
   cudaKernel_t spec_kernel = nullptr;
   struct SpecShort // its short-call entry points (q streams x fq frames per CTA; fq = 64, 128, 256), may be absent
   {
@@ -455,6 +456,8 @@ struct nam_b200_model
       cudaFree(d_glayers);
     if (spec_lib)
       cudaLibraryUnload(spec_lib);
+    if (spec_lib_extra)
+      cudaLibraryUnload(spec_lib_extra);
     if (lat_lib)
       cudaLibraryUnload(lat_lib);
     if (d_tile_flags)
@@ -934,11 +937,15 @@ void setup_spec_kernel(nam_b200_model* m)
     {
       const char* const names[3] = {"wavenet_spec_short_kernel", "wavenet_spec_short128_kernel", "wavenet_spec_short256_kernel"};
       const int fqs[3] = {64, 128, 256}, qs[3] = {b.geom.short_streams, b.geom.short128_streams, b.geom.short256_streams};
+      if (!b.cubin_extra.empty()
+          && cudaLibraryLoadData(&m->spec_lib_extra, b.cubin_extra.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess)
+        m->spec_lib_extra = nullptr;
       for (int v = 0; v < 3; v++)
       {
         nam_b200_model::SpecShort& sv = m->spec_short[v];
         sv = nam_b200_model::SpecShort{};
-        if (cudaLibraryGetKernel(&sv.kernel, m->spec_lib, names[v]) != cudaSuccess)
+        cudaLibrary_t lib = (v == 0) ? m->spec_lib : m->spec_lib_extra;
+        if (lib == nullptr || cudaLibraryGetKernel(&sv.kernel, lib, names[v]) != cudaSuccess)
         {
           sv.kernel = nullptr;
           continue;
@@ -961,7 +968,11 @@ void setup_spec_kernel(nam_b200_model* m)
   {
     if (m->spec_lib)
       cudaLibraryUnload(m->spec_lib);
-    m->spec_lib = nullptr;
+    if (m->spec_lib_extra)
+      cudaLibraryUnload(m->spec_lib_extra);
+    m->spec_lib = m->spec_lib_extra = nullptr;
+    for (auto& sv : m->spec_short)
+      sv = nam_b200_model::SpecShort{};
     m->spec_kernel = nullptr;
     m->spec_state = -1;
     m->spec_note = ex.what();
@@ -2239,7 +2250,7 @@ int nam_b200_jit_prepare_json_for_batch(const char* nam_json_text, int fast_tanh
                   "{\"ok\": %s, \"from_cache\": %s, \"compile_seconds\": %.3f, \"cubin_bytes\": %zu, \"threads\": %d, "
                   "\"frames_per_thread\": %d, \"smem_bytes\": %zu, \"why_not\": \"%s\", \"lat_ok\": %s, "
                   "\"lat_compile_seconds\": %.3f, \"lat_cubin_bytes\": %zu}",
-                  b.ok ? "true" : "false", b.from_cache ? "true" : "false", b.compile_seconds, b.cubin.size(), b.geom.nt,
+                  b.ok ? "true" : "false", b.from_cache ? "true" : "false", b.compile_seconds, b.cubin.size() + b.cubin_extra.size(), b.geom.nt,
                   b.geom.s, b.ok ? b.smem_bytes() : (size_t)0, why.c_str(), lat.ok ? "true" : "false", lat.compile_seconds,
                   lat.cubin.size());
     if (out && capacity > 0)

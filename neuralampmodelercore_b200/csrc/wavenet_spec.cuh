@@ -1063,12 +1063,16 @@ __device__ __forceinline__ void wavenet_spec_short_body(const SpecParams& p)
 #define NAMB200_SPEC_MINB 2
 #endif
 
+// (the entry points are compiled as two NVRTC programs side by side -- jit_spec.cpp: this one and the 64-frame short-call
+// variant in the first, the 128- / 256-frame variants in the second, NAMB200_SPEC_ONLY_EXTRA_SHORT)
+#ifndef NAMB200_SPEC_ONLY_EXTRA_SHORT
 extern "C" __global__ void __launch_bounds__(NAMB200_SPEC_NT, NAMB200_SPEC_MINB)
   wavenet_spec_kernel(const __grid_constant__ namb200_spec::SpecParams p)
 {
   namb200_spec::wavenet_spec_body<NAMB200_SPEC_NT, NAMB200_SPEC_S, NAMB200_SPEC_MINB>(p);
 }
-#ifdef NAMB200_SPEC_SHORT_FQ
+#endif
+#if defined(NAMB200_SPEC_SHORT_FQ) && !defined(NAMB200_SPEC_ONLY_EXTRA_SHORT)
 // short-call variant: NAMB200_SPEC_SHORT_NT / NAMB200_SPEC_SHORT_FQ streams per CTA, calls of up to NAMB200_SPEC_SHORT_FQ frames
 #ifndef NAMB200_SPEC_SHORT_NT
 #define NAMB200_SPEC_SHORT_NT NAMB200_SPEC_NT

@@ -268,9 +268,16 @@ def test_jit_compiles_without_a_gpu_and_the_sass_is_what_design_md_says(tmp_path
     rep = nb.jit_prepare(nam, fast_tanh=True)
     assert rep["ok"] and not rep["from_cache"], rep
     assert nb.jit_prepare(nam, fast_tanh=True)["from_cache"]  # second time: the disk cache
-    cubins = sorted(tmp_path.glob("wavenet_spec_*.cubin"))
-    assert len(cubins) == 1
+    # two programs per model, compiled side by side: the throughput kernel + 64-frame short-call variant, and the 128- /
+    # 256-frame variants (wavenet_spec_x_*)
+    cubins = sorted(p for p in tmp_path.glob("wavenet_spec_*.cubin") if not p.name.startswith("wavenet_spec_x_"))
+    extra = sorted(tmp_path.glob("wavenet_spec_x_*.cubin"))
+    assert len(cubins) == 1 and len(extra) == 1
+    names = subprocess.run(["cuobjdump", "-sass", str(extra[0])], capture_output=True, text=True, check=True).stdout
+    assert "wavenet_spec_short128_kernel" in names and "wavenet_spec_short256_kernel" in names
+    assert "Function : wavenet_spec_kernel" not in names
     sass = subprocess.run(["cuobjdump", "-sass", str(cubins[0])], capture_output=True, text=True, check=True).stdout
+    assert "wavenet_spec_short_kernel" in sass
     body = sass.split("Function : wavenet_spec_kernel")[1].split("Function :")[0]
     n_weights = len(nam["weights"]) - 1  # (the last one is head_scale)
     imm = len(re.findall(r"FFMA R\d+, R\d+(?:\.reuse)?, -?[0-9]", body))
